@@ -1,0 +1,260 @@
+"""ctypes binding of the CPU oracle (oracle/libgsm_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs. The product package (gsm_renderer_b200) never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgsm_oracle.so")
+
+F32, F16 = 0, 1
+
+RENDER_DATA_DTYPE = np.dtype(
+    [("meanX", "<f2"), ("meanY", "<f2"), ("theta", "<u2"), ("sigma1", "<f2"), ("sigma2", "<f2"),
+     ("depth", "<f2"), ("colorR", "u1"), ("colorG", "u1"), ("colorB", "u1"), ("opacity", "u1")]
+)
+STEREO_RENDER_DATA_DTYPE = np.dtype(
+    [("leftMeanX", "<f2"), ("leftMeanY", "<f2"), ("leftCxx", "<f2"), ("leftCyy", "<f2"),
+     ("leftCxy2", "<f2"), ("leftDepth", "<f2"),
+     ("rightMeanX", "<f2"), ("rightMeanY", "<f2"), ("rightCxx", "<f2"), ("rightCyy", "<f2"),
+     ("rightCxy2", "<f2"), ("rightDepth", "<f2"),
+     ("colorR", "u1"), ("colorG", "u1"), ("colorB", "u1"), ("opacity", "u1"),
+     ("centerDepth", "<f2"), ("_pad0", "<u2")]
+)
+assert RENDER_DATA_DTYPE.itemsize == 16 and STEREO_RENDER_DATA_DTYPE.itemsize == 32
+
+
+class Camera(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("center", C.c_float * 3),
+                ("width", C.c_float), ("height", C.c_float), ("nearPlane", C.c_float),
+                ("farPlane", C.c_float), ("shComponents", C.c_uint32), ("gaussianCount", C.c_uint32),
+                ("inputIsSRGB", C.c_float)]
+
+
+class StereoCamera(C.Structure):
+    _fields_ = [("leftView", C.c_float * 16), ("leftProj", C.c_float * 16), ("leftCenter", C.c_float * 3),
+                ("rightView", C.c_float * 16), ("rightProj", C.c_float * 16), ("rightCenter", C.c_float * 3),
+                ("width", C.c_float), ("height", C.c_float), ("nearPlane", C.c_float),
+                ("farPlane", C.c_float), ("shComponents", C.c_uint32), ("gaussianCount", C.c_uint32),
+                ("inputIsSRGB", C.c_float), ("sceneTransform", C.c_float * 16)]
+
+
+class Binning(C.Structure):
+    _fields_ = [("tilesX", C.c_uint32), ("tilesY", C.c_uint32), ("tileWidth", C.c_uint32),
+                ("tileHeight", C.c_uint32), ("alphaThreshold", C.c_float),
+                ("totalInkThreshold", C.c_float)]
+
+
+class DFHeader(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("visibleCount", "totalInstances", "paddedVisibleCount",
+                                          "paddedInstanceCount", "overflow", "padding0", "padding1",
+                                          "padding2")]
+
+
+class Frame(C.Structure):
+    _fields_ = [("maxGaussians", C.c_uint32), ("maxInstances", C.c_uint32),
+                ("depthKey16", C.c_int), ("tileId16", C.c_int),
+                ("renderData", C.c_void_p), ("bounds", C.c_void_p), ("nTouched", C.c_void_p),
+                ("preDepthKeys", C.c_void_p), ("depthKeys", C.c_void_p),
+                ("primitiveIndices", C.c_void_p), ("orderedTileCounts", C.c_void_p),
+                ("instanceTileIds", C.c_void_p), ("instanceGaussianIndices", C.c_void_p),
+                ("tileHeaders", C.c_void_p), ("activeTiles", C.c_void_p),
+                ("header", DFHeader), ("activeTileCount", C.c_uint32),
+                ("rawVisibleCount", C.c_uint32), ("rawTotalInstances", C.c_uint32),
+                ("stageSeconds", C.c_double * 10)]
+
+
+STAGE_NAMES = ("project", "compact", "depthSort", "applyScan", "expand", "tileSort", "ranges",
+               "clearBlend", "copy", "total")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with oracle/Makefile (gcc). Building the checker is not using it."""
+    src = [os.path.join(_HERE, f) for f in ("gsm_oracle.c", "gsm_oracle.h", "gsmo_math.h", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.gsmo_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def binning_for(width: int, height: int) -> Binning:
+    return Binning((width + 15) // 16, (height + 15) // 16, 16, 16, 0.005, 2.0)
+
+
+def make_camera(view, proj, center, width, height, near, far, sh_components, count, srgb) -> Camera:
+    cam = Camera()
+    cam.view[:] = np.asarray(view, np.float32).reshape(16).tolist()
+    cam.proj[:] = np.asarray(proj, np.float32).reshape(16).tolist()
+    cam.center[:] = np.asarray(center, np.float32).reshape(3).tolist()
+    cam.width, cam.height = float(width), float(height)
+    cam.nearPlane, cam.farPlane = float(near), float(far)
+    cam.shComponents, cam.gaussianCount = int(sh_components), int(count)
+    cam.inputIsSRGB = 1.0 if srgb else 0.0
+    return cam
+
+
+def make_stereo_camera(lview, lproj, lcenter, rview, rproj, rcenter, width, height, near, far,
+                       sh_components, count, srgb, scene=None) -> StereoCamera:
+    cam = StereoCamera()
+    cam.leftView[:] = np.asarray(lview, np.float32).reshape(16).tolist()
+    cam.leftProj[:] = np.asarray(lproj, np.float32).reshape(16).tolist()
+    cam.leftCenter[:] = np.asarray(lcenter, np.float32).reshape(3).tolist()
+    cam.rightView[:] = np.asarray(rview, np.float32).reshape(16).tolist()
+    cam.rightProj[:] = np.asarray(rproj, np.float32).reshape(16).tolist()
+    cam.rightCenter[:] = np.asarray(rcenter, np.float32).reshape(3).tolist()
+    cam.width, cam.height = float(width), float(height)
+    cam.nearPlane, cam.farPlane = float(near), float(far)
+    cam.shComponents, cam.gaussianCount = int(sh_components), int(count)
+    cam.inputIsSRGB = 1.0 if srgb else 0.0
+    scene = np.eye(4, dtype=np.float32) if scene is None else np.asarray(scene, np.float32)
+    cam.sceneTransform[:] = scene.reshape(16).tolist()
+    return cam
+
+
+# ------------------------------------------------------------------ math probes
+def probe_sincos(x):
+    x = np.ascontiguousarray(x, np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().gsmo_probe_sincos(_p(x), _p(s), _p(c), C.c_int(x.size))
+    return s, c
+
+
+def probe_log(x):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty_like(x)
+    lib().gsmo_probe_log(_p(x), _p(y), C.c_int(x.size))
+    return y
+
+
+def probe_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    r = np.empty_like(x)
+    lib().gsmo_probe_atan2(_p(y), _p(x), _p(r), C.c_int(x.size))
+    return r
+
+
+def probe_powr(x, yexp):
+    x = np.ascontiguousarray(x, np.float32)
+    r = np.empty_like(x)
+    lib().gsmo_probe_powr(_p(x), C.c_float(yexp), _p(r), C.c_int(x.size))
+    return r
+
+
+def probe_hexp(xbits):
+    x = np.ascontiguousarray(xbits, np.uint16)
+    y = np.empty_like(x)
+    lib().gsmo_probe_hexp(_p(x), _p(y), C.c_int(x.size))
+    return y
+
+
+def probe_f2h(x):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty(x.shape, np.uint16)
+    lib().gsmo_probe_f2h(_p(x), _p(y), C.c_int(x.size))
+    return y
+
+
+# ------------------------------------------------------------------ stages
+def sort_pairs_u32(keys, payload, passes=4):
+    keys = np.ascontiguousarray(keys, np.uint32).copy()
+    payload = np.ascontiguousarray(payload, np.int32).copy()
+    lib().gsmo_sort_pairs_u32(_p(keys), _p(payload), C.c_uint32(keys.size), C.c_int(passes))
+    return keys, payload
+
+
+def sort_pairs_u16(keys, payload, passes=2):
+    keys = np.ascontiguousarray(keys, np.uint16).copy()
+    payload = np.ascontiguousarray(payload, np.int32).copy()
+    lib().gsmo_sort_pairs_u16(_p(keys), _p(payload), C.c_uint32(keys.size), C.c_int(passes))
+    return keys, payload
+
+
+def exclusive_scan(x):
+    x = np.ascontiguousarray(x, np.uint32)
+    y = np.empty_like(x)
+    lib().gsmo_exclusive_scan(_p(x), C.c_uint32(x.size), _p(y))
+    return y
+
+
+def tile_sort_passes(tile_count: int) -> int:
+    return int(lib().gsmo_tile_sort_passes(C.c_uint32(tile_count)))
+
+
+class OracleFrame:
+    """Runs a whole frame through the oracle and keeps every intermediate as numpy arrays."""
+
+    def __init__(self, max_gaussians: int, max_width: int, max_height: int, stereo: bool = False,
+                 depth_key16: bool = False, tile_id16: bool = True):
+        G = int(max_gaussians)
+        self.G, self.I = G, 4 * G
+        self.stereo = stereo
+        T = ((max_width + 15) // 16) * ((max_height + 15) // 16)
+        self.renderData = np.zeros(G, STEREO_RENDER_DATA_DTYPE if stereo else RENDER_DATA_DTYPE)
+        self.bounds = np.zeros((G, 4), np.int32)
+        self.nTouched = np.zeros(G, np.uint32)
+        self.preDepthKeys = np.zeros(G, np.uint32)
+        self.depthKeys = np.zeros(G, np.uint32)
+        self.primitiveIndices = np.zeros(G, np.int32)
+        self.orderedTileCounts = np.zeros(G, np.uint32)
+        self.instanceTileIds = np.zeros(self.I, np.uint16 if tile_id16 else np.uint32)
+        self.instanceGaussianIndices = np.zeros(self.I, np.int32)
+        self.tileHeaders = np.zeros((max(T, 1), 2), np.uint32)
+        self.activeTiles = np.zeros(max(T, 1), np.uint32)
+        f = Frame()
+        f.maxGaussians, f.maxInstances = G, 4 * G
+        f.depthKey16, f.tileId16 = int(depth_key16), int(tile_id16)
+        for name in ("renderData", "bounds", "nTouched", "preDepthKeys", "depthKeys", "primitiveIndices",
+                     "orderedTileCounts", "instanceTileIds", "instanceGaussianIndices", "tileHeaders",
+                     "activeTiles"):
+            setattr(f, name, getattr(self, name).ctypes.data)
+        self.f = f
+
+    @property
+    def header(self):
+        return self.f.header
+
+    @property
+    def stage_seconds(self):
+        return dict(zip(STAGE_NAMES, list(self.f.stageSeconds)))
+
+    def render_mono(self, gaussians, harmonics, precision, cam: Camera, width, height, want_depth=True):
+        color = np.full((height, width, 4), 0x7E00, np.uint16)  # NaN pattern: "untouched"
+        depth = np.full((height, width), 0x7E00, np.uint16) if want_depth else None
+        lib().gsmo_render_mono(C.byref(self.f), _p(gaussians), _p(harmonics), C.c_int(precision),
+                               C.byref(cam), C.c_uint32(width), C.c_uint32(height), _p(color), _p(depth))
+        return color, depth
+
+    def render_stereo(self, gaussians, harmonics, precision, cam: StereoCamera, width, height, flip_y=True):
+        scratch = np.zeros((2, height, width, 4), np.uint16)
+        dst = np.full((height, 2 * width, 4), 0x7E00, np.uint16)
+        lib().gsmo_render_stereo(C.byref(self.f), _p(gaussians), _p(harmonics), C.c_int(precision),
+                                 C.byref(cam), C.c_uint32(width), C.c_uint32(height), C.c_int(int(flip_y)),
+                                 _p(scratch), _p(dst))
+        return dst, scratch
