@@ -1,0 +1,120 @@
+"""ctypes binding of the C ABI in include/gsm/gsm.h (gsm_renderer_b200/lib/libgsm_b200.so).
+
+There is no fallback: if the CUDA library is missing or does not load, importing a renderer fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgsm_b200.so")
+
+GSM_NUM_STAGES = 8
+
+
+class gsm_config(C.Structure):
+    _fields_ = [("maxGaussians", C.c_uint32), ("maxWidth", C.c_uint32), ("maxHeight", C.c_uint32),
+                ("precision", C.c_uint32), ("gaussianColorSpace", C.c_uint32),
+                ("depthSortKeyPrecision", C.c_uint32), ("tileIdPrecision", C.c_uint32),
+                ("device", C.c_int32), ("stereoCopyFlipY", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+
+
+class gsm_camera(C.Structure):
+    _fields_ = [("viewMatrix", C.c_float * 16), ("projectionMatrix", C.c_float * 16),
+                ("position", C.c_float * 3), ("focalX", C.c_float), ("focalY", C.c_float),
+                ("nearPlane", C.c_float), ("farPlane", C.c_float)]
+
+
+class DepthFirstHeader(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("visibleCount", "totalInstances", "paddedVisibleCount",
+                                          "paddedInstanceCount", "overflow", "padding0", "padding1",
+                                          "padding2")]
+
+
+# every symbol include/gsm/gsm.h declares (tests check the library exports each one)
+EXPORTS = {
+    "gsm_config_default": (None, [C.POINTER(gsm_config)]),
+    "gsm_renderer_create": (C.c_int, [C.POINTER(gsm_config), C.POINTER(C.c_void_p)]),
+    "gsm_renderer_destroy": (None, [C.c_void_p]),
+    "gsm_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_uint32, C.c_uint32, C.POINTER(gsm_camera), C.c_uint32, C.c_uint32]),
+    "gsm_render_stereo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_uint32, C.c_uint32, C.POINTER(gsm_camera), C.POINTER(gsm_camera),
+                                    C.c_uint32, C.c_uint32]),
+    "gsm_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                  C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gsm_last_gpu_time_ms": (C.c_double, [C.c_void_p]),
+    "gsm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "gsm_get_stage_times_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "gsm_stage_name": (C.c_char_p, [C.c_int]),
+    "gsm_debug_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "gsm_debug_element_size": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "gsm_buffer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "gsm_buffer_free": (C.c_int, [C.c_void_p]),
+    "gsm_buffer_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gsm_buffer_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gsm_stream_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "gsm_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "gsm_stream_destroy": (C.c_int, [C.c_void_p]),
+    "gsm_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int]),
+    "gsm_strip_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                    C.c_uint32, C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.c_void_p,
+                                    C.POINTER(C.c_uint32)]),
+    "gsm_strip_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                   C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "gsm_probe_math": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "gsm_status_string": (C.c_char_p, [C.c_int]),
+    "gsm_last_error_string": (C.c_char_p, []),
+    "gsm_abi_version": (C.c_int, []),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Loads libgsm_b200.so. Raises if it is absent -- there is no CPU or PyTorch fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                "gsm_renderer_b200 has no fallback path.")
+        try:
+            l = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(l, name)  # AttributeError here means the header and the library diverged
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def ptr(obj) -> int | None:
+    """Device or host pointer of a torch tensor / numpy array / int / None."""
+    if obj is None:
+        return None
+    if isinstance(obj, int):
+        return obj
+    if hasattr(obj, "data_ptr"):
+        return int(obj.data_ptr())
+    if hasattr(obj, "ctypes"):
+        return int(obj.ctypes.data)
+    raise TypeError(f"cannot take the address of {type(obj)!r}")
+
+
+def stream_handle(stream) -> int | None:
+    """cudaStream_t of a torch.cuda.Stream / int / None (None = the legacy default stream)."""
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return stream or None
+    if hasattr(stream, "cuda_stream"):
+        return int(stream.cuda_stream) or None
+    raise TypeError(f"not a stream: {type(stream)!r}")

@@ -1,0 +1,279 @@
+// blend.cu -- stage 8: front-to-back alpha blending of 16x16 tiles, 8x8 threads x 2x2 pixels, all pixel
+// arithmetic in binary16 exactly as depthFirstRender (DFS.metal:1703-1811) and depthFirstStereoRender
+// (DFS.metal:1825-1982) do it, with the clear (DFS.metal:2020-2034, :1813-1823) and the stereo copy
+// (DFS.metal:1984-2018) fused in.
+//
+// B200 mapping: one CTA per tile; the tile's splat list is staged through shared memory in chunks (one
+// 32-byte pre-expanded record per splat, gathered once per tile instead of once per thread); the four pixels
+// of a thread are two half2 rows so every half op is a packed HADD2/HMUL2; exp() is the canonical
+// polynomial of gsm_dmath.cuh; a CTA-wide vote stops fetching once every thread has closed its quad.
+// Per-thread semantics are untouched: a thread's early exit depends only on its own four transmittances
+// (quirk Q8), and unfused mul/add keep one rounding per reference operation.
+#include "gsm_common.cuh"
+#include "gsm_dmath.cuh"
+#include "gsm_kernels.h"
+
+namespace gsm {
+
+constexpr int kBlendThreads = 64;
+constexpr int kBlendChunk = 64;
+
+__device__ __forceinline__ __half2 h2(float v) { return __float2half2_rn(v); }
+__device__ __forceinline__ uint32_t h2bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+struct QuadState {
+    __half2 T0, T1;             // transmittance rows (x, x+1)
+    __half2 r0, g0, b0, d0;     // row 0 accumulators
+    __half2 r1, g1, b1, d1;     // row 1
+};
+
+// one splat against one eye's quad; returns false if all four alphas are zero (nothing to do)
+__device__ __forceinline__ void accumulate(QuadState& q, __half2 a0, __half2 a1, __half2 cr, __half2 cg, __half2 cb, __half2 cd,
+                                           bool withDepth) {
+    const __half2 one = h2(1.0f);
+    __half2 w0 = __hmul2_rn(a0, q.T0), w1 = __hmul2_rn(a1, q.T1);
+    q.r0 = __hadd2_rn(q.r0, __hmul2_rn(cr, w0)); q.r1 = __hadd2_rn(q.r1, __hmul2_rn(cr, w1));
+    q.g0 = __hadd2_rn(q.g0, __hmul2_rn(cg, w0)); q.g1 = __hadd2_rn(q.g1, __hmul2_rn(cg, w1));
+    q.b0 = __hadd2_rn(q.b0, __hmul2_rn(cb, w0)); q.b1 = __hadd2_rn(q.b1, __hmul2_rn(cb, w1));
+    if (withDepth) {
+        q.d0 = __hadd2_rn(q.d0, __hmul2_rn(cd, w0)); q.d1 = __hadd2_rn(q.d1, __hmul2_rn(cd, w1));
+    }
+    q.T0 = __hmul2_rn(q.T0, __hsub2_rn(one, a0));
+    q.T1 = __hmul2_rn(q.T1, __hsub2_rn(one, a1));
+}
+
+// p = dx*dx*cxx + dy*dy*cyy + dx*dy*cxy2 for one row (two pixels), one rounding per op (DFS.metal:1770)
+__device__ __forceinline__ __half2 power(__half2 dx, __half2 dy, __half2 cxx, __half2 cyy, __half2 cxy2) {
+    __half2 t0 = __hmul2_rn(__hmul2_rn(dx, dx), cxx);
+    __half2 t1 = __hmul2_rn(__hmul2_rn(dy, dy), cyy);
+    __half2 t2 = __hmul2_rn(__hmul2_rn(dx, dy), cxy2);
+    return __hadd2_rn(__hadd2_rn(t0, t1), t2);
+}
+
+__device__ __forceinline__ bool quadClosed(const __half2& T0, const __half2& T1, __half thr) {
+    __half2 m = __hmax2(T0, T1);
+    __half mm = __hmax(__low2half(m), __high2half(m));
+    return __hlt(mm, thr);  // DFS.metal:1746-1747
+}
+
+__device__ __forceinline__ void storePixelRow(__half* color, __half* depth, uint32_t width, uint32_t height, uint32_t x, uint32_t y,
+                                              __half2 r, __half2 g, __half2 b, __half2 a, __half2 d) {
+    if (y >= height || x >= width) return;
+    const size_t o = (size_t)y * width + x;
+    uint2 v;  // 8-byte pixel stores: always aligned, and 8 lanes x 2 pixels still cover one 128-byte line per row
+    v.x = h2bits(__halves2half2(__low2half(r), __low2half(g)));
+    v.y = h2bits(__halves2half2(__low2half(b), __low2half(a)));
+    *reinterpret_cast<uint2*>(color + 4 * o) = v;
+    if (depth) depth[o] = __low2half(d);
+    if (x + 1 < width) {
+        v.x = h2bits(__halves2half2(__high2half(r), __high2half(g)));
+        v.y = h2bits(__halves2half2(__high2half(b), __high2half(a)));
+        *reinterpret_cast<uint2*>(color + 4 * o + 4) = v;
+        if (depth) depth[o + 1] = __high2half(d);
+    }
+}
+
+__global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_t* __restrict__ lowerBounds,
+                                                                   const BlendSplat* __restrict__ splats,
+                                                                   const int32_t* __restrict__ instanceIdx, uint32_t width,
+                                                                   uint32_t height, uint32_t tilesX, uint32_t tileRowFirst,
+                                                                   __half* __restrict__ color, __half* __restrict__ depth) {
+    __shared__ uint4 s_rec[kBlendChunk][2];
+    const unsigned tid = threadIdx.x;
+    const uint32_t tileX = blockIdx.x % tilesX, tileY = tileRowFirst + blockIdx.x / tilesX;
+    const uint32_t tile = tileY * tilesX + tileX;
+    const uint32_t start = lowerBounds[tile];
+    const uint32_t end = lowerBounds[tile + 1];
+    const uint32_t count = end > start ? end - start : 0u;
+
+    const uint32_t baseX = tileX * 16u + (tid & 7u) * 2u, baseY = tileY * 16u + (tid >> 3) * 2u;
+    const __half2 px = __halves2half2(__uint2half_rn(baseX), __uint2half_rn(baseX + 1u));  // half(baseX+k), quirk Q7
+    const __half2 py0 = __half2half2(__uint2half_rn(baseY)), py1 = __half2half2(__uint2half_rn(baseY + 1u));
+    const __half thr = __float2half_rn(1.0f / 255.0f);  // half(1.0h/255.0h): both roundings agree (0x1C04)
+    const __half2 h099 = h2(0.99f), negHalf = h2(-0.5f), zero = h2(0.0f), one = h2(1.0f);
+
+    QuadState q;
+    q.T0 = one; q.T1 = one;
+    q.r0 = q.g0 = q.b0 = q.d0 = q.r1 = q.g1 = q.b1 = q.d1 = zero;
+    bool done = false;
+
+    for (uint32_t base = 0; base < count; base += kBlendChunk) {
+        const uint32_t n = min((uint32_t)kBlendChunk, count - base);
+        if (tid < n) {
+            const int32_t gi = __ldg(instanceIdx + start + base + tid);
+            if (gi >= 0) {
+                const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
+                s_rec[tid][0] = __ldg(src);
+                s_rec[tid][1] = __ldg(src + 1);
+            } else {
+                s_rec[tid][1] = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
+            }
+        }
+        __syncthreads();
+        if (!done) {
+            for (uint32_t j = 0; j < n; ++j) {
+                if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
+                const uint4 ra = s_rec[j][0], rb = s_rec[j][1];
+                if (rb.y == 0u) continue;
+                const __half2 mean = *reinterpret_cast<const __half2*>(&ra.x);
+                const __half2 cxx_cyy = *reinterpret_cast<const __half2*>(&ra.y);
+                const __half2 cxy2_op = *reinterpret_cast<const __half2*>(&ra.z);
+                const __half2 rg = *reinterpret_cast<const __half2*>(&ra.w);
+                const __half2 b_d = *reinterpret_cast<const __half2*>(&rb.x);
+                const __half2 mx = __low2half2(mean), my = __high2half2(mean);
+                const __half2 cxx = __low2half2(cxx_cyy), cyy = __high2half2(cxx_cyy);
+                const __half2 cxy2 = __low2half2(cxy2_op), op = __high2half2(cxy2_op);
+                const __half2 dx = __hsub2_rn(px, mx);
+                const __half2 dy0 = __hsub2_rn(py0, my), dy1 = __hsub2_rn(py1, my);
+                const __half2 p0 = power(dx, dy0, cxx, cyy, cxy2), p1 = power(dx, dy1, cxx, cyy, cxy2);
+                const __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p0))), h099);
+                const __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p1))), h099);
+                if (((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) == 0u) continue;  // all(alphas == 0), DFS.metal:1781
+                accumulate(q, a0, a1, __low2half2(rg), __high2half2(rg), __low2half2(b_d), __high2half2(b_d), true);
+            }
+        }
+        if (__syncthreads_and(done ? 1 : 0)) break;
+    }
+
+    // active tiles: alpha = 1 - T; inactive tiles keep the clear value alpha = 1 (quirk Q6)
+    __half2 al0, al1;
+    if (count > 0) { al0 = __hsub2_rn(one, q.T0); al1 = __hsub2_rn(one, q.T1); }
+    else { al0 = one; al1 = one; }
+    storePixelRow(color, depth, width, height, baseX, baseY, q.r0, q.g0, q.b0, al0, q.d0);
+    storePixelRow(color, depth, width, height, baseX, baseY + 1u, q.r1, q.g1, q.b1, al1, q.d1);
+}
+
+// one eye of depthFirstStereoRender for one splat (DFS.metal:1881-1920)
+__device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 mean, __half2 cxx_cyy, __half cxy2h, __half2 op,
+                                          __half2 cr, __half2 cg, __half2 cb, __half2 px, __half2 py0, __half2 py1) {
+    if (!eyeOpen) return;
+    if (!__hge(__low2half(mean), __float2half_rn(-60000.0f))) return;  // invisible eye: mean = -inf
+    const __half2 negHalf = h2(-0.5f), h099 = h2(0.99f), r2Max = h2(9.0f), zero = h2(0.0f);
+    const __half2 mx = __low2half2(mean), my = __high2half2(mean);
+    const __half2 cxx = __low2half2(cxx_cyy), cyy = __high2half2(cxx_cyy), cxy2 = __half2half2(cxy2h);
+    const __half2 dx = __hsub2_rn(px, mx);
+    const __half2 p0 = power(dx, __hsub2_rn(py0, my), cxx, cyy, cxy2), p1 = power(dx, __hsub2_rn(py1, my), cxx, cyy, cxy2);
+    const __half2 out0 = __hgt2(p0, r2Max), out1 = __hgt2(p1, r2Max);  // 1.0 where p > r2Max (false for NaN)
+    const uint32_t o0 = h2bits(out0), o1 = h2bits(out1);
+    if (o0 == 0x3C003C00u && o1 == 0x3C003C00u) return;  // all four beyond the cutoff: alphas stay 0
+    __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p0))), h099);
+    __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p1))), h099);
+    // per-pixel cutoff: alpha = 0 where p > r2Max
+    uint32_t m0 = ((o0 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o0 >> 16) ? 0u : 0xFFFF0000u);
+    uint32_t m1 = ((o1 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o1 >> 16) ? 0u : 0xFFFF0000u);
+    uint32_t b0 = h2bits(a0) & m0, b1 = h2bits(a1) & m1;
+    a0 = *reinterpret_cast<__half2*>(&b0);
+    a1 = *reinterpret_cast<__half2*>(&b1);
+    if (((b0 | b1) & 0x7FFF7FFFu) == 0u) return;
+    accumulate(q, a0, a1, cr, cg, cb, zero, false);
+}
+
+__global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint32_t* __restrict__ lowerBounds,
+                                                                     const GSMStereoTiledRenderData* __restrict__ splats,
+                                                                     const int32_t* __restrict__ instanceIdx, uint32_t width,
+                                                                     uint32_t height, uint32_t tilesX,
+                                                                     __half* __restrict__ dstSideBySide, int flipY) {
+    __shared__ uint4 s_rec[kBlendChunk][2];
+    __shared__ uint32_t s_valid[kBlendChunk];
+    const unsigned tid = threadIdx.x;
+    const uint32_t tileX = blockIdx.x % tilesX, tileY = blockIdx.x / tilesX;
+    const uint32_t tile = tileY * tilesX + tileX;
+    const uint32_t start = lowerBounds[tile];
+    const uint32_t end = lowerBounds[tile + 1];
+    const uint32_t count = end > start ? end - start : 0u;
+    const uint32_t baseX = tileX * 16u + (tid & 7u) * 2u, baseY = tileY * 16u + (tid >> 3) * 2u;
+    const __half2 px = __halves2half2(__uint2half_rn(baseX), __uint2half_rn(baseX + 1u));
+    const __half2 py0 = __half2half2(__uint2half_rn(baseY)), py1 = __half2half2(__uint2half_rn(baseY + 1u));
+    const __half thr = __float2half_rn(1.0f / 255.0f);
+    const __half2 zero = h2(0.0f), one = h2(1.0f);
+    QuadState qL, qR;
+    qL.T0 = qL.T1 = qR.T0 = qR.T1 = one;
+    qL.r0 = qL.g0 = qL.b0 = qL.d0 = qL.r1 = qL.g1 = qL.b1 = qL.d1 = zero;
+    qR = qL;
+    bool done = false;
+    for (uint32_t base = 0; base < count; base += kBlendChunk) {
+        const uint32_t n = min((uint32_t)kBlendChunk, count - base);
+        if (tid < n) {
+            const int32_t gi = __ldg(instanceIdx + start + base + tid);
+            s_valid[tid] = gi >= 0 ? 1u : 0u;
+            if (gi >= 0) {
+                const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
+                s_rec[tid][0] = __ldg(src);
+                s_rec[tid][1] = __ldg(src + 1);
+            }
+        }
+        __syncthreads();
+        if (!done) {
+            for (uint32_t j = 0; j < n; ++j) {
+                const bool closedL = quadClosed(qL.T0, qL.T1, thr), closedR = quadClosed(qR.T0, qR.T1, thr);
+                if (closedL && closedR) { done = true; break; }  // DFS.metal:1868-1871
+                if (!s_valid[j]) continue;
+                const uint4 ra = s_rec[j][0], rb = s_rec[j][1];
+                // halfs: ra = {LmeanX,LmeanY | Lcxx,Lcyy | Lcxy2,Ldepth | RmeanX,RmeanY}; rb = {Rcxx,Rcyy | Rcxy2,Rdepth | r,g,b,op | cDepth,pad}
+                const __half2 op = __half2half2(__float2half_rn((float)(rb.z >> 24) / 255.0f));
+                const __half2 cr = __half2half2(__float2half_rn((float)(rb.z & 0xFFu) / 255.0f));
+                const __half2 cg = __half2half2(__float2half_rn((float)((rb.z >> 8) & 0xFFu) / 255.0f));
+                const __half2 cb = __half2half2(__float2half_rn((float)((rb.z >> 16) & 0xFFu) / 255.0f));
+                stereoEye(qL, !closedL, *reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&ra.y),
+                          __low2half(*reinterpret_cast<const __half2*>(&ra.z)), op, cr, cg, cb, px, py0, py1);
+                stereoEye(qR, !closedR, *reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
+                          __low2half(*reinterpret_cast<const __half2*>(&rb.y)), op, cr, cg, cb, px, py0, py1);
+            }
+        }
+        if (__syncthreads_and(done ? 1 : 0)) break;
+    }
+    // write both eyes straight into the side-by-side target (left at x in [0,W), right at [W,2W)); the literal
+    // stereoCopy maps NDC(-1,-1) to uv(0,0), i.e. dst row y = src row H-1-y (quirk Q9).
+    const uint32_t sbsWidth = 2u * width;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+        const uint32_t y = baseY + row;
+        if (y >= height) continue;
+        const uint32_t dy = flipY ? (height - 1u - y) : y;
+        __half2 aL, aR;
+        if (count > 0) {
+            aL = __hsub2_rn(one, row ? qL.T1 : qL.T0);
+            aR = __hsub2_rn(one, row ? qR.T1 : qR.T0);
+        } else { aL = one; aR = one; }
+        // bounds are per-eye: x < width
+        if (baseX < width) {
+            const bool two = baseX + 1u < width;
+            __half* l = dstSideBySide + 4 * ((size_t)dy * sbsWidth + baseX);
+            __half* r = dstSideBySide + 4 * ((size_t)dy * sbsWidth + width + baseX);
+            const __half2 Lr = row ? qL.r1 : qL.r0, Lg = row ? qL.g1 : qL.g0, Lb = row ? qL.b1 : qL.b0;
+            const __half2 Rr = row ? qR.r1 : qR.r0, Rg = row ? qR.g1 : qR.g0, Rb = row ? qR.b1 : qR.b0;
+            uint2 v;
+            v.x = h2bits(__halves2half2(__low2half(Lr), __low2half(Lg))); v.y = h2bits(__halves2half2(__low2half(Lb), __low2half(aL)));
+            *reinterpret_cast<uint2*>(l) = v;
+            v.x = h2bits(__halves2half2(__low2half(Rr), __low2half(Rg))); v.y = h2bits(__halves2half2(__low2half(Rb), __low2half(aR)));
+            *reinterpret_cast<uint2*>(r) = v;
+            if (two) {
+                v.x = h2bits(__halves2half2(__high2half(Lr), __high2half(Lg))); v.y = h2bits(__halves2half2(__high2half(Lb), __high2half(aL)));
+                *reinterpret_cast<uint2*>(l + 4) = v;
+                v.x = h2bits(__halves2half2(__high2half(Rr), __high2half(Rg))); v.y = h2bits(__halves2half2(__high2half(Rb), __high2half(aR)));
+                *reinterpret_cast<uint2*>(r + 4) = v;
+            }
+        }
+    }
+}
+
+cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,
+                            uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY, uint32_t tileRowFirst,
+                            uint32_t tileRowCount, __half* color, __half* depth) {
+    (void)tilesY;
+    if (tileRowCount == 0) return cudaSuccess;
+    blend_mono_kernel<<<tilesX * tileRowCount, kBlendThreads, 0, s>>>(lowerBounds, splats, instanceIdx, width, height, tilesX,
+                                                                       tileRowFirst, color, depth);
+    return cudaGetLastError();
+}
+
+cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
+                              const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
+                              __half* dstSideBySide, __half* intermediate, int flipY) {
+    (void)intermediate;
+    blend_stereo_kernel<<<tilesX * tilesY, kBlendThreads, 0, s>>>(lowerBounds, splats, instanceIdx, width, height, tilesX,
+                                                                   dstSideBySide, flipY);
+    return cudaGetLastError();
+}
+
+}  // namespace gsm

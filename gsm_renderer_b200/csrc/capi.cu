@@ -1,0 +1,722 @@
+// capi.cu -- the C ABI of include/gsm/gsm.h: renderer handle, device arena, stage sequencing on the caller's
+// stream, white-box reads. The stage order is the reference's encodeRender / encodeStereoPipeline
+// (DepthFirstRenderer.swift:237-465, :595-831) with the fusions listed in DESIGN.md section 5.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "gsm_common.cuh"
+#include "gsm_kernels.h"
+
+using namespace gsm;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+gsm_status fail(gsm_status s, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_lastError = buf;
+    return s;
+}
+
+#define GSM_CUDA(call, what)                                            \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return fail(GSM_ERR_RENDER_FAILED, what, e__); \
+    } while (0)
+
+constexpr uint32_t kMaxSupportedGaussians = 30000000u;  // DFR.swift:7
+
+size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Resources {
+    char* arena = nullptr;
+    size_t bytes = 0;
+    bool stereo = false;
+    uint32_t maxGaussians = 0, maxInstances = 0, maxTiles = 0;
+    uint32_t depthTilesCap = 0, tileTilesCap = 0;
+    // per Gaussian
+    void* renderData = nullptr;
+    int32_t* bounds = nullptr;
+    uint32_t* nTouched = nullptr;
+    BlendSplat* blendSplats = nullptr;
+    // per visible (ping-pong pairs)
+    uint32_t* depthKeys[2] = {nullptr, nullptr};
+    int32_t* primIdx[2] = {nullptr, nullptr};
+    uint32_t* offsets = nullptr;
+    // per instance
+    void* tileIds[2] = {nullptr, nullptr};
+    int32_t* instIdx[2] = {nullptr, nullptr};
+    // per tile
+    uint32_t* lowerBounds = nullptr;
+    GSMGaussianHeader* tileHeaders = nullptr;
+    uint32_t* activeTiles = nullptr;
+    GSMDepthFirstHeader* header = nullptr;
+    // zeroed every frame
+    FrameState* fs = nullptr;
+    unsigned long long* projStatus = nullptr;
+    unsigned long long* scanStatus = nullptr;
+    size_t zeroBytes = 0;
+    // zeroed by the sort's histogram kernel
+    uint32_t* depthSortStatus = nullptr;
+    uint32_t* tileSortStatus = nullptr;
+};
+
+}  // namespace
+
+struct gsm_renderer {
+    gsm_config cfg;
+    int device = 0;
+    int numSMs = 148;
+    Resources mono, stereoRes;
+    bool profiling = false;
+    cudaEvent_t ev[GSM_NUM_STAGES + 1] = {};
+    bool evValid = false;
+    bool evRecorded = false;
+    float stageMs[GSM_NUM_STAGES] = {};
+    double lastMs = -1.0;
+    // gsm_render_host staging
+    cudaStream_t hostStream = nullptr;
+    void* stGaussians = nullptr; size_t stGaussiansBytes = 0;
+    void* stHarmonics = nullptr; size_t stHarmonicsBytes = 0;
+    void* stColor = nullptr; size_t stColorBytes = 0;
+    void* stDepth = nullptr; size_t stDepthBytes = 0;
+    uint32_t lastTilesX = 0, lastTilesY = 0;
+    bool lastStereo = false;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// DepthFirstViewResources / StereoTiledResources (DepthFirstResources.swift:58-325, :377-615): one arena.
+gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
+    if (res.arena) return GSM_OK;
+    const gsm_config& c = r->cfg;
+    const uint32_t G = c.maxGaussians < 1 ? 1 : c.maxGaussians;
+    const uint32_t I = 4u * G;  // DepthFirstResources.swift:80
+    const uint32_t tilesX = (c.maxWidth + kTile - 1) / kTile, tilesY = (c.maxHeight + kTile - 1) / kTile;
+    const uint32_t T = tilesX * tilesY < 1 ? 1 : tilesX * tilesY;
+    const bool tile16 = c.tileIdPrecision == GSM_KEY_BITS16;
+    const size_t tileIdBytes = tile16 ? 2 : 4;
+    res.stereo = stereo;
+    res.maxGaussians = G; res.maxInstances = I; res.maxTiles = T;
+    res.depthTilesCap = (G + sortTileSize(32) - 1) / sortTileSize(32);
+    res.tileTilesCap = (I + sortTileSize(tile16 ? 16 : 32) - 1) / sortTileSize(tile16 ? 16 : 32);
+
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = alignUp(off + bytes, 256); return o; };
+    const size_t oRender = take((size_t)G * (stereo ? 32 : 16));
+    const size_t oBounds = take((size_t)G * 16);
+    const size_t oTouched = take((size_t)G * 4);
+    const size_t oBlend = stereo ? 0 : take((size_t)G * sizeof(BlendSplat));
+    const size_t oKeys0 = take((size_t)G * 4), oKeys1 = take((size_t)G * 4);
+    const size_t oIdx0 = take((size_t)G * 4), oIdx1 = take((size_t)G * 4);
+    const size_t oOffsets = take((size_t)G * 4);
+    const size_t oTid0 = take((size_t)I * tileIdBytes), oTid1 = take((size_t)I * tileIdBytes);
+    const size_t oIi0 = take((size_t)I * 4), oIi1 = take((size_t)I * 4);
+    const size_t oLB = take((size_t)(T + 1) * 4);
+    const size_t oTH = take((size_t)T * 8);
+    const size_t oAT = take((size_t)T * 4);
+    const size_t oHeader = take(sizeof(GSMDepthFirstHeader));
+    const size_t oZero = off;
+    const size_t oFS = take(sizeof(FrameState));
+    const size_t oProjStatus = take(((size_t)(G + 255) / 256) * 8);
+    const size_t oScanStatus = take(((size_t)(G + 2047) / 2048 + 1) * 8);
+    const size_t zeroEnd = off;
+    const size_t oDepthStatus = take((size_t)4 * res.depthTilesCap * 256 * 4);
+    const size_t oTileStatus = take((size_t)4 * res.tileTilesCap * 256 * 4);
+    res.bytes = off;
+
+    cudaError_t e = cudaMalloc((void**)&res.arena, res.bytes);
+    if (e != cudaSuccess) {
+        res.arena = nullptr;
+        char msg[128];
+        snprintf(msg, sizeof msg, "failed to allocate device arena of %zu bytes", res.bytes);
+        return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, msg, e);
+    }
+    char* a = res.arena;
+    res.renderData = a + oRender;
+    res.bounds = (int32_t*)(a + oBounds);
+    res.nTouched = (uint32_t*)(a + oTouched);
+    res.blendSplats = stereo ? nullptr : (BlendSplat*)(a + oBlend);
+    res.depthKeys[0] = (uint32_t*)(a + oKeys0); res.depthKeys[1] = (uint32_t*)(a + oKeys1);
+    res.primIdx[0] = (int32_t*)(a + oIdx0); res.primIdx[1] = (int32_t*)(a + oIdx1);
+    res.offsets = (uint32_t*)(a + oOffsets);
+    res.tileIds[0] = a + oTid0; res.tileIds[1] = a + oTid1;
+    res.instIdx[0] = (int32_t*)(a + oIi0); res.instIdx[1] = (int32_t*)(a + oIi1);
+    res.lowerBounds = (uint32_t*)(a + oLB);
+    res.tileHeaders = (GSMGaussianHeader*)(a + oTH);
+    res.activeTiles = (uint32_t*)(a + oAT);
+    res.header = (GSMDepthFirstHeader*)(a + oHeader);
+    res.fs = (FrameState*)(a + oFS);
+    res.projStatus = (unsigned long long*)(a + oProjStatus);
+    res.scanStatus = (unsigned long long*)(a + oScanStatus);
+    res.zeroBytes = zeroEnd - oZero;
+    res.depthSortStatus = (uint32_t*)(a + oDepthStatus);
+    res.tileSortStatus = (uint32_t*)(a + oTileStatus);
+    e = cudaMemset(res.arena, 0, res.bytes);
+    if (e != cudaSuccess) return fail(GSM_ERR_RENDER_FAILED, "arena memset", e);
+    return GSM_OK;
+}
+
+void freeResources(Resources& res) {
+    if (res.arena) cudaFree(res.arena);
+    res = Resources();
+}
+
+int tileSortPasses(uint32_t tileCount) {  // TileSortEncoder.swift:61-62
+    uint32_t v = tileCount > 0 ? (tileCount - 1 > 1 ? tileCount - 1 : 1) : 1;
+    int bits = 0;
+    while (v) { bits++; v >>= 1; }
+    if (tileCount == 0) bits = 1;
+    return (bits + 7) / 8;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+void recordStage(gsm_renderer* r, cudaStream_t s, int idx) {
+    if (r->profiling && r->evValid) cudaEventRecord(r->ev[idx], s);
+}
+
+// stages 2-7 shared by the mono and stereo frames (DFR.swift:325-430, :683-787)
+gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s, bool stereo, uint32_t tilesX, uint32_t tilesY) {
+    const gsm_config& c = r->cfg;
+    const bool tile16 = c.tileIdPrecision == GSM_KEY_BITS16;
+    const bool key16 = c.depthSortKeyPrecision == GSM_KEY_BITS16;
+    // stage 2: depth sort (4 passes; 2 with 16-bit depth keys -- the keys stay u32, DepthRadixSortEncoder.swift:45-46)
+    SortPlan dp;
+    dp.k0 = res.depthKeys[0]; dp.k1 = res.depthKeys[1];
+    dp.v0 = (uint32_t*)res.primIdx[0]; dp.v1 = (uint32_t*)res.primIdx[1];
+    dp.countPtr = &res.header->visibleCount; dp.countCap = res.maxGaussians;
+    dp.hist = &res.fs->hist[0][0]; dp.status = res.depthSortStatus; dp.tickets = &res.fs->ticketSort[0];
+    dp.tilesCap = res.depthTilesCap; dp.keyBits = 32; dp.numPasses = key16 ? 2 : 4; dp.numSMs = r->numSMs;
+    GSM_CUDA(launchSort(s, dp), "depth sort");
+    recordStage(r, s, 2);
+    // stages 3+4
+    GSM_CUDA(launchApplyOrderScan(s, res.primIdx[0], res.nTouched, res.offsets, res.header, res.scanStatus, &res.fs->ticketScan,
+                                  r->numSMs), "apply order + scan");
+    recordStage(r, s, 3);
+    // stage 5
+    GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.offsets, res.bounds, res.renderData, res.tileIds[0],
+                                   res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians), "create instances");
+    recordStage(r, s, 4);
+    // stage 6
+    SortPlan tp;
+    tp.k0 = res.tileIds[0]; tp.k1 = res.tileIds[1];
+    tp.v0 = (uint32_t*)res.instIdx[0]; tp.v1 = (uint32_t*)res.instIdx[1];
+    tp.countPtr = &res.header->totalInstances; tp.countCap = res.maxInstances;
+    tp.hist = &res.fs->hist[4][0]; tp.status = res.tileSortStatus; tp.tickets = &res.fs->ticketSort[4];
+    tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tileSortPasses(tilesX * tilesY);
+    tp.numSMs = r->numSMs;
+    GSM_CUDA(launchSort(s, tp), "tile sort");
+    recordStage(r, s, 5);
+    // stage 7
+    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.tileHeaders,
+                              res.activeTiles, &res.fs->activeTileCount, r->numSMs), "tile ranges");
+    recordStage(r, s, 6);
+    return GSM_OK;
+}
+
+gsm_status validateFrame(gsm_renderer* r, uint32_t width, uint32_t height, const void* gaussians, const void* harmonics,
+                         const void* color) {
+    if (!r) return fail(GSM_ERR_INVALID_ARGUMENT, "null renderer");
+    if (!gaussians || !harmonics || !color) return fail(GSM_ERR_INVALID_ARGUMENT, "null buffer");
+    if (width == 0 || height == 0 || width > r->cfg.maxWidth || height > r->cfg.maxHeight)
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "dimensions exceed RendererConfig.maxWidth/maxHeight");
+    if (!aligned16(gaussians) || !aligned16(harmonics)) return fail(GSM_ERR_INVALID_ARGUMENT, "input buffers must be 16-byte aligned");
+    if (((uintptr_t)color & 7u) != 0) return fail(GSM_ERR_INVALID_ARGUMENT, "colour target must be 8-byte aligned");
+    return GSM_OK;
+}
+
+void fillMonoCam(MonoCam& mc, const gsm_camera* cam, uint32_t count, uint32_t sh, uint32_t w, uint32_t h, bool srgb) {
+    memcpy(mc.view, cam->viewMatrix, 64);
+    memcpy(mc.proj, cam->projectionMatrix, 64);
+    memcpy(mc.center, cam->position, 12);
+    mc.width = (float)w; mc.height = (float)h;
+    mc.nearPlane = cam->nearPlane; mc.farPlane = cam->farPlane;
+    mc.shComponents = sh; mc.gaussianCount = count;
+    mc.inputIsSRGB = srgb ? 1.0f : 0.0f;
+    mc.tilesX = (w + kTile - 1) / kTile; mc.tilesY = (h + kTile - 1) / kTile;
+}
+
+}  // namespace
+
+extern "C" {
+
+void gsm_config_default(gsm_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->maxGaussians = 6000000u;  // GRP.swift:211-218
+    cfg->maxWidth = 1920;
+    cfg->maxHeight = 1080;
+    cfg->precision = GSM_PRECISION_FLOAT16;
+    cfg->gaussianColorSpace = GSM_COLORSPACE_SRGB;
+    cfg->depthSortKeyPrecision = GSM_KEY_BITS32;  // DFR.swift:48-49
+    cfg->tileIdPrecision = GSM_KEY_BITS16;
+    cfg->device = -1;
+    cfg->stereoCopyFlipY = 1;
+}
+
+gsm_status gsm_renderer_create(const gsm_config* cfg, gsm_renderer** out) {
+    if (!cfg || !out) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (cfg->maxGaussians > kMaxSupportedGaussians)  // DFR.swift:51-56
+        return fail(GSM_ERR_INVALID_GAUSSIAN_COUNT, "maxGaussians exceeds 30,000,000");
+    if (cfg->precision > 1 || cfg->gaussianColorSpace > 1 ||
+        (cfg->depthSortKeyPrecision != 16 && cfg->depthSortKeyPrecision != 32) ||
+        (cfg->tileIdPrecision != 16 && cfg->tileIdPrecision != 32))
+        return fail(GSM_ERR_INVALID_ARGUMENT, "bad enum value in gsm_config");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(GSM_ERR_DEVICE_NOT_AVAILABLE, "no CUDA device");  // DFR.swift:58-61
+    }
+    int dev = cfg->device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= n) return fail(GSM_ERR_DEVICE_NOT_AVAILABLE, "device ordinal out of range");
+    // limits: RendererLimits(from:) clamps to >= 1 (GlobalRenderer.swift:17-23)
+    gsm_config c = *cfg;
+    if (c.maxGaussians < 1) c.maxGaussians = 1;
+    if (c.maxWidth < 1) c.maxWidth = 1;
+    if (c.maxHeight < 1) c.maxHeight = 1;
+    const uint64_t tiles = (uint64_t)((c.maxWidth + kTile - 1) / kTile) * ((c.maxHeight + kTile - 1) / kTile);
+    if (c.tileIdPrecision == GSM_KEY_BITS16 && tiles > 65535u)
+        return fail(GSM_ERR_INVALID_TILE_COUNT, "more than 65535 tiles need tileIdPrecision 32");
+    DeviceGuard guard(dev);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail(GSM_ERR_DEVICE_NOT_AVAILABLE, "cudaGetDeviceProperties", e);
+    // the kernels are built for sm_100a only: fail loudly anywhere else (no fallback path exists)
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, (const void*)finalize_header_probe());
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GSM_ERR_FAILED_TO_CREATE_PIPELINE, "sm_100a kernels cannot be loaded on this device", e);
+    }
+    gsm_renderer* r = new (std::nothrow) gsm_renderer();
+    if (!r) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "host allocation failed");
+    r->cfg = c;
+    r->cfg.device = dev;
+    r->device = dev;
+    r->numSMs = prop.multiProcessorCount;
+    *out = r;
+    return GSM_OK;
+}
+
+void gsm_renderer_destroy(gsm_renderer* r) {
+    if (!r) return;
+    DeviceGuard guard(r->device);
+    cudaDeviceSynchronize();
+    freeResources(r->mono);
+    freeResources(r->stereoRes);
+    if (r->evValid) for (auto& e : r->ev) cudaEventDestroy(e);
+    if (r->stGaussians) cudaFree(r->stGaussians);
+    if (r->stHarmonics) cudaFree(r->stHarmonics);
+    if (r->stColor) cudaFree(r->stColor);
+    if (r->stDepth) cudaFree(r->stDepth);
+    if (r->hostStream) cudaStreamDestroy(r->hostStream);
+    delete r;
+}
+
+gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, const void* gaussians, const void* harmonics,
+                      uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height) {
+    if (!r || !camera) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;  // DFR.swift:249 (quirk Q10)
+    gsm_status st = validateFrame(r, width, height, gaussians, harmonics, color);
+    if (st != GSM_OK) return st;
+    DeviceGuard guard(r->device);
+    st = ensureResources(r, r->mono, false);
+    if (st != GSM_OK) return st;  // the reference returns silently here (DFR.swift:189); we report
+    Resources& res = r->mono;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
+    r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = false;
+
+    recordStage(r, s, 0);
+    // step 0: reset state + counters (DFR.swift:259-272)
+    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    // step 1 + 1.25 + 1.5
+    MonoCam mc;
+    fillMonoCam(mc, camera, gaussianCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
+    ProjectOut po;
+    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians;
+    po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
+    GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
+    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
+    recordStage(r, s, 1);
+    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);
+    if (st != GSM_OK) return st;
+    // step 8: clear + blend (DFR.swift:433-464), fused
+    GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, 0, tilesY,
+                             (__half*)color, (__half*)depth), "blend");
+    recordStage(r, s, 7);
+    recordStage(r, s, 8);
+    if (r->profiling) r->evRecorded = true;
+    return GSM_OK;
+}
+
+gsm_status gsm_render_stereo(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians, const void* harmonics,
+                             uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* leftEye, const gsm_camera* rightEye,
+                             uint32_t width, uint32_t height) {
+    if (!r || !leftEye || !rightEye) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;  // DFR.swift:478,607
+    gsm_status st = validateFrame(r, width, height, gaussians, harmonics, colorSideBySide);
+    if (st != GSM_OK) return st;
+    DeviceGuard guard(r->device);
+    st = ensureResources(r, r->stereoRes, true);
+    if (st != GSM_OK) return st;
+    Resources& res = r->stereoRes;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
+    r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = true;
+
+    recordStage(r, s, 0);
+    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    // makeStereoCameraUniforms (DFR.swift:554-591): near/far from the left eye, sceneTransform = identity for sideBySide
+    StereoCam sc;
+    memcpy(sc.leftView, leftEye->viewMatrix, 64); memcpy(sc.leftProj, leftEye->projectionMatrix, 64);
+    memcpy(sc.leftCenter, leftEye->position, 12);
+    memcpy(sc.rightView, rightEye->viewMatrix, 64); memcpy(sc.rightProj, rightEye->projectionMatrix, 64);
+    memcpy(sc.rightCenter, rightEye->position, 12);
+    memset(sc.sceneTransform, 0, 64);
+    sc.sceneTransform[0] = sc.sceneTransform[5] = sc.sceneTransform[10] = sc.sceneTransform[15] = 1.0f;
+    sc.width = (float)width; sc.height = (float)height;
+    sc.nearPlane = leftEye->nearPlane; sc.farPlane = leftEye->farPlane;
+    sc.shComponents = shComponents; sc.gaussianCount = gaussianCount;
+    sc.inputIsSRGB = r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB ? 1.0f : 0.0f;
+    sc.tilesX = tilesX; sc.tilesY = tilesY;
+    ProjectOut po;
+    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians;
+    po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
+    GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
+    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
+    recordStage(r, s, 1);
+    st = encodeSortExpandRange(r, res, s, true, tilesX, tilesY);
+    if (st != GSM_OK) return st;
+    // steps 9+10: clear, blend both eyes, copy into the side-by-side target (DFR.swift:789-830), fused
+    GSM_CUDA(launchBlendStereo(s, res.lowerBounds, (const GSMStereoTiledRenderData*)res.renderData, res.instIdx[0], width, height,
+                               tilesX, tilesY, (__half*)colorSideBySide, nullptr, r->cfg.stereoCopyFlipY ? 1 : 0), "stereo blend");
+    recordStage(r, s, 7);
+    recordStage(r, s, 8);
+    if (r->profiling) r->evRecorded = true;
+    return GSM_OK;
+}
+
+gsm_status gsm_render_host(gsm_renderer* r, const void* hostGaussians, const void* hostHarmonics, uint32_t gaussianCount,
+                           uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height, void* hostColor,
+                           void* hostDepth) {
+    if (!r || !camera || !hostGaussians || !hostHarmonics || !hostColor) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;
+    if (width == 0 || height == 0 || width > r->cfg.maxWidth || height > r->cfg.maxHeight)
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "dimensions exceed RendererConfig.maxWidth/maxHeight");
+    DeviceGuard guard(r->device);
+    const bool half = r->cfg.precision == GSM_PRECISION_FLOAT16;
+    const int deg = shDegreeFromComponents(shComponents);
+    const size_t k = deg == 0 ? 1 : (deg == 1 ? 4 : (deg == 2 ? 9 : 16));
+    const size_t gBytes = (size_t)gaussianCount * (half ? 32 : 48);
+    const size_t hBytes = (size_t)gaussianCount * 3 * k * (half ? 2 : 4);
+    const size_t cBytes = (size_t)width * height * 8, dBytes = (size_t)width * height * 2;
+    auto ensure = [&](void*& p, size_t& have, size_t need) -> cudaError_t {
+        if (have >= need) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; have = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) have = need;
+        return e;
+    };
+    if (!r->hostStream) GSM_CUDA(cudaStreamCreateWithFlags(&r->hostStream, cudaStreamNonBlocking), "stream create");
+    GSM_CUDA(ensure(r->stGaussians, r->stGaussiansBytes, gBytes), "staging alloc");
+    GSM_CUDA(ensure(r->stHarmonics, r->stHarmonicsBytes, hBytes), "staging alloc");
+    GSM_CUDA(ensure(r->stColor, r->stColorBytes, cBytes), "staging alloc");
+    if (hostDepth) GSM_CUDA(ensure(r->stDepth, r->stDepthBytes, dBytes), "staging alloc");
+    cudaStream_t s = r->hostStream;
+    GSM_CUDA(cudaMemcpyAsync(r->stGaussians, hostGaussians, gBytes, cudaMemcpyHostToDevice, s), "H2D gaussians");
+    GSM_CUDA(cudaMemcpyAsync(r->stHarmonics, hostHarmonics, hBytes, cudaMemcpyHostToDevice, s), "H2D harmonics");
+    gsm_status st = gsm_render(r, s, r->stColor, hostDepth ? r->stDepth : nullptr, r->stGaussians, r->stHarmonics, gaussianCount,
+                               shComponents, camera, width, height);
+    if (st != GSM_OK) return st;
+    GSM_CUDA(cudaMemcpyAsync(hostColor, r->stColor, cBytes, cudaMemcpyDeviceToHost, s), "D2H colour");
+    if (hostDepth) GSM_CUDA(cudaMemcpyAsync(hostDepth, r->stDepth, dBytes, cudaMemcpyDeviceToHost, s), "D2H depth");
+    GSM_CUDA(cudaStreamSynchronize(s), "stream sync");
+    return GSM_OK;
+}
+
+gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussians, const void* harmonics, uint32_t gidFirst,
+                             uint32_t gidCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height,
+                             void* recordsOut, uint32_t* hostCount) {
+    if (!r || !camera || !recordsOut || !hostCount) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    *hostCount = 0;
+    if (gidCount == 0) return GSM_OK;
+    if ((uint64_t)gidFirst + gidCount > r->cfg.maxGaussians) return fail(GSM_ERR_INVALID_GAUSSIAN_COUNT, "gid range exceeds maxGaussians");
+    gsm_status st = validateFrame(r, width, height, gaussians, harmonics, recordsOut);
+    if (st != GSM_OK) return st;
+    DeviceGuard guard(r->device);
+    st = ensureResources(r, r->mono, false);
+    if (st != GSM_OK) return st;
+    Resources& res = r->mono;
+    cudaStream_t s = (cudaStream_t)stream;
+    r->lastStereo = false;
+    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    MonoCam mc;
+    fillMonoCam(mc, camera, gidCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
+    ProjectOut po;
+    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians;
+    po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
+    GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "strip project+cull");
+    GSM_CUDA(launchPackRecords(s, res.fs, res.depthKeys[0], res.primIdx[0], res.renderData, res.bounds, res.nTouched, recordsOut,
+                               gidCount, r->numSMs), "pack records");
+    GSM_CUDA(cudaMemcpyAsync(hostCount, &res.fs->visibleCountRaw, 4, cudaMemcpyDeviceToHost, s), "count readback");
+    GSM_CUDA(cudaStreamSynchronize(s), "strip project sync");
+    return GSM_OK;
+}
+
+gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* depth, const void* records, uint32_t recordCount,
+                            uint32_t width, uint32_t height, uint32_t tileRowFirst, uint32_t tileRowCount) {
+    if (!r || !color || (!records && recordCount)) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (recordCount > r->cfg.maxGaussians) return fail(GSM_ERR_INVALID_GAUSSIAN_COUNT, "record count exceeds maxGaussians");
+    if (width == 0 || height == 0 || width > r->cfg.maxWidth || height > r->cfg.maxHeight)
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "dimensions exceed RendererConfig.maxWidth/maxHeight");
+    const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
+    if (tileRowFirst > tilesY || tileRowCount > tilesY - tileRowFirst) return fail(GSM_ERR_INVALID_ARGUMENT, "tile rows out of range");
+    DeviceGuard guard(r->device);
+    gsm_status st = ensureResources(r, r->mono, false);
+    if (st != GSM_OK) return st;
+    Resources& res = r->mono;
+    cudaStream_t s = (cudaStream_t)stream;
+    r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = false;
+    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    ProjectOut po;
+    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.depthKey16 = 0; po.gidFirst = 0;
+    GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po), "ingest records");
+    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
+    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);
+    if (st != GSM_OK) return st;
+    GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
+                             tileRowCount, (__half*)color, (__half*)depth), "strip blend");
+    return GSM_OK;
+}
+
+double gsm_last_gpu_time_ms(gsm_renderer* r) {
+    if (!r || !r->profiling || !r->evRecorded) return -1.0;
+    float ms[GSM_NUM_STAGES];
+    if (gsm_get_stage_times_ms(r, ms) != GSM_OK) return -1.0;
+    return r->lastMs;
+}
+
+gsm_status gsm_set_profiling(gsm_renderer* r, int enabled) {
+    if (!r) return fail(GSM_ERR_INVALID_ARGUMENT, "null renderer");
+    DeviceGuard guard(r->device);
+    if (enabled && !r->evValid) {
+        for (auto& e : r->ev) GSM_CUDA(cudaEventCreate(&e), "event create");
+        r->evValid = true;
+    }
+    r->profiling = enabled != 0;
+    r->evRecorded = false;
+    return GSM_OK;
+}
+
+gsm_status gsm_get_stage_times_ms(gsm_renderer* r, float* ms) {
+    if (!r || !ms) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!r->profiling || !r->evRecorded) return fail(GSM_ERR_INVALID_ARGUMENT, "profiling is off or no frame recorded");
+    DeviceGuard guard(r->device);
+    GSM_CUDA(cudaEventSynchronize(r->ev[GSM_NUM_STAGES]), "event sync");
+    double total = 0;
+    for (int i = 0; i < GSM_NUM_STAGES; ++i) {
+        float t = 0;
+        GSM_CUDA(cudaEventElapsedTime(&t, r->ev[i], r->ev[i + 1]), "event elapsed");
+        ms[i] = r->stageMs[i] = t;
+        total += t;
+    }
+    r->lastMs = total;
+    return GSM_OK;
+}
+
+const char* gsm_stage_name(int stage) {
+    static const char* names[GSM_NUM_STAGES] = {"project", "depthSort", "applyScan", "expand", "tileSort", "ranges", "blend", "copy"};
+    return (stage >= 0 && stage < GSM_NUM_STAGES) ? names[stage] : "";
+}
+
+size_t gsm_debug_element_size(gsm_renderer* r, int which) {
+    if (!r) return 0;
+    const bool tile16 = r->cfg.tileIdPrecision == GSM_KEY_BITS16;
+    switch (which) {
+        case GSM_DBG_HEADER: return sizeof(GSMDepthFirstHeader);
+        case GSM_DBG_ACTIVE_TILE_COUNT: return 4;
+        case GSM_DBG_SORTED_TILE_IDS: return tile16 ? 2 : 4;
+        case GSM_DBG_TILE_BOUNDS: return 16;
+        case GSM_DBG_RENDER_DATA: return r->lastStereo ? 32 : 16;
+        case GSM_DBG_TILE_HEADERS: return 8;
+        case GSM_DBG_SORTED_PRIMITIVE_INDICES: case GSM_DBG_INSTANCE_OFFSETS: case GSM_DBG_N_TOUCHED_TILES:
+        case GSM_DBG_INSTANCE_GAUSSIAN_INDICES: case GSM_DBG_DEPTH_KEYS: case GSM_DBG_ACTIVE_TILES:
+        case GSM_DBG_SCRATCH_DEPTH_KEYS: case GSM_DBG_SCRATCH_PRIMITIVE_INDICES: return 4;
+        default: return 0;
+    }
+}
+
+gsm_status gsm_debug_read(gsm_renderer* r, void* stream, int which, void* dst, size_t first, size_t count) {
+    if (!r || !dst) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    Resources& res = r->lastStereo ? r->stereoRes : r->mono;
+    if (!res.arena) return fail(GSM_ERR_INVALID_ARGUMENT, "no frame has been rendered");
+    DeviceGuard guard(r->device);
+    const char* src = nullptr;
+    size_t cap = 0;
+    const size_t es = gsm_debug_element_size(r, which);
+    switch (which) {
+        case GSM_DBG_HEADER: src = (const char*)res.header; cap = 1; break;
+        case GSM_DBG_ACTIVE_TILE_COUNT: src = (const char*)&res.fs->activeTileCount; cap = 1; break;
+        case GSM_DBG_SORTED_TILE_IDS: src = (const char*)res.tileIds[0]; cap = res.maxInstances; break;
+        case GSM_DBG_TILE_BOUNDS: src = (const char*)res.bounds; cap = res.maxGaussians; break;
+        case GSM_DBG_SORTED_PRIMITIVE_INDICES: src = (const char*)res.primIdx[0]; cap = res.maxGaussians; break;
+        case GSM_DBG_INSTANCE_OFFSETS: src = (const char*)res.offsets; cap = res.maxGaussians; break;
+        case GSM_DBG_N_TOUCHED_TILES: src = (const char*)res.nTouched; cap = res.maxGaussians; break;
+        case GSM_DBG_INSTANCE_GAUSSIAN_INDICES: src = (const char*)res.instIdx[0]; cap = res.maxInstances; break;
+        case GSM_DBG_DEPTH_KEYS: src = (const char*)res.depthKeys[0]; cap = res.maxGaussians; break;
+        case GSM_DBG_RENDER_DATA: src = (const char*)res.renderData; cap = res.maxGaussians; break;
+        case GSM_DBG_TILE_HEADERS: src = (const char*)res.tileHeaders; cap = res.maxTiles; break;
+        case GSM_DBG_ACTIVE_TILES: src = (const char*)res.activeTiles; cap = res.maxTiles; break;
+        case GSM_DBG_SCRATCH_DEPTH_KEYS: src = (const char*)res.depthKeys[1]; cap = res.maxGaussians; break;
+        case GSM_DBG_SCRATCH_PRIMITIVE_INDICES: src = (const char*)res.primIdx[1]; cap = res.maxGaussians; break;
+        default: return fail(GSM_ERR_INVALID_ARGUMENT, "unknown debug buffer");
+    }
+    if (first > cap || count > cap - first) return fail(GSM_ERR_INVALID_ARGUMENT, "debug read out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    GSM_CUDA(cudaMemcpyAsync(dst, src + first * es, count * es, cudaMemcpyDeviceToHost, s), "debug read");
+    GSM_CUDA(cudaStreamSynchronize(s), "debug read sync");
+    return GSM_OK;
+}
+
+gsm_status gsm_buffer_alloc(int device, size_t bytes, void** out) {
+    if (!out) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (device < 0) cudaGetDevice(&device);
+    DeviceGuard guard(device);
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "cudaMalloc", e);
+    return GSM_OK;
+}
+gsm_status gsm_buffer_free(void* p) {
+    if (p) GSM_CUDA(cudaFree(p), "cudaFree");
+    return GSM_OK;
+}
+gsm_status gsm_buffer_upload(void* dst, const void* src, size_t bytes, void* stream) {
+    GSM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "upload");
+    return GSM_OK;
+}
+gsm_status gsm_buffer_download(void* dst, const void* src, size_t bytes, void* stream) {
+    GSM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "download");
+    GSM_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "download sync");
+    return GSM_OK;
+}
+gsm_status gsm_stream_create(int device, void** out) {
+    if (!out) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (device < 0) cudaGetDevice(&device);
+    DeviceGuard guard(device);
+    cudaStream_t s;
+    GSM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "stream create");
+    *out = (void*)s;
+    return GSM_OK;
+}
+gsm_status gsm_stream_synchronize(void* stream) {
+    GSM_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "stream sync");
+    return GSM_OK;
+}
+gsm_status gsm_stream_destroy(void* stream) {
+    GSM_CUDA(cudaStreamDestroy((cudaStream_t)stream), "stream destroy");
+    return GSM_OK;
+}
+
+gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* payload, uint32_t count, int keyBits, int numPasses) {
+    if (!r || !keys || !payload) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if ((keyBits != 16 && keyBits != 32) || numPasses < 1 || numPasses > keyBits / 8) return fail(GSM_ERR_INVALID_ARGUMENT, "bad key width / pass count");
+    if (count == 0) return GSM_OK;
+    DeviceGuard guard(r->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t tile = sortTileSize(keyBits);
+    const uint32_t tiles = (count + tile - 1) / tile;
+    const size_t keyBytes = (size_t)count * (keyBits / 8);
+    // scratch: [count u32][hist 4*256][tickets 4][status passes*tiles*256][k1][v1]
+    const size_t oHist = 256, oTickets = oHist + 4 * 256 * 4, oStatus = alignUp(oTickets + 16, 256);
+    const size_t oK1 = alignUp(oStatus + (size_t)numPasses * tiles * 256 * 4, 256), oV1 = alignUp(oK1 + keyBytes, 256);
+    const size_t total = oV1 + (size_t)count * 4;
+    char* scratch = nullptr;
+    cudaError_t e = cudaMalloc((void**)&scratch, total);
+    if (e != cudaSuccess) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "sort scratch", e);
+    gsm_status st = GSM_OK;
+    do {
+        if ((e = cudaMemsetAsync(scratch, 0, oK1, s)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(scratch, &count, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+        SortPlan p;
+        p.k0 = keys; p.k1 = scratch + oK1; p.v0 = (uint32_t*)payload; p.v1 = (uint32_t*)(scratch + oV1);
+        p.countPtr = (const uint32_t*)scratch; p.countCap = count;
+        p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.tickets = (uint32_t*)(scratch + oTickets);
+        p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = r->numSMs;
+        if ((e = launchSort(s, p)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(s);
+    } while (false);
+    if (e != cudaSuccess) st = fail(GSM_ERR_RENDER_FAILED, "gsm_sort_pairs", e);
+    cudaFree(scratch);
+    return st;
+}
+
+gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void* out, uint32_t n) {
+    if (!a || !out || n == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (device < 0) cudaGetDevice(&device);
+    DeviceGuard guard(device);
+    const size_t inEl = (op == 5 || op == 7) ? 2 : 4, outEl = (op == 5 || op == 6 || op == 7) ? 2 : 4;
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    gsm_status st = GSM_OK;
+    cudaError_t e;
+    do {
+        if ((e = cudaMalloc(&da, n * inEl)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&dout, n * outEl)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(da, a, n * inEl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (b) {
+            if ((e = cudaMalloc(&db, n * inEl)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(db, b, n * inEl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        }
+        if ((e = launchProbe(nullptr, op, da, db, dout, n)) != cudaSuccess) break;
+        e = cudaMemcpy(out, dout, n * outEl, cudaMemcpyDeviceToHost);
+    } while (false);
+    if (e != cudaSuccess) st = fail(GSM_ERR_RENDER_FAILED, "gsm_probe_math", e);
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return st;
+}
+
+const char* gsm_status_string(gsm_status s) {
+    switch (s) {
+        case GSM_OK: return "ok";
+        case GSM_ERR_DEVICE_NOT_AVAILABLE: return "CUDA device not available";
+        case GSM_ERR_FAILED_TO_CREATE_PIPELINE: return "failed to create pipeline";
+        case GSM_ERR_FAILED_TO_ALLOCATE_BUFFER: return "failed to allocate buffer";
+        case GSM_ERR_INVALID_GAUSSIAN_COUNT: return "Gaussian count exceeds maximum";
+        case GSM_ERR_INVALID_DIMENSIONS: return "dimensions exceed maximum";
+        case GSM_ERR_INVALID_TILE_COUNT: return "tile count exceeds maximum";
+        case GSM_ERR_RENDER_FAILED: return "render failed";
+        case GSM_ERR_INVALID_ARGUMENT: return "invalid argument";
+    }
+    return "unknown";
+}
+const char* gsm_last_error_string(void) { return g_lastError.c_str(); }
+int gsm_abi_version(void) { return GSM_ABI_VERSION; }
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// gsm_common.cuh -- shared device-side declarations of the DepthFirst path (internal; the public
+// boundary is include/gsm/gsm.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsm/gsm.h"
+#include "../../include/gsm/gsm_types.h"
+
+namespace gsm {
+
+constexpr int kTile = 16;               // DFR.swift:8-9
+constexpr float kAlphaThreshold = 0.005f;   // GlobalRenderer.swift:66
+constexpr float kTotalInkThreshold = 2.0f;  // GlobalRenderer.swift:67
+constexpr uint32_t kRadixAlignment = 1024;  // radixBlockSize*radixGrainSize, DFR.swift:40-41
+
+// Per-frame device state, zeroed by one memset at the start of every frame (replaces
+// resetDepthFirstStateKernel DFS.metal:1372 + the ClearCounters blit DFR.swift:267-272).
+struct FrameState {
+    uint32_t visibleCountRaw;    // written by the last project tile (visibilityScatterCompact, DFS.metal:618-620)
+    uint32_t totalInstancesRaw;  // atomic sum of nTouched (DFS.metal:218)
+    uint32_t activeTileCount;    // DFS.metal:1310
+    uint32_t ticketProject;      // dynamic tile ids => look-back forward progress
+    uint32_t ticketScan;
+    uint32_t ticketSort[8];      // depth passes 0-3, tile passes 4-7
+    uint32_t _pad[3];
+    uint32_t hist[8][256];       // global digit histograms: depth passes 0-3, tile passes 4-7
+};
+
+// What the blend stage reads per splat: the quantised record pre-expanded once per visible Gaussian
+// (conic from conicFromThetaSigmas GaussianShared.h:490-510 rounded to half exactly as
+// DFS.metal:1753-1764 does per thread). 32 bytes = two 128-bit loads.
+struct __align__(16) BlendSplat {
+    __half2 mean;      // meanX, meanY
+    __half2 cxx_cyy;   // half(conic.x), half(conic.z)
+    __half2 cxy2_op;   // half(2*conic.y), half(opacity_u8)/255h
+    __half2 rg;        // colour R,G as half(u8)/255h
+    __half2 b_depth;   // colour B, depth
+    uint32_t valid;    // 1
+    uint32_t _pad[2];
+};
+static_assert(sizeof(BlendSplat) == 32, "BlendSplat is 32 bytes");
+
+// Camera constants as the kernels take them (by value, __grid_constant__).
+struct MonoCam {
+    float view[16];
+    float proj[16];
+    float center[3];
+    float width, height, nearPlane, farPlane;
+    uint32_t shComponents, gaussianCount;
+    float inputIsSRGB;
+    uint32_t tilesX, tilesY;
+};
+struct StereoCam {
+    float leftView[16], leftProj[16], leftCenter[3];
+    float rightView[16], rightProj[16], rightCenter[3];
+    float sceneTransform[16];
+    float width, height, nearPlane, farPlane;
+    uint32_t shComponents, gaussianCount;
+    float inputIsSRGB;
+    uint32_t tilesX, tilesY;
+};
+
+// 64-bit look-back word for single-value chained scans: flag in the high half, value in the low half.
+constexpr uint32_t kFlagAggregate = 1u, kFlagInclusive = 2u;
+
+__device__ __forceinline__ void st_status64(unsigned long long* p, uint32_t flag, uint32_t value) {
+    unsigned long long v = ((unsigned long long)flag << 32) | value;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_status64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_status32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Decoupled look-back over single-value tile aggregates, run by one full warp. Returns the exclusive
+// prefix of `tile` (sum of aggregates of tiles < tile) to every lane and publishes the inclusive value.
+__device__ __forceinline__ uint32_t lookback_exclusive(unsigned long long* status, uint32_t tile, uint32_t aggregate) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0) {
+        if (lane == 0) st_status64(&status[0], kFlagInclusive, aggregate);
+        return 0;
+    }
+    if (lane == 0) st_status64(&status[tile], kFlagAggregate, aggregate);
+    uint32_t exclusive = 0;
+    int look = (int)tile - 1;
+    while (true) {
+        int idx = look - (int)lane;
+        unsigned long long s = (idx >= 0) ? ld_status64(&status[idx]) : ((unsigned long long)kFlagInclusive << 32);
+        uint32_t flag = (uint32_t)(s >> 32);
+        // all lanes must have a published word before the window is consumed
+        if (__any_sync(0xFFFFFFFFu, flag == 0)) continue;
+        unsigned incl = __ballot_sync(0xFFFFFFFFu, flag == kFlagInclusive);
+        uint32_t v = (uint32_t)s;
+        if (incl) {
+            int first = __ffs(incl) - 1;  // nearest predecessor holding an inclusive prefix
+            uint32_t contrib = (lane <= (unsigned)first) ? v : 0u;
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
+            exclusive += contrib;
+            break;
+        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        exclusive += v;
+        look -= 32;
+    }
+    if (lane == 0) st_status64(&status[tile], kFlagInclusive, exclusive + aggregate);
+    return exclusive;
+}
+
+// exclusive scan of one value per thread over a 256-thread block; returns the exclusive prefix and
+// writes the block total. smem: 9 words.
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* smem9, uint32_t& total) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) smem9[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < 8) ? smem9[lane] : 0u;
+        uint32_t winc = w;
+        for (int o = 1; o < 8; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+            if (lane >= (unsigned)o) winc += t;
+        }
+        if (lane < 8) smem9[lane] = winc - w;
+        if (lane == 7) smem9[8] = winc;
+    }
+    __syncthreads();
+    uint32_t r = smem9[warp] + inc - v;
+    total = smem9[8];
+    __syncthreads();
+    return r;
+}
+
+}  // namespace gsm

@@ -1,0 +1,169 @@
+// gsm_dmath.cuh -- canonical transcendental definitions on the device.
+//
+// The reference's MSL built-ins (fast::sincos, log, atan2, exp(half), fast::powr, normalize) have no
+// specified bits (Metal -ffast-math, compile_shaders.sh:45-53), so tile counts can only be bit-exact
+// against a CPU checker if both sides evaluate ONE written-down definition. These are those definitions:
+// IEEE binary32 + - * / sqrt in a fixed order (this TU is compiled with -fmad=false, default
+// -prec-div/-prec-sqrt/-ftz=false), explicit __fmaf_rn where stated, fixed polynomial coefficients
+// (Cephes single-precision sets; degree-5 Chebyshev fit for 2^f). No libdevice transcendental is called.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace gsm {
+
+#define GSM_PI_F 3.14159265358979323846f            // kPiF, GaussianShared.h:432
+#define GSM_THETA_PACK 0x1.45f1c0p+14f              // binary32(65535.0f / kPiF), GaussianShared.h:438
+#define GSM_THETA_UNPACK 0x1.922148p-15f            // binary32(kPiF / 65535.0f), GaussianShared.h:443
+
+__device__ __forceinline__ float dmax(float a, float b) {  // NaN operand loses; ties return b
+    if (a != a) return b;
+    if (b != b) return a;
+    return (a > b) ? a : b;
+}
+__device__ __forceinline__ float dmin(float a, float b) {
+    if (a != a) return b;
+    if (b != b) return a;
+    return (a < b) ? a : b;
+}
+__device__ __forceinline__ float dclamp(float x, float lo, float hi) { return dmin(dmax(x, lo), hi); }
+__device__ __forceinline__ bool dfinite(float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
+
+// fast::sincos (GaussianShared.h:495,571)
+__device__ __forceinline__ void dsincos(float x, float& sn, float& cs) {
+    float ax = fabsf(x);
+    float kf = floorf(ax * 0.636619772367581343f + 0.5f);
+    int k = (int)kf;
+    float r = ax - kf * 1.5703125f;
+    r = r - kf * 4.837512969970703125e-4f;
+    r = r - kf * 7.54978995489188216e-8f;
+    float z = r * r;
+    float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z
+               - 0.5f * z + 1.0f;
+    float s, c;
+    switch (k & 3) {
+        case 0: s = ps; c = pc; break;
+        case 1: s = pc; c = -ps; break;
+        case 2: s = -ps; c = -pc; break;
+        default: s = -pc; c = ps; break;
+    }
+    if (x < 0.0f) s = -s;
+    sn = s;
+    cs = c;
+}
+
+// log (GaussianShared.h:592)
+__device__ __forceinline__ float dlog(float x) {
+    uint32_t u = __float_as_uint(x);
+    int e = (int)((u >> 23) & 0xFFu) - 126;
+    float m = __uint_as_float((u & 0x807FFFFFu) | 0x3F000000u);
+    if (m < 0.707106781186547524f) {
+        e -= 1;
+        m = m + m - 1.0f;
+    } else {
+        m = m - 1.0f;
+    }
+    float z = m * m;
+    float y = ((((((((7.0376836292e-2f * m - 1.1514610310e-1f) * m + 1.1676998740e-1f) * m
+                    - 1.2420140846e-1f) * m + 1.4249322787e-1f) * m - 1.6668057665e-1f) * m
+                 + 2.0000714765e-1f) * m - 2.4999993993e-1f) * m + 3.3333331174e-1f) * m * z;
+    float fe = (float)e;
+    y = y + -2.12194440e-4f * fe;
+    y = y + -0.5f * z;
+    z = m + y;
+    z = z + 0.693359375f * fe;
+    return z;
+}
+
+__device__ __forceinline__ float dexp(float x) {
+    float n = floorf(1.44269504088896341f * x + 0.5f);
+    x = x - n * 0.693359375f;
+    x = x - n * -2.12194440e-4f;
+    float z = x * x;
+    z = (((((1.9875691500e-4f * x + 1.3981999507e-3f) * x + 8.3334519073e-3f) * x
+           + 4.1665795894e-2f) * x + 1.6666665459e-1f) * x + 5.0000001201e-1f) * z + x + 1.0f;
+    int ni = (int)n;
+    return __uint_as_float(__float_as_uint(z) + ((uint32_t)ni << 23));
+}
+
+// fast::powr (GaussianShared.h:120)
+__device__ __forceinline__ float dpowr(float x, float y) { return dexp(y * dlog(x)); }
+
+__device__ __forceinline__ float datan(float t) {
+    float at = fabsf(t);
+    float y0, u;
+    if (at > 2.414213562373095f) {
+        y0 = 1.5707963267948966f;
+        u = -(1.0f / at);
+    } else if (at > 0.4142135623730950f) {
+        y0 = 0.7853981633974483f;
+        u = (at - 1.0f) / (at + 1.0f);
+    } else {
+        y0 = 0.0f;
+        u = at;
+    }
+    float z = u * u;
+    float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z
+               - 3.33329491539e-1f) * z * u + u;
+    float r = y0 + p;
+    return (t < 0.0f) ? -r : r;
+}
+
+// atan2 (GaussianShared.h:479)
+__device__ __forceinline__ float datan2(float y, float x) {
+    if (x != x || y != y) return __uint_as_float(0x7FC00000u);
+    if (x == 0.0f) {
+        if (y > 0.0f) return 1.5707963267948966f;
+        if (y < 0.0f) return -1.5707963267948966f;
+        return 0.0f;
+    }
+    float a = datan(y / x);
+    if (x < 0.0f) {
+        if (y < 0.0f) return a - GSM_PI_F;
+        return a + GSM_PI_F;
+    }
+    return a;
+}
+
+// fmod(t, kPiF) (GaussianShared.h:436,481)
+__device__ __forceinline__ float dfmod_pi(float t) {
+    if (!dfinite(t)) return __uint_as_float(0x7FC00000u);
+    float a = fabsf(t);
+    while (a >= GSM_PI_F) a = a - GSM_PI_F;
+    return (t < 0.0f) ? -a : a;
+}
+
+// exp(half) -> half for one lane, evaluated in binary32 (DepthFirstShaders.metal:1775).
+__device__ __forceinline__ float dhexp_f32(float x) {  // x is an exact half value; returns the binary32 pre-rounding value
+    float xc = fminf(fmaxf(x, -17.5f), 11.5f);         // keeps the integer trick in range; selects below fix the ends
+    float t = xc * 1.44269504088896341f;
+    float zb = t + 12582912.0f;
+    float n = zb - 12582912.0f;
+    float f = t - n;
+    float p = 0x1.5f0890p-10f;
+    p = __fmaf_rn(p, f, 0x1.3d1070p-7f);
+    p = __fmaf_rn(p, f, 0x1.c6af6cp-5f);
+    p = __fmaf_rn(p, f, 0x1.ebf906p-3f);
+    p = __fmaf_rn(p, f, 0x1.62e430p-1f);
+    p = __fmaf_rn(p, f, 0x1.000002p+0f);
+    float r = __uint_as_float(__float_as_uint(p) + (__float_as_uint(zb) << 23));
+    r = (x < -17.5f) ? 0.0f : r;
+    r = (x > 11.5f) ? __uint_as_float(0x7F800000u) : r;
+    return r;
+}
+__device__ __forceinline__ __half dhexp(__half xh) {
+    if (__hisnan(xh)) return __ushort_as_half((unsigned short)0x7FFFu);
+    return __float2half_rn(dhexp_f32(__half2float(xh)));
+}
+__device__ __forceinline__ __half2 dhexp2(__half2 x) {
+    float2 xf = __half22float2(x);
+    float rx = dhexp_f32(xf.x), ry = dhexp_f32(xf.y);
+    __half2 r = __floats2half2_rn(rx, ry);
+    // NaN lanes: canonical 0x7FFF
+    if (xf.x != xf.x) r = __halves2half2(__ushort_as_half((unsigned short)0x7FFFu), __high2half(r));
+    if (xf.y != xf.y) r = __halves2half2(__low2half(r), __ushort_as_half((unsigned short)0x7FFFu));
+    return r;
+}
+
+}  // namespace gsm

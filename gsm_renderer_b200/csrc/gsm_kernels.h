@@ -1,0 +1,74 @@
+// gsm_kernels.h -- host-callable launchers of the stage kernels (internal).
+#pragma once
+#include "gsm_common.cuh"
+
+namespace gsm {
+
+struct ProjectOut {
+    FrameState* fs;
+    unsigned long long* status;   // look-back words, one per 256-Gaussian tile
+    void* renderData;             // GSMGaussianRenderData[] or GSMStereoTiledRenderData[]
+    int32_t* bounds;              // int4 per Gaussian
+    uint32_t* nTouched;
+    BlendSplat* blendSplats;      // mono only (may be null)
+    uint32_t* depthKeys;          // compacted, ascending gid
+    int32_t* primitiveIndices;
+    uint32_t maxOut;
+    uint32_t depthKey16;
+    uint32_t gidFirst;
+};
+
+int shDegreeFromComponents(uint32_t n);
+const void* finalize_header_probe();  // a kernel symbol, to test that the sm_100a image loads
+cudaError_t launchProjectMono(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam, const ProjectOut& o);
+cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, const void* h, const StereoCam& cam, const ProjectOut& o);
+cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians, uint32_t maxInstances);
+
+// Onesweep radix sort (sort.cu). keys/vals ping-pong between (k0,v0) and (k1,v1); after numPasses the
+// result is in (k0,v0) if numPasses is even, else it is copied back. countPtr is read on the device.
+struct SortPlan {
+    void* k0; void* k1; uint32_t* v0; uint32_t* v1;
+    const uint32_t* countPtr; uint32_t countCap;
+    uint32_t* hist;      // [numPasses][256] zeroed
+    uint32_t* status;    // [numPasses][tilesCap][256] zeroed
+    uint32_t* tickets;   // [numPasses] zeroed
+    uint32_t tilesCap;
+    int keyBits;         // 16 or 32
+    int numPasses;
+    int numSMs;
+};
+uint32_t sortTileSize(int keyBits);
+cudaError_t launchSort(cudaStream_t s, const SortPlan& p);
+
+// apply depth order + exclusive scan (scan.cu)
+cudaError_t launchApplyOrderScan(cudaStream_t s, const int32_t* sortedIdx, const uint32_t* nTouched, uint32_t* offsetsOut,
+                                 const GSMDepthFirstHeader* header, unsigned long long* status, uint32_t* ticket, int numSMs);
+
+// instance expansion (expand.cu)
+cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* offsets,
+                                  const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
+                                  const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible);
+
+// tile ranges (ranges.cu)
+cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,
+                             uint32_t tileCount, uint32_t* lowerBounds, GSMGaussianHeader* tileHeaders, uint32_t* activeTiles,
+                             uint32_t* activeTileCount, int numSMs);
+
+// blend (blend.cu)
+cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,
+                            uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY, uint32_t tileRowFirst,
+                            uint32_t tileRowCount, __half* color, __half* depth);
+cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
+                              const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
+                              __half* dstSideBySide, __half* intermediate, int flipY);
+
+// strip-sharded frame (strip.cu)
+cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,
+                              const int32_t* bounds, const uint32_t* nTouched, void* out, uint32_t cap, int numSMs);
+cudaError_t launchIngestRecords(cudaStream_t s, const void* records, uint32_t recordCount, uint32_t rowFirst, uint32_t rowCount,
+                                const ProjectOut& o);
+
+// math probes (probe.cu)
+cudaError_t launchProbe(cudaStream_t s, int op, const void* a, const void* b, void* out, uint32_t n);
+
+}  // namespace gsm

@@ -1,0 +1,40 @@
+// probe.cu -- runs the device restatement of the canonical math definitions over arrays so tests can
+// compare it bit-for-bit with the CPU oracle (gsm_probe_math in include/gsm/gsm.h).
+#include "gsm_common.cuh"
+#include "gsm_dmath.cuh"
+#include "gsm_kernels.h"
+
+namespace gsm {
+
+__global__ void probe_kernel(int op, const void* a, const void* b, void* out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* fa = (const float*)a;
+    const float* fb = (const float*)b;
+    float* fo = (float*)out;
+    switch (op) {
+        case 0: { float s, c; dsincos(fa[i], s, c); fo[i] = s; break; }
+        case 1: { float s, c; dsincos(fa[i], s, c); fo[i] = c; break; }
+        case 2: fo[i] = dlog(fa[i]); break;
+        case 3: fo[i] = datan2(fa[i], fb[i]); break;
+        case 4: fo[i] = dpowr(fa[i], 2.4f); break;
+        case 5: ((unsigned short*)out)[i] = __half_as_ushort(dhexp(__ushort_as_half(((const unsigned short*)a)[i]))); break;
+        case 6: ((unsigned short*)out)[i] = __half_as_ushort(__float2half_rn(fa[i])); break;
+        case 7: {  // packed variant used by the blend kernel: lanes (x[i], x[i^1])
+            const unsigned short* ha = (const unsigned short*)a;
+            __half2 v = __halves2half2(__ushort_as_half(ha[i]), __ushort_as_half(ha[i ^ 1u]));
+            ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2(v)));
+            break;
+        }
+        default: break;
+    }
+}
+
+cudaError_t launchProbe(cudaStream_t s, int op, const void* a, const void* b, void* out, uint32_t n) {
+    probe_kernel<<<(n + 255) / 256, 256, 0, s>>>(op, a, b, out, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);
+}
+
+}  // namespace gsm

@@ -1,0 +1,226 @@
+// sort.cu -- stable LSD radix sort of (key, payload) pairs, 8-bit digits, Onesweep style:
+// one pass over the keys builds every digit histogram, then each digit pass is ONE kernel that ranks a
+// tile with warp match-any, resolves its global bin bases by decoupled look-back (one thread per digit)
+// and scatters through shared memory. Persistent CTAs take tiles from an atomic ticket so a tile's
+// predecessors are always resident (forward progress) and the grid does not depend on the device-side
+// count.
+//
+// Replaces the reference's 5-kernels-per-pass sorts: depthSort* (DFS.metal:1387-1696, driver
+// DepthRadixSortEncoder.swift:139-217) and tileRadix* (DFS.metal:866-1256, driver TileSortEncoder.swift:51-178).
+// Semantics kept: stable, ascending, first `count` elements, digit = (key >> 8p) & 0xFF
+// (RadixSortHelpers.h:85-88). Stability argument: a tile ranks its elements in index order (warp-major,
+// then item, then lane == ascending index) and tiles are prefixed in tile order.
+#include "gsm_common.cuh"
+#include "gsm_kernels.h"
+
+namespace gsm {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr uint32_t kStatusValueMask = 0x3FFFFFFFu;
+constexpr uint32_t kStatusAggregate = 0x40000000u;
+constexpr uint32_t kStatusInclusive = 0x80000000u;
+
+template <typename KeyT> struct SortCfg;
+template <> struct SortCfg<uint32_t> { static constexpr int ITEMS = 8; };   // 2048 keys / tile
+template <> struct SortCfg<uint16_t> { static constexpr int ITEMS = 16; };  // 4096 keys / tile
+
+uint32_t sortTileSize(int keyBits) {
+    return keyBits == 16 ? kSortThreads * SortCfg<uint16_t>::ITEMS : kSortThreads * SortCfg<uint32_t>::ITEMS;
+}
+
+// ---- all digit histograms in one read of the keys
+template <typename KeyT, int NPASS>
+__global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ countPtr,
+                                                              uint32_t countCap, uint32_t* __restrict__ hist,
+                                                              uint32_t* __restrict__ status, uint32_t tilesCap) {
+    __shared__ uint32_t s_hist[NPASS][256];
+    for (int i = threadIdx.x; i < NPASS * 256; i += 256) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t count = min(*countPtr, countCap);
+    {   // reset the look-back words this frame's passes will use (sized by the device-side count, not the capacity)
+        constexpr uint32_t TILE = kSortThreads * SortCfg<KeyT>::ITEMS;
+        const uint32_t words = ((count + TILE - 1) / TILE) * 256u;
+        for (int p = 0; p < NPASS; ++p)
+            for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < words; i += gridDim.x * 256u)
+                status[(size_t)p * tilesCap * 256u + i] = 0u;
+    }
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < count; i += gridDim.x * 256u) {
+        uint32_t k = (uint32_t)keys[i];
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) atomicAdd(&s_hist[p][(k >> (8 * p)) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPASS * 256; i += 256) {
+        uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+
+// ---- one digit pass
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                                     KeyT* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
+                                                                     const uint32_t* __restrict__ countPtr, uint32_t countCap,
+                                                                     const uint32_t* __restrict__ digitHist, uint32_t* status,
+                                                                     uint32_t* ticket, int shift) {
+    constexpr int ITEMS = SortCfg<KeyT>::ITEMS;
+    constexpr int TILE = kSortThreads * ITEMS;
+    constexpr KeyT SENTINEL = (KeyT)~(KeyT)0;
+
+    __shared__ uint32_t s_warpHist[kSortWarps][256];
+    __shared__ uint32_t s_binExcl[256];     // tile-local exclusive offset of each digit
+    __shared__ uint32_t s_globalBase[256];  // global position of the tile's first element of each digit, minus s_binExcl
+    __shared__ uint32_t s_histPrefix[256];  // exclusive prefix of the global digit histogram
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_tile;
+    __shared__ KeyT s_keys[TILE];
+    __shared__ uint32_t s_vals[TILE];
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t count = min(*countPtr, countCap);
+    const uint32_t numTiles = (count + TILE - 1) / TILE;
+    {
+        uint32_t total;
+        uint32_t e = block_exclusive_scan_256(digitHist[tid], s_scan, total);
+        s_histPrefix[tid] = e;
+    }
+
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= numTiles) break;
+        const uint32_t base = tile * TILE;
+        const uint32_t tileValid = min((uint32_t)TILE, count - base);
+
+        for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
+        __syncthreads();
+
+        // warp-striped load: element (warp, item, lane) has index base + warp*ITEMS*32 + item*32 + lane
+        KeyT key[ITEMS];
+        uint32_t rank[ITEMS];
+        const uint32_t warpBase = warp * ITEMS * 32u + lane;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint32_t j = warpBase + i * 32u;
+            key[i] = (j < tileValid) ? keysIn[base + j] : SENTINEL;
+        }
+        // rank inside the warp, in index order
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint32_t d = ((uint32_t)key[i] >> shift) & 0xFFu;
+            unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+            uint32_t lower = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pre = s_warpHist[warp][d];
+            __syncwarp();
+            if (lower == 0) s_warpHist[warp][d] = pre + __popc(peers);
+            __syncwarp();
+            rank[i] = pre + lower;
+        }
+        __syncthreads();
+
+        // thread d: exclusive prefix over warps, tile count of digit d
+        uint32_t binCount = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            uint32_t c = s_warpHist[w][tid];
+            s_warpHist[w][tid] = binCount;
+            binCount += c;
+        }
+        // padding lanes carry the sentinel and sit at the END of the tile, hence at the end of their bin;
+        // they are not counted globally and never stored.
+        const uint32_t sentinelDigit = ((uint32_t)SENTINEL >> shift) & 0xFFu;
+        uint32_t validCount = binCount - ((tid == sentinelDigit) ? (TILE - tileValid) : 0u);
+
+        // decoupled look-back, one thread per digit
+        uint32_t* myStatus = status + (size_t)tile * 256u + tid;
+        uint32_t exclusive = 0;
+        if (tile == 0) {
+            st_status32(myStatus, kStatusInclusive | validCount);
+        } else {
+            st_status32(myStatus, kStatusAggregate | validCount);
+            const uint32_t* look = myStatus - 256;
+            while (true) {
+                uint32_t s = ld_status32(look);
+                if (s & kStatusInclusive) { exclusive += s & kStatusValueMask; break; }
+                if (s & kStatusAggregate) { exclusive += s & kStatusValueMask; look -= 256; }
+            }
+            st_status32(myStatus, kStatusInclusive | (exclusive + validCount));
+        }
+        uint32_t total;
+        uint32_t binExcl = block_exclusive_scan_256(binCount, s_scan, total);
+        s_binExcl[tid] = binExcl;
+        s_globalBase[tid] = s_histPrefix[tid] + exclusive - binExcl;
+        __syncthreads();
+
+        // scatter keys into tile order
+        uint32_t pos[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint32_t d = ((uint32_t)key[i] >> shift) & 0xFFu;
+            pos[i] = s_binExcl[d] + s_warpHist[warp][d] + rank[i];
+            s_keys[pos[i]] = key[i];
+        }
+        // payload of the same elements
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint32_t j = warpBase + i * 32u;
+            uint32_t v = (j < tileValid) ? valsIn[base + j] : 0u;
+            s_vals[pos[i]] = v;
+        }
+        __syncthreads();
+        // valid elements occupy tile positions [0, tileValid) except that sentinel padding sits at the end of
+        // the sentinel digit's bin; bins after it (none: the sentinel digit is 0xFF) would shift.
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            uint32_t j = tid + i * kSortThreads;
+            if (j < tileValid) {
+                KeyT k = s_keys[j];
+                uint32_t d = ((uint32_t)k >> shift) & 0xFFu;
+                uint32_t dst = s_globalBase[d] + j;
+                keysOut[dst] = k;
+                valsOut[dst] = s_vals[j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename KeyT>
+static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
+    if (p.numPasses <= 0) return cudaSuccess;
+    const int gridHist = p.numSMs * 4;
+    KeyT* k0 = (KeyT*)p.k0;
+    KeyT* k1 = (KeyT*)p.k1;
+    switch (p.numPasses) {
+        case 1: radix_histogram_kernel<KeyT, 1><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
+        case 2: radix_histogram_kernel<KeyT, 2><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
+        case 3: radix_histogram_kernel<KeyT, 3><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
+        default: radix_histogram_kernel<KeyT, 4><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
+    }
+    int blocksPerSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, onesweep_pass_kernel<KeyT>, kSortThreads, 0);
+    if (blocksPerSM < 1) blocksPerSM = 1;
+    const int grid = p.numSMs * blocksPerSM;  // every CTA is resident: the look-back cannot starve
+    for (int pass = 0; pass < p.numPasses; ++pass) {
+        const bool even = (pass & 1) == 0;
+        onesweep_pass_kernel<KeyT><<<grid, kSortThreads, 0, s>>>(
+            even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
+            p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u, p.tickets + pass, 8 * pass);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (p.numPasses & 1) {  // odd pass count: result is in the scratch pair, copy back (TileSortEncoder.swift:170-177)
+        e = cudaMemcpyAsync(p.k0, p.k1, (size_t)p.countCap * sizeof(KeyT), cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(p.v0, p.v1, (size_t)p.countCap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+    }
+    return e;
+}
+
+cudaError_t launchSort(cudaStream_t s, const SortPlan& p) {
+    return p.keyBits == 16 ? runSort<uint16_t>(s, p) : runSort<uint32_t>(s, p);
+}
+
+}  // namespace gsm

@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's public surface for the DepthFirst path.
+
+Same names, argument meaning and error behaviour as
+Sources/Renderer/Shared/GaussianRendererProtocol.swift (RenderPrecision :4-7, GaussianInput :9-26,
+CameraParams :28-54, StereoCameraParams :56-67, RendererConfig :195-228, StereoRenderTarget :233-239,
+GaussianRenderer :243-272, RendererError :274-324) and
+Sources/Renderer/DepthFirstRenderer/DepthFirstRenderer.swift (init :45-101, render :166-203,
+renderStereo :205-235), over the C ABI of include/gsm/gsm.h.
+
+Metal objects map to: MTLCommandBuffer -> a CUDA stream (torch.cuda.Stream, a raw cudaStream_t int, or
+None); MTLBuffer / MTLTexture -> anything with .data_ptr() (torch CUDA tensors) or a raw device pointer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _native as N
+
+
+class RenderPrecision(enum.Enum):
+    float32 = 0
+    float16 = 1
+
+
+class GaussianColorSpace(enum.IntEnum):
+    linear = 0
+    srgb = 1
+
+
+class RadixSortKeyPrecision(enum.IntEnum):
+    bits16 = 16
+    bits32 = 32
+
+    @property
+    def numPasses(self) -> int:
+        return 2 if self is RadixSortKeyPrecision.bits16 else 4
+
+
+class RendererError(Exception):
+    """RendererError (GaussianRendererProtocol.swift:274-324)."""
+
+    CASES = {1: "deviceNotAvailable", 2: "failedToCreatePipeline", 3: "failedToAllocateBuffer",
+             4: "invalidGaussianCount", 5: "invalidDimensions", 6: "invalidTileCount", 7: "renderFailed",
+             8: "invalidArgument"}
+
+    def __init__(self, status: int, detail: str = ""):
+        self.status = int(status)
+        self.case = self.CASES.get(self.status, "unknown")
+        super().__init__(f"{self.case}: {detail}" if detail else self.case)
+
+
+def _check(status: int) -> None:
+    if status != 0:
+        raise RendererError(status, (N.lib().gsm_last_error_string() or b"").decode())
+
+
+@dataclass
+class GaussianInput:
+    gaussians: Any   # PackedWorldGaussian (48 B) or PackedWorldGaussianHalf (32 B) records on the device
+    harmonics: Any   # float32 / float16 SH coefficients, planar per Gaussian
+    gaussianCount: int
+    shComponents: int
+
+
+@dataclass
+class CameraParams:
+    viewMatrix: Any          # 4x4, m[col][row] (simd_float4x4 layout)
+    projectionMatrix: Any
+    position: Any            # 3 floats
+    focalX: float
+    focalY: float
+    near: float = 0.1
+    far: float = 10.0
+
+    def to_native(self) -> N.gsm_camera:
+        c = N.gsm_camera()
+        c.viewMatrix[:] = np.asarray(self.viewMatrix, np.float32).reshape(16).tolist()
+        c.projectionMatrix[:] = np.asarray(self.projectionMatrix, np.float32).reshape(16).tolist()
+        c.position[:] = np.asarray(self.position, np.float32).reshape(3).tolist()
+        c.focalX, c.focalY = float(self.focalX), float(self.focalY)
+        c.nearPlane, c.farPlane = float(self.near), float(self.far)
+        return c
+
+
+@dataclass
+class StereoCameraParams:
+    leftEye: CameraParams
+    rightEye: CameraParams
+
+
+@dataclass
+class RendererConfig:
+    maxGaussians: int = 6_000_000
+    maxWidth: int = 1920
+    maxHeight: int = 1080
+    precision: RenderPrecision = RenderPrecision.float16
+    colorFormat: str = "bgra8Unorm_srgb"      # ignored by DepthFirst
+    gaussianColorSpace: GaussianColorSpace = GaussianColorSpace.srgb
+    backToFront: bool = False                 # ignored by DepthFirst
+
+
+@dataclass
+class StereoRenderTarget:
+    """.sideBySide(colorTexture:, depthTexture:) -- the only target on this path; .foveated is out of scope."""
+    colorTexture: Any
+    depthTexture: Any = None
+    kind: str = "sideBySide"
+
+    @staticmethod
+    def sideBySide(colorTexture, depthTexture=None) -> "StereoRenderTarget":
+        return StereoRenderTarget(colorTexture, depthTexture, "sideBySide")
+
+
+# debugRead* ids (include/gsm/gsm.h gsm_debug_buffer)
+_DBG = dict(header=0, activeTileCount=1, sortedTileIds=2, tileBounds=3, sortedPrimitiveIndices=4,
+            instanceOffsets=5, nTouchedTiles=6, instanceGaussianIndices=7, depthKeys=8, renderData=9,
+            tileHeaders=10, activeTiles=11, scratchDepthKeys=12, scratchPrimitiveIndices=13)
+
+RENDER_DATA_DTYPE = np.dtype(
+    [("meanX", "<f2"), ("meanY", "<f2"), ("theta", "<u2"), ("sigma1", "<f2"), ("sigma2", "<f2"),
+     ("depth", "<f2"), ("colorR", "u1"), ("colorG", "u1"), ("colorB", "u1"), ("opacity", "u1")])
+STEREO_RENDER_DATA_DTYPE = np.dtype(
+    [("leftMeanX", "<f2"), ("leftMeanY", "<f2"), ("leftCxx", "<f2"), ("leftCyy", "<f2"),
+     ("leftCxy2", "<f2"), ("leftDepth", "<f2"),
+     ("rightMeanX", "<f2"), ("rightMeanY", "<f2"), ("rightCxx", "<f2"), ("rightCyy", "<f2"),
+     ("rightCxy2", "<f2"), ("rightDepth", "<f2"),
+     ("colorR", "u1"), ("colorG", "u1"), ("colorB", "u1"), ("opacity", "u1"),
+     ("centerDepth", "<f2"), ("_pad0", "<u2")])
+
+
+class DepthFirstRenderer:
+    """DepthFirstRenderer (DepthFirstRenderer.swift:6). One host thread per instance."""
+
+    maxSupportedGaussians = 30_000_000
+    tileWidth = 16
+    tileHeight = 16
+
+    def __init__(self, device: Optional[int] = None, config: RendererConfig = None,
+                 depthSortKeyPrecision: RadixSortKeyPrecision = RadixSortKeyPrecision.bits32,
+                 tileIdPrecision: RadixSortKeyPrecision = RadixSortKeyPrecision.bits16,
+                 stereoCopyFlipY: bool = True):
+        config = config or RendererConfig()
+        self.config = config
+        self.lastGPUTime: Optional[float] = None
+        self._lib = N.lib()
+        cfg = N.gsm_config()
+        self._lib.gsm_config_default(C.byref(cfg))
+        cfg.maxGaussians, cfg.maxWidth, cfg.maxHeight = config.maxGaussians, config.maxWidth, config.maxHeight
+        cfg.precision = config.precision.value
+        cfg.gaussianColorSpace = int(config.gaussianColorSpace)
+        cfg.depthSortKeyPrecision = int(depthSortKeyPrecision)
+        cfg.tileIdPrecision = int(tileIdPrecision)
+        cfg.device = -1 if device is None else int(device)
+        cfg.stereoCopyFlipY = 1 if stereoCopyFlipY else 0
+        self._cfg = cfg
+        self._tile_dtype = np.uint16 if tileIdPrecision == RadixSortKeyPrecision.bits16 else np.uint32
+        h = C.c_void_p()
+        _check(self._lib.gsm_renderer_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._stereo_last = False
+
+    # -- lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.gsm_renderer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- GaussianRenderer protocol
+    def render(self, commandBuffer, colorTexture, depthTexture, input: GaussianInput, camera: CameraParams,
+               width: int, height: int) -> None:
+        cam = camera.to_native()
+        _check(self._lib.gsm_render(self._h, N.stream_handle(commandBuffer), N.ptr(colorTexture),
+                                    N.ptr(depthTexture), N.ptr(input.gaussians), N.ptr(input.harmonics),
+                                    int(input.gaussianCount), int(input.shComponents), C.byref(cam),
+                                    int(width), int(height)))
+        self._stereo_last = False
+
+    def renderStereo(self, commandBuffer, target: StereoRenderTarget, input: GaussianInput,
+                     camera: StereoCameraParams, width: int, height: int) -> None:
+        if target.kind != "sideBySide":
+            raise NotImplementedError("StereoRenderTarget.foveated needs a rasterization-rate map (visionOS only)")
+        l, r = camera.leftEye.to_native(), camera.rightEye.to_native()
+        _check(self._lib.gsm_render_stereo(self._h, N.stream_handle(commandBuffer), N.ptr(target.colorTexture),
+                                           N.ptr(input.gaussians), N.ptr(input.harmonics),
+                                           int(input.gaussianCount), int(input.shComponents), C.byref(l),
+                                           C.byref(r), int(width), int(height)))
+        self._stereo_last = True
+
+    def renderHost(self, hostGaussians, hostHarmonics, gaussianCount, shComponents, camera: CameraParams,
+                   width, height, hostColor, hostDepth=None) -> None:
+        """gsm_render_host: the same frame with host buffers (H2D + render + D2H + sync)."""
+        cam = camera.to_native()
+        _check(self._lib.gsm_render_host(self._h, N.ptr(hostGaussians), N.ptr(hostHarmonics), int(gaussianCount),
+                                         int(shComponents), C.byref(cam), int(width), int(height),
+                                         N.ptr(hostColor), N.ptr(hostDepth)))
+        self._stereo_last = False
+
+    # -- profiling
+    def setProfiling(self, enabled: bool) -> None:
+        _check(self._lib.gsm_set_profiling(self._h, int(enabled)))
+
+    def stageTimesMs(self) -> dict:
+        ms = (C.c_float * N.GSM_NUM_STAGES)()
+        _check(self._lib.gsm_get_stage_times_ms(self._h, ms))
+        out = {self._lib.gsm_stage_name(i).decode(): float(ms[i]) for i in range(N.GSM_NUM_STAGES)}
+        self.lastGPUTime = sum(out.values()) * 1e-3
+        return out
+
+    # -- standalone sort (what the reference's sort unit tests drive)
+    def sortPairs(self, commandBuffer, keys, payload, count: int, keyBits: int = 32, numPasses: int = 4) -> None:
+        _check(self._lib.gsm_sort_pairs(self._h, N.stream_handle(commandBuffer), N.ptr(keys), N.ptr(payload),
+                                        int(count), int(keyBits), int(numPasses)))
+
+    # -- white-box reads (DepthFirstUnitTests.swift:911-1252)
+    def _read(self, which: str, dtype, count: int, first: int = 0, stream=None) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        out = np.empty(count, dtype)
+        if count:
+            _check(self._lib.gsm_debug_read(self._h, N.stream_handle(stream), _DBG[which], N.ptr(out), first, count))
+        return out
+
+    def debugReadHeader(self) -> N.DepthFirstHeader:
+        h = N.DepthFirstHeader()
+        _check(self._lib.gsm_debug_read(self._h, None, _DBG["header"], C.addressof(h), 0, 1))
+        return h
+
+    def debugReadActiveTileCount(self) -> int:
+        return int(self._read("activeTileCount", np.uint32, 1)[0])
+
+    def debugReadSortedTileIds(self, count: int) -> np.ndarray:
+        return self._read("sortedTileIds", self._tile_dtype, count).astype(np.uint32)
+
+    def debugReadTileBounds(self, count: int) -> np.ndarray:
+        return self._read("tileBounds", np.dtype((np.int32, 4)), count)
+
+    def debugReadSingleBounds(self, at: int) -> np.ndarray:
+        return self._read("tileBounds", np.dtype((np.int32, 4)), 1, first=at)[0]
+
+    def debugReadSortedPrimitiveIndices(self, count: int) -> np.ndarray:
+        return self._read("sortedPrimitiveIndices", np.int32, count)
+
+    def debugReadSortedPrimitiveIndicesRange(self, start: int, count: int) -> np.ndarray:
+        return self._read("sortedPrimitiveIndices", np.int32, count, first=start)
+
+    def debugReadInstanceOffsets(self, count: int) -> np.ndarray:
+        return self._read("instanceOffsets", np.uint32, count)
+
+    debugReadOrderedTileCounts = debugReadInstanceOffsets  # same buffer after the in-place scan
+
+    def debugReadNTouchedTiles(self, count: int) -> np.ndarray:
+        return self._read("nTouchedTiles", np.uint32, count)
+
+    def debugReadInstanceGaussianIndices(self, count: int) -> np.ndarray:
+        return self._read("instanceGaussianIndices", np.int32, count)
+
+    def debugReadDepthKeys(self, count: int) -> np.ndarray:
+        return self._read("depthKeys", np.uint32, count)
+
+    def debugReadScratchDepthKeys(self, count: int) -> np.ndarray:
+        return self._read("scratchDepthKeys", np.uint32, count)
+
+    def debugReadScratchPrimitiveIndices(self, count: int) -> np.ndarray:
+        return self._read("scratchPrimitiveIndices", np.int32, count)
+
+    def debugReadRenderData(self, count: int) -> np.ndarray:
+        return self._read("renderData", STEREO_RENDER_DATA_DTYPE if self._stereo_last else RENDER_DATA_DTYPE, count)
+
+    def debugReadTileHeaders(self, count: int) -> np.ndarray:
+        return self._read("tileHeaders", np.dtype((np.uint32, 2)), count)
+
+    def debugReadActiveTiles(self, count: int) -> np.ndarray:
+        return self._read("activeTiles", np.uint32, count)
+
+
+def probe_math(op: int, a, b=None, device: int = -1) -> np.ndarray:
+    """gsm_probe_math: device restatement of the canonical math (0 sin, 1 cos, 2 log, 3 atan2, 4 powr 2.4,
+    5 half exp, 6 float->half, 7 packed half exp)."""
+    a = np.ascontiguousarray(a)
+    out = np.empty(a.shape, np.uint16 if op in (5, 6, 7) else np.float32)
+    bp = None if b is None else N.ptr(np.ascontiguousarray(b))
+    _check(N.lib().gsm_probe_math(device, op, N.ptr(a), bp, N.ptr(out), a.size))
+    return out

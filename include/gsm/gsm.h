@@ -1,0 +1,178 @@
+/*
+ * gsm.h -- C ABI of the B200-native DepthFirstRenderer path (libgsm_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types. Each entry point
+ * cites the reference interface it replaces (paths relative to the reference repo):
+ *   GRP.swift = Sources/Renderer/Shared/GaussianRendererProtocol.swift
+ *   DFR.swift = Sources/Renderer/DepthFirstRenderer/DepthFirstRenderer.swift
+ *   DFUT.swift = Tests/RendererTests/DepthFirstUnitTests.swift
+ *
+ * Object mapping:  MTLDevice -> CUDA device ordinal;  MTLCommandBuffer -> cudaStream_t (passed as void*;
+ * enqueue-only, the caller synchronises, exactly like commit()/waitUntilCompleted());  MTLBuffer -> device
+ * pointer;  MTLTexture rgba16Float -> device buffer of W*H*4 halfs, row pitch W*8 B;  r16Float -> W*H halfs.
+ * Threading: one host thread per renderer handle (the reference class is @unchecked Sendable with
+ * unsynchronised caches, DFR.swift:6,29-31); all work is stream-ordered; gsm_render* never synchronises
+ * after the handle's first use and is safe to capture into a CUDA graph from the second call on.
+ */
+#ifndef GSM_H
+#define GSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSM_ABI_VERSION 1
+
+/* RendererError (GRP.swift:274-324), one code per case that can arise on this path. */
+typedef enum {
+    GSM_OK = 0,
+    GSM_ERR_DEVICE_NOT_AVAILABLE = 1,    /* .deviceNotAvailable */
+    GSM_ERR_FAILED_TO_CREATE_PIPELINE = 2, /* .failedToCreatePipeline: kernels for sm_100a cannot load */
+    GSM_ERR_FAILED_TO_ALLOCATE_BUFFER = 3, /* .failedToAllocateBuffer */
+    GSM_ERR_INVALID_GAUSSIAN_COUNT = 4,  /* .invalidGaussianCount: maxGaussians > 30,000,000 (DFR.swift:51-56) */
+    GSM_ERR_INVALID_DIMENSIONS = 5,      /* .invalidDimensions */
+    GSM_ERR_INVALID_TILE_COUNT = 6,      /* .invalidTileCount: > 65535 tiles with 16-bit tile ids */
+    GSM_ERR_RENDER_FAILED = 7,           /* .renderFailed: a CUDA call failed; see gsm_last_error_string */
+    GSM_ERR_INVALID_ARGUMENT = 8
+} gsm_status;
+
+typedef enum { GSM_PRECISION_FLOAT32 = 0, GSM_PRECISION_FLOAT16 = 1 } gsm_precision;   /* RenderPrecision, GRP.swift:4-7 */
+typedef enum { GSM_COLORSPACE_LINEAR = 0, GSM_COLORSPACE_SRGB = 1 } gsm_color_space;   /* GRP.swift:196-201 */
+typedef enum { GSM_KEY_BITS16 = 16, GSM_KEY_BITS32 = 32 } gsm_key_precision;           /* RadixSortKeyPrecision */
+
+/* RendererConfig (GRP.swift:195-228) + the two init enums of DepthFirstRenderer.init (DFR.swift:45-50).
+ * colorFormat and backToFront are ignored by the DepthFirst path (only HardwareRenderer reads them). */
+typedef struct {
+    uint32_t maxGaussians;       /* default 6,000,000 */
+    uint32_t maxWidth;           /* default 1920 */
+    uint32_t maxHeight;          /* default 1080 */
+    uint32_t precision;          /* gsm_precision, default FLOAT16 */
+    uint32_t gaussianColorSpace; /* gsm_color_space, default SRGB */
+    uint32_t depthSortKeyPrecision; /* gsm_key_precision, default BITS32 */
+    uint32_t tileIdPrecision;       /* gsm_key_precision, default BITS16 */
+    int32_t device;              /* CUDA ordinal; -1 = current device */
+    uint32_t stereoCopyFlipY;    /* 1 = literal stereoCopy semantics (rows flipped, quirk Q9); 0 = straight copy */
+    uint32_t reserved[7];
+} gsm_config;
+
+/* CameraParams (GRP.swift:28-54). Matrices are simd_float4x4: column-major, m[4*col + row]. */
+typedef struct {
+    float viewMatrix[16];
+    float projectionMatrix[16];
+    float position[3];
+    float focalX, focalY; /* carried, unused on this path */
+    float nearPlane, farPlane; /* defaults 0.1, 10.0 */
+} gsm_camera;
+
+typedef struct gsm_renderer gsm_renderer;
+
+void gsm_config_default(gsm_config* cfg);
+
+/* DepthFirstRenderer.init (DFR.swift:45-101). Resources are allocated lazily on first render, like
+ * ensureMonoResources / ensureStereoResources (DFR.swift:105-137). */
+gsm_status gsm_renderer_create(const gsm_config* cfg, gsm_renderer** out);
+void gsm_renderer_destroy(gsm_renderer* r);
+
+/* GaussianRenderer.render (GRP.swift:248-256, DFR.swift:166-203). color: rgba16f W*H; depth: r16f W*H or
+ * NULL. gaussians: PackedWorldGaussian[count] (FLOAT32) or PackedWorldGaussianHalf[count] (FLOAT16);
+ * harmonics: float or half, planar per Gaussian. Returns GSM_OK and enqueues nothing when count == 0 or
+ * count > maxGaussians (the reference's silent no-op, DFR.swift:249). */
+gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, const void* gaussians,
+                      const void* harmonics, uint32_t gaussianCount, uint32_t shComponents,
+                      const gsm_camera* camera, uint32_t width, uint32_t height);
+
+/* GaussianRenderer.renderStereo with StereoRenderTarget.sideBySide (GRP.swift:264-271, DFR.swift:205-235,
+ * :469-512). colorSideBySide: rgba16f (2*width) x height; width/height are per eye. The depth texture of
+ * the target is ignored by the reference (DFR.swift:472) and has no parameter here. */
+gsm_status gsm_render_stereo(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians,
+                             const void* harmonics, uint32_t gaussianCount, uint32_t shComponents,
+                             const gsm_camera* leftEye, const gsm_camera* rightEye, uint32_t width,
+                             uint32_t height);
+
+/* Same frame as gsm_render but with HOST buffers: copies inputs host->device, renders, copies the images
+ * device->host and synchronises. This is what a host with no device allocator of its own calls (and what
+ * bench.py times as `e2e`). hostDepth may be NULL. */
+gsm_status gsm_render_host(gsm_renderer* r, const void* hostGaussians, const void* hostHarmonics,
+                           uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* camera,
+                           uint32_t width, uint32_t height, void* hostColor, void* hostDepth);
+
+/* lastGPUTime (GRP.swift:245; declared but never assigned by the reference, DFR.swift:43). Here: device
+ * time of the last frame in ms when profiling is on, else a negative number. */
+double gsm_last_gpu_time_ms(gsm_renderer* r);
+
+/* Per-stage device timing (cudaEvent pairs around each stage). Costs a host sync per readout, so it is
+ * off by default. names: project, depthSort, applyScan, expand, tileSort, ranges, blend, copy. */
+#define GSM_NUM_STAGES 8
+gsm_status gsm_set_profiling(gsm_renderer* r, int enabled);
+gsm_status gsm_get_stage_times_ms(gsm_renderer* r, float* ms /* GSM_NUM_STAGES */);
+const char* gsm_stage_name(int stage);
+
+/* White-box reads mirroring the test-side debugRead* helpers (DFUT.swift:911-1252). Each copies
+ * `count` elements starting at element `first` into host memory `dst` after synchronising `stream`. */
+typedef enum {
+    GSM_DBG_HEADER = 0,               /* debugReadHeader: GSMDepthFirstHeader x1 */
+    GSM_DBG_ACTIVE_TILE_COUNT = 1,    /* debugReadActiveTileCount: u32 x1 */
+    GSM_DBG_SORTED_TILE_IDS = 2,      /* debugReadSortedTileIds: u16 (tileIdPrecision 16) or u32 */
+    GSM_DBG_TILE_BOUNDS = 3,          /* debugReadTileBounds / debugReadSingleBounds: int32 x4 per Gaussian */
+    GSM_DBG_SORTED_PRIMITIVE_INDICES = 4, /* debugReadSortedPrimitiveIndices(+Range): int32 per visible */
+    GSM_DBG_INSTANCE_OFFSETS = 5,     /* debugReadInstanceOffsets == debugReadOrderedTileCounts after the scan */
+    GSM_DBG_N_TOUCHED_TILES = 6,      /* debugReadNTouchedTiles: u32 per Gaussian */
+    GSM_DBG_INSTANCE_GAUSSIAN_INDICES = 7, /* debugReadInstanceGaussianIndices: int32 per instance, tile-sorted */
+    GSM_DBG_DEPTH_KEYS = 8,           /* debugReadDepthKeys: u32 per visible, sorted */
+    GSM_DBG_RENDER_DATA = 9,          /* debugReadRenderData: GSMGaussianRenderData (mono) / GSMStereoTiledRenderData */
+    GSM_DBG_TILE_HEADERS = 10,        /* debugReadTileHeaders: GSMGaussianHeader per tile */
+    GSM_DBG_ACTIVE_TILES = 11,        /* activeTiles list (ascending here; atomic order in the reference) */
+    GSM_DBG_SCRATCH_DEPTH_KEYS = 12,  /* debugReadScratchDepthKeys: ping-pong buffer, content unspecified */
+    GSM_DBG_SCRATCH_PRIMITIVE_INDICES = 13, /* debugReadScratchPrimitiveIndices: same */
+    GSM_DBG_COUNT_
+} gsm_debug_buffer;
+
+gsm_status gsm_debug_read(gsm_renderer* r, void* stream, int which, void* dst, size_t first, size_t count);
+size_t gsm_debug_element_size(gsm_renderer* r, int which);
+
+/* Device memory and streams for hosts without a CUDA runtime binding (the Swift facade): the MTLBuffer /
+ * MTLCommandQueue replacements. */
+gsm_status gsm_buffer_alloc(int device, size_t bytes, void** out);
+gsm_status gsm_buffer_free(void* p);
+gsm_status gsm_buffer_upload(void* dst, const void* src, size_t bytes, void* stream);
+gsm_status gsm_buffer_download(void* dst, const void* src, size_t bytes, void* stream);
+gsm_status gsm_stream_create(int device, void** out);
+gsm_status gsm_stream_synchronize(void* stream);
+gsm_status gsm_stream_destroy(void* stream);
+
+/* Standalone stable radix sort of (key, payload) pairs on the device -- the entry the reference's sort
+ * unit tests drive directly (DFUT.swift:120-468 call DepthRadixSortEncoder.encode). keyBits 16 or 32;
+ * numPasses 8-bit digits from bit 0. Sorted data ends in keys/payload. */
+gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* payload, uint32_t count,
+                          int keyBits, int numPasses);
+
+/* Multi-GPU helpers with no reference counterpart: a single large frame split into
+ * horizontal strips of whole tile rows. Step 1 (per rank): project+cull the gid range
+ * [gidFirst, gidFirst+gidCount) and emit compacted 48-byte splat records (count in *hostCount after the
+ * call synchronises). Step 2 (per rank, after an all-gather of the records in rank order): sort, expand,
+ * tile-sort and blend only tile rows [tileRowFirst, tileRowFirst+tileRowCount) into the full-size targets. */
+#define GSM_SPLAT_RECORD_BYTES 48
+gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussians, const void* harmonics,
+                             uint32_t gidFirst, uint32_t gidCount, uint32_t shComponents,
+                             const gsm_camera* camera, uint32_t width, uint32_t height, void* recordsOut,
+                             uint32_t* hostCount);
+gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* depth, const void* records,
+                            uint32_t recordCount, uint32_t width, uint32_t height, uint32_t tileRowFirst,
+                            uint32_t tileRowCount);
+
+/* Math probes: run the device restatement of the canonical transcendental definitions on arrays, so the
+ * tests can compare them bit-for-bit with the CPU oracle. op: 0 sin, 1 cos, 2 log, 3 atan2(a,b),
+ * 4 powr(a, 2.4), 5 half exp (a,out are u16), 6 float->half (out u16). Host pointers. */
+gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void* out, uint32_t n);
+
+const char* gsm_status_string(gsm_status s);
+const char* gsm_last_error_string(void);
+int gsm_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSM_H */
