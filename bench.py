@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DepthFirst hot path (BASELINE.json metric, config C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C5v|...]
+
+One "step" = one 1920x1080 mono frame of a 1M-Gaussian SH3 float16 synthetic cloud (SURVEY.md 8(d) recipe)
+through gsm_render (C ABI). Prints ONE JSON line (rank 0):
+  value        frames/s with inputs resident in HBM, per-step CUDA events on the launching stream,
+               L2 flushed between steps; whole job = sum over ranks (views shard with no collective)
+  e2e          the same frame through gsm_render_host: pinned host inputs -> H2D -> render -> D2H, every step
+  roofline     dominant kernel: algorithmic bytes / its measured duration vs the
+               measured HBM peak of MEASURED_PEAKS.json; stage_roofline lists every stage
+  cpu_baseline the CPU oracle (a port of the reference's Metal kernels) timed on this box's cores (rank 0, N=1)
+--impl reference times that CPU implementation alone on the same config (the Metal reference cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gsm_renderer_b200 import synthetic as syn  # noqa: E402
+
+WORKLOADS = {
+    # name: (N, sh_degree, precision, W, H, scale_median, description)
+    "C1": (50_000, 1, "float32", 1920, 1080, 0.015, "C1: 50k Gaussians SH1 float32, 1920x1080 mono"),
+    "C2": (1_000_000, 3, "float16", 1920, 1080, 0.015, "C2: 1M Gaussians SH3 float16, 1920x1080 mono"),
+    "C5v": (3_000_000, 3, "float16", 1280, 720, 0.012, "C5 (one view): 3M Gaussians SH3 float16, 1280x720"),
+}
+NEAR, FAR = 0.1, 100.0  # PLYBenchmarkTests.swift:60-62
+KERNELS_PER_FRAME = 15  # project, header, 2 histograms, 6 onesweep passes, scan, expand, bounds, headers, blend
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def stage_bytes(N, V, Vp, I, T, P, rec_bytes, sh_bytes):
+    """Algorithmic bytes per stage, BASELINE.md section 4 (compaction is fused into project: 0 extra)."""
+    return {
+        "project": N * (rec_bytes + 24) + Vp * sh_bytes + 16 * V,
+        "depthSort": 68 * V,
+        "applyScan": 20 * V,
+        "expand": 40 * V + 6 * I,
+        "tileSort": 26 * I,
+        "ranges": 2 * I + 12 * T,
+        "blend": 20 * I + 10 * P,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, seed=42):
+    N, deg, prec, W, H, sm, desc = WORKLOADS[name]
+    cloud = syn.synthetic_cloud(N, deg, seed=seed, scale_median=sm)
+    g, h = cloud.pack(prec)
+    return cloud, np.ascontiguousarray(g), np.ascontiguousarray(h), (N, deg, prec, W, H, desc)
+
+
+def oracle_frame_runner(g, h, spec, threads=None):
+    """Returns (run(), frame) for the CPU implementation of the whole frame (oracle/gsm_oracle.c)."""
+    from oracle import binding as ob
+    ob.build()
+    N, deg, prec, W, H, _ = spec
+    if threads:
+        ob.lib().gsmo_set_num_threads(int(threads))
+    proj = syn.make_projection_matrix(W, H, NEAR, FAR)
+    cam = ob.make_camera(np.eye(4), proj, (0, 0, 0), W, H, NEAR, FAR, syn.SH_COEFFS[deg], N, False)
+    fr = ob.OracleFrame(N, W, H)
+    p = ob.F16 if prec == "float16" else ob.F32
+
+    def run():
+        t = time.perf_counter()
+        fr.render_mono(g, h, p, cam, W, H)
+        return time.perf_counter() - t
+    return run, fr, ob
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (CPU port; Metal cannot run here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cloud, g, h, spec = build_workload(args.workload)
+    run, fr, ob = oracle_frame_runner(g, h, spec)
+    cores = ob.lib().gsmo_num_threads()
+    for _ in range(max(1, min(args.warmup, 2))):
+        run()
+    times = [run() for _ in range(args.steps)]
+    ms = 1e3 * float(np.mean(times))
+    fps = 1e3 / ms
+    line = {
+        "impl": "reference", "metric": "1080p frames/s at 1M Gaussians SH3 (DepthFirst mono frame)", "value": fps,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": spec[5], "seed": 42, "near": NEAR, "far": FAR, "N": spec[0], "V": fr.header.visibleCount,
+                   "I": fr.header.totalInstances, "note": "CPU port of the reference's Metal kernels (oracle/), full frames"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full frames of the workload", "stage_ms": {k: 1e3 * v for k, v in fr.stage_seconds.items()}},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps")
+    ap.add_argument("--check", action="store_true", help="also verify the frame against the oracle (slow)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gsm_renderer_b200.renderer import (CameraParams, DepthFirstRenderer, GaussianColorSpace, GaussianInput,
+                                            RendererConfig, RenderPrecision)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cloud, g, h, spec = build_workload(args.workload)
+    N, deg, prec, W, H, desc = spec
+    K = syn.SH_COEFFS[deg]
+    cfg = RendererConfig(maxGaussians=N, maxWidth=W, maxHeight=H,
+                         precision=RenderPrecision.float16 if prec == "float16" else RenderPrecision.float32,
+                         gaussianColorSpace=GaussianColorSpace.linear)  # PLYBenchmarkTests.swift:157-164
+    r = DepthFirstRenderer(device=local, config=cfg)
+    # views shard across ranks with no collective: rank k renders its own camera of a seeded orbit
+    if world > 1:
+        view, pos = syn.orbit_cameras(world, center=(0, 0, 11.0), radius=11.0, seed=7)[rank]
+        if rank == 0:
+            view, pos = np.eye(4, dtype=np.float32), np.zeros(3, np.float32)
+    else:
+        view, pos = np.eye(4, dtype=np.float32), np.zeros(3, np.float32)
+    proj = syn.make_projection_matrix(W, H, NEAR, FAR)
+    fx, fy = syn.focal_lengths(W, H)
+    cam = CameraParams(view, proj, pos, fx, fy, NEAR, FAR)
+
+    tg = torch.from_numpy(g.view(np.uint8).reshape(-1)).to(dev)
+    th = torch.from_numpy(h.view(np.uint8).reshape(-1)).to(dev)
+    color = torch.zeros((H, W, 4), dtype=torch.float16, device=dev)
+    depth = torch.zeros((H, W), dtype=torch.float16, device=dev)
+    inp = GaussianInput(tg, th, N, K)
+    stream = torch.cuda.current_stream()
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        r.render(stream, color, depth, inp, cam, W, H)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    hd = r.debugReadHeader()
+    V, I = hd.visibleCount, hd.totalInstances
+    active = r.debugReadActiveTileCount()
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    max_per_tile = int(r.debugReadTileHeaders(T)[:, 1].max())
+
+    # ---- timed region: per-step CUDA events on the launching stream, L2 flushed between steps
+    r.setProfiling(True)
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stage_acc = {}
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        ev0[i].record(stream)
+        step()
+        ev1[i].record(stream)
+        ev1[i].synchronize()
+        for k, v in r.stageTimesMs().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    r.setProfiling(False)
+    step_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(args.steps)]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        dist.barrier()
+    ms_per_step = total_ms / args.steps
+    value = world * 1e3 / ms_per_step
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+
+    # ---- e2e: host buffers through gsm_render_host (H2D + frame + D2H every step)
+    pg = torch.from_numpy(g.view(np.uint8).reshape(-1)).pin_memory()
+    ph = torch.from_numpy(h.view(np.uint8).reshape(-1)).pin_memory()
+    pc = torch.zeros((H, W, 4), dtype=torch.float16).pin_memory()
+    pd = torch.zeros((H, W), dtype=torch.float16).pin_memory()
+    for _ in range(2):
+        r.renderHost(pg, ph, N, K, cam, W, H, pc, pd)
+    e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r.renderHost(pg, ph, N, K, cam, W, H, pc, pd)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * e2e_steps / e2e_s
+    h2d = int(pg.numel() + ph.numel())
+    d2h = int(pc.numel() * 2 + pd.numel() * 2)
+    same = bool(torch.equal(pc.to(dev), color))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- rooflines
+    peak, peak_src = measured_peaks()
+    Vp = V  # Gaussians reaching the SH fetch >= V; the (9) exit after the fetch is rare. Lower bound used.
+    sb = stage_bytes(N, V, Vp, I, T, W * H, 32 if prec == "float16" else 48, 3 * K * (2 if prec == "float16" else 4))
+    stage_roofline = []
+    for k in ("project", "depthSort", "applyScan", "expand", "tileSort", "ranges", "blend"):
+        ms = stage_ms.get(k, 0.0)
+        gbs = sb[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stage_roofline.append({"stage": k, "ms": ms, "bytes": int(sb[k]), "GBps": gbs, "frac": gbs / peak})
+    dom = max(stage_roofline, key=lambda s: s["ms"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom["stage"])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom["stage"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "note": ("blend is FP16/FP32-pipe bound, not HBM bound (SURVEY.md 8d); see stage_roofline for the "
+                         "HBM-bound sort/scan/expand stages") if dom["stage"] == "blend" else ""}
+    sort_blend_ms = stage_ms.get("tileSort", 0) + stage_ms.get("ranges", 0) + stage_ms.get("blend", 0)
+
+    # ---- CPU baseline (bounded sample: whole frames of the same workload on this box's cores)
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        run, fr, ob = oracle_frame_runner(g, h, spec)
+        run()
+        n_s, t_acc = 0, 0.0
+        while n_s < 3 and t_acc < 20.0:
+            t_acc += run()
+            n_s += 1
+        cpu_baseline = {"value": n_s / t_acc, "unit": "frames/s", "cores": ob.lib().gsmo_num_threads(), "kind": "port",
+                        "sample": f"{n_s} full frames of the workload after 1 warm-up",
+                        "stage_ms": {k: 1e3 * v for k, v in fr.stage_seconds.items()}}
+        if args.check:
+            assert fr.header.visibleCount == V and fr.header.totalInstances == I
+
+    line = {
+        "metric": "1080p frames/s at 1M Gaussians SH3 (DepthFirst mono frame)", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": desc, "seed": 42, "near": NEAR, "far": FAR, "N": N, "V": V, "I": I, "activeTiles": active,
+                   "tiles": T, "maxInstancesPerTile": max_per_tile, "overflow": hd.overflow,
+                   "parallelism": f"views sharded over {world} GPU(s), no collective",
+                   "l2": "inputs+arena > L2 and " + ("no flush" if args.no_flush else "L2 flushed between steps (256 MiB write, untimed)"),
+                   "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
+        "mtile_instances_per_s": (I / (sort_blend_ms * 1e-3) / 1e6) if sort_blend_ms > 0 else None,
+        "stage_ms": stage_ms,
+        "roofline": roofline,
+        "stage_roofline": stage_roofline,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "matches_device_path": same},
+        "gpu_launches": KERNELS_PER_FRAME * args.steps,
+        "clocks": clocks,
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
     const __half2 px = __halves2half2(__uint2half_rn(baseX), __uint2half_rn(baseX + 1u));  // half(baseX+k), quirk Q7
     const __half2 py0 = __half2half2(__uint2half_rn(baseY)), py1 = __half2half2(__uint2half_rn(baseY + 1u));
     const __half thr = __float2half_rn(1.0f / 255.0f);  // half(1.0h/255.0h): both roundings agree (0x1C04)
-    const __half2 h099 = h2(0.99f), negHalf = h2(-0.5f), zero = h2(0.0f), one = h2(1.0f);
+    const __half2 h099 = h2(0.99f), negHalf = h2(-0.5f), zero = h2(0.0f), one = h2(1.0f), farP = h2(35.0f);
 
     QuadState q;
     q.T0 = one; q.T1 = one;
@@ -126,8 +126,11 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                 const __half2 dx = __hsub2_rn(px, mx);
                 const __half2 dy0 = __hsub2_rn(py0, my), dy1 = __hsub2_rn(py1, my);
                 const __half2 p0 = power(dx, dy0, cxx, cyy, cxy2), p1 = power(dx, dy1, cxx, cyy, cxy2);
-                const __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p0))), h099);
-                const __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p1))), h099);
+                // p > 35 on all four pixels => -0.5h*p < -17.5 => exp() is exactly +0 => alphas are 0 => "continue"
+                // (NaN compares false and takes the full path)
+                if (__hbgt2(p0, farP) && __hbgt2(p1, farP)) continue;
+                const __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p0))), h099);
+                const __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p1))), h099);
                 if (((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) == 0u) continue;  // all(alphas == 0), DFS.metal:1781
                 accumulate(q, a0, a1, __low2half2(rg), __high2half2(rg), __low2half2(b_d), __high2half2(b_d), true);
             }
@@ -156,8 +159,8 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
     const __half2 out0 = __hgt2(p0, r2Max), out1 = __hgt2(p1, r2Max);  // 1.0 where p > r2Max (false for NaN)
     const uint32_t o0 = h2bits(out0), o1 = h2bits(out1);
     if (o0 == 0x3C003C00u && o1 == 0x3C003C00u) return;  // all four beyond the cutoff: alphas stay 0
-    __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p0))), h099);
-    __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2(__hmul2_rn(negHalf, p1))), h099);
+    __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p0))), h099);
+    __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p1))), h099);
     // per-pixel cutoff: alpha = 0 where p > r2Max
     uint32_t m0 = ((o0 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o0 >> 16) ? 0u : 0xFFFF0000u);
     uint32_t m1 = ((o1 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o1 >> 16) ? 0u : 0xFFFF0000u);

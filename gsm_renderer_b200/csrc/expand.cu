@@ -16,38 +16,45 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
                                                                TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx,
                                                                const GSMDepthFirstHeader* __restrict__ header, uint32_t tilesX,
                                                                uint32_t maxAssignments) {
+    __shared__ WarpTileWork s_work[8];
+    __shared__ uint32_t s_base[8][32];
+    __shared__ int32_t s_idx[8][32];
     const uint32_t visibleCount = header->visibleCount;
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < visibleCount; i += gridDim.x * 256u) {
-        const int32_t originalIdx = sortedIdx[i];
-        if (originalIdx < 0) continue;
-        const int4 b = __ldg(reinterpret_cast<const int4*>(bounds) + originalIdx);
-        const int minTX = b.x, maxTX = b.y, minTY = b.z, maxTY = b.w;
-        if (minTX > maxTX || minTY > maxTY) continue;
-        uint32_t writeOffset = offsets[i];
-        if (STEREO) {
-            for (int ty = minTY; ty <= maxTY; ++ty)
-                for (int tx = minTX; tx <= maxTX; ++tx)
-                    if (writeOffset < maxAssignments) {
-                        tileIds[writeOffset] = (TileT)(ty * (int)tilesX + tx);
-                        instanceIdx[writeOffset] = originalIdx;
-                        writeOffset++;
+    const unsigned warp = threadIdx.x >> 5;
+    // whole warps stay together: the tile walk is warp-cooperative
+    for (uint32_t i0 = blockIdx.x * 256u; i0 < visibleCount; i0 += gridDim.x * 256u) {
+        const uint32_t i = i0 + threadIdx.x;
+        int32_t originalIdx = -1;
+        int minTX = 0, maxTX = -1, minTY = 0, maxTY = -1;
+        uint32_t writeOffset = 0, n = 0;
+        QuantSplat q = {};
+        if (i < visibleCount) {
+            originalIdx = sortedIdx[i];
+            if (originalIdx >= 0) {
+                const int4 b = __ldg(reinterpret_cast<const int4*>(bounds) + originalIdx);
+                minTX = b.x; maxTX = b.y; minTY = b.z; maxTY = b.w;
+                if (minTX <= maxTX && minTY <= maxTY) {
+                    writeOffset = offsets[i];
+                    n = (uint32_t)((maxTX - minTX + 1) * (maxTY - minTY + 1));
+                    if (!STEREO) {
+                        const uint4 rd = __ldg(reinterpret_cast<const uint4*>(renderData) + originalIdx);
+                        q = makeQuantSplat(__ushort_as_half((unsigned short)(rd.x & 0xFFFFu)),
+                                           __ushort_as_half((unsigned short)(rd.x >> 16)), (uint16_t)(rd.y & 0xFFFFu),
+                                           __ushort_as_half((unsigned short)(rd.y >> 16)),
+                                           __ushort_as_half((unsigned short)(rd.z & 0xFFFFu)), (uint8_t)(rd.w >> 24));
+                        if (!(q.d2Cutoff >= 0.0f)) n = 0;
                     }
-        } else {
-            const uint4 rd = __ldg(reinterpret_cast<const uint4*>(renderData) + originalIdx);
-            QuantSplat q = makeQuantSplat(__ushort_as_half((unsigned short)(rd.x & 0xFFFFu)),
-                                          __ushort_as_half((unsigned short)(rd.x >> 16)), (uint16_t)(rd.y & 0xFFFFu),
-                                          __ushort_as_half((unsigned short)(rd.y >> 16)),
-                                          __ushort_as_half((unsigned short)(rd.z & 0xFFFFu)), (uint8_t)(rd.w >> 24));
-            if (q.d2Cutoff >= 0.0f) {
-                for (int ty = minTY; ty <= maxTY; ++ty)
-                    for (int tx = minTX; tx <= maxTX; ++tx)
-                        if (tileHit(q, tx, ty) && writeOffset < maxAssignments) {
-                            tileIds[writeOffset] = (TileT)(ty * (int)tilesX + tx);
-                            instanceIdx[writeOffset] = originalIdx;
-                            writeOffset++;
-                        }
+                }
             }
         }
+        if (STEREO) {
+            // every tile of the union AABB, no ellipse test (DFS.metal:816-825): a splat whose mean is inside every
+            // tile makes tileHitP return true for all of them without changing the walk
+            q.meanX = 0.0f; q.meanY = 0.0f; q.ca = 0.0f; q.cb = 0.0f; q.cc = 0.0f;
+            q.d2Cutoff = __uint_as_float(0x7F800000u);  // d2min <= +inf always (d2min is never NaN for a = b = c = 0)
+        }
+        warpEmitTiles<TileT>(s_work[warp], n, q, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
+                             tileIds, instanceIdx, s_base[warp], s_idx[warp]);
     }
 }
 

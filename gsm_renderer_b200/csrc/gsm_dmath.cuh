@@ -166,4 +166,26 @@ __device__ __forceinline__ __half2 dhexp2(__half2 x) {
     return r;
 }
 
+// The blend kernel's form of dhexp2: packed binary32 arithmetic (sm_100 FMUL2/FADD2/FFMA2) and no end
+// selects. Bit-identical to dhexp2 on every non-NaN input: the clamp is done in half (exact), e^-17.5 < 2^-25
+// rounds to +0 and e^11.5 > 65520 rounds to +inf, which are the values dhexp2 selects. A NaN lane comes out
+// as +inf instead of NaN; the caller's min(opacity * e, 0.99h) maps both to 0.99h (opacity > 0).
+__device__ __forceinline__ __half2 dhexp2_packed(__half2 x) {
+    const __half2 xc = __hmax2(__hmin2(x, __float2half2_rn(11.5f)), __float2half2_rn(-17.5f));
+    const float2 xf = __half22float2(xc);
+    const float2 t = __fmul2_rn(xf, make_float2(1.44269504088896341f, 1.44269504088896341f));
+    const float2 zb = __fadd2_rn(t, make_float2(12582912.0f, 12582912.0f));
+    const float2 n = __fadd2_rn(zb, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), t);  // t - n (the product is exact)
+    float2 p = make_float2(0x1.5f0890p-10f, 0x1.5f0890p-10f);
+    p = __ffma2_rn(p, f, make_float2(0x1.3d1070p-7f, 0x1.3d1070p-7f));
+    p = __ffma2_rn(p, f, make_float2(0x1.c6af6cp-5f, 0x1.c6af6cp-5f));
+    p = __ffma2_rn(p, f, make_float2(0x1.ebf906p-3f, 0x1.ebf906p-3f));
+    p = __ffma2_rn(p, f, make_float2(0x1.62e430p-1f, 0x1.62e430p-1f));
+    p = __ffma2_rn(p, f, make_float2(0x1.000002p+0f, 0x1.000002p+0f));
+    const float rx = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(zb.x) << 23));
+    const float ry = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(zb.y) << 23));
+    return __floats2half2_rn(rx, ry);
+}
+
 }  // namespace gsm

@@ -26,6 +26,12 @@ __global__ void probe_kernel(int op, const void* a, const void* b, void* out, ui
             ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2(v)));
             break;
         }
+        case 8: {  // the blend kernel's packed form (NaN lanes excluded by the caller)
+            const unsigned short* ha = (const unsigned short*)a;
+            __half2 v = __halves2half2(__ushort_as_half(ha[i]), __ushort_as_half(ha[i ^ 1u]));
+            ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2_packed(v)));
+            break;
+        }
         default: break;
     }
 }

@@ -415,7 +415,15 @@ __global__ void __launch_bounds__(256) project_cull_mono_kernel(const void* __re
     const uint32_t gid = o.gidFirst + lid;            // global Gaussian id: what every output is keyed by
     const bool inRange = lid < N;
 
+    __shared__ WarpTileWork s_work[8];
     uint32_t touched = 0, key = 0xFFFFFFFFu;
+    // state carried from the per-lane projection to the warp-cooperative tile walk
+    bool alive = false;
+    QuantSplat q = {};
+    int bMinTX = 0, bMaxTX = -1, bMinTY = 0, bMaxTY = -1;
+    uint32_t nTiles = 0, sColor = 0;
+    float keyDepth = 0.0f;
+    __half sMeanX = __ushort_as_half((unsigned short)0), sMeanY = sMeanX, sDepth = sMeanX;
     if (inRange) {
         do {
             GaussianIn g = loadGaussian<HALF>(gaussians, lid);
@@ -477,24 +485,31 @@ __global__ void __launch_bounds__(256) project_cull_mono_kernel(const void* __re
             TileBounds tb = computeTileBounds(screenX, screenY, obbX, obbY, cam.width, cam.height, (int)cam.tilesX,
                                               (int)cam.tilesY);
 
-            // DFS.metal:166-205 on the quantised record (quirk Q3)
-            QuantSplat q = makeQuantSplat(hMeanX, hMeanY, thetaP, hS1, hS2, cO);
-            uint32_t cnt = 0;
-            if (q.d2Cutoff >= 0.0f) {
-                for (int ty = tb.minTY; ty <= tb.maxTY; ++ty)
-                    for (int tx = tb.minTX; tx <= tb.maxTX; ++tx)
-                        if (tileHit(q, tx, ty)) cnt++;
-            }
-            if (cnt == 0) break;  // (9) DFS.metal:207-212 (renderData stays written)
-
+            // DFS.metal:166-205 runs on the quantised record (quirk Q3); the walk itself is warp-cooperative below
+            q = makeQuantSplat(hMeanX, hMeanY, thetaP, hS1, hS2, cO);
+            bMinTX = tb.minTX; bMaxTX = tb.maxTX; bMinTY = tb.minTY; bMaxTY = tb.maxTY;
+            if (q.d2Cutoff >= 0.0f && tb.valid) nTiles = (uint32_t)((tb.maxTX - tb.minTX + 1) * (tb.maxTY - tb.minTY + 1));
+            keyDepth = depth;
+            sMeanX = hMeanX; sMeanY = hMeanY; sDepth = hDepth;
+            sColor = (uint32_t)cR | ((uint32_t)cG << 8) | ((uint32_t)cB << 16) | ((uint32_t)cO << 24);
+            alive = true;
+        } while (false);
+    }
+    // exact ellipse-vs-tile count, 32 tiles of the warp's concatenated AABBs per step
+    const uint32_t cnt = warpCountTiles(s_work[threadIdx.x >> 5], nTiles, q, bMinTX, bMinTY, bMaxTX - bMinTX + 1);
+    if (inRange) {
+        if (alive && cnt > 0) {  // cnt == 0 is exit (9), DFS.metal:207-212 (renderData stays written)
             // the pre-expanded blend record (conicFromThetaSigmas on the same quantised values)
-            if (o.blendSplats) storeBlendSplat(o.blendSplats + gid, q, hMeanX, hMeanY, cR, cG, cB, cO, hDepth);
-            reinterpret_cast<int4*>(o.bounds)[gid] = make_int4(tb.minTX, tb.maxTX, tb.minTY, tb.maxTY);
+            if (o.blendSplats)
+                storeBlendSplat(o.blendSplats + gid, q, sMeanX, sMeanY, (uint8_t)sColor, (uint8_t)(sColor >> 8), (uint8_t)(sColor >> 16),
+                                (uint8_t)(sColor >> 24), sDepth);
+            reinterpret_cast<int4*>(o.bounds)[gid] = make_int4(bMinTX, bMaxTX, bMinTY, bMaxTY);
             o.nTouched[gid] = cnt;
             touched = cnt;
-            key = float_to_sortable_uint(depth);
-        } while (false);
-        if (touched == 0) writeCulled(o, gid);
+            key = float_to_sortable_uint(keyDepth);
+        } else {
+            writeCulled(o, gid);
+        }
     }
     compactAndCount(inRange, gid, touched, key, tile, numTiles, o);
 }

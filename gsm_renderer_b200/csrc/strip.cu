@@ -48,33 +48,34 @@ __global__ void __launch_bounds__(256) ingest_records_kernel(const SplatRecord* 
     const uint32_t numTiles = (recordCount + 255u) / 256u;
     const uint32_t j = tile * 256u + threadIdx.x;
     const bool inRange = j < recordCount;
-    uint32_t touched = 0, key = 0xFFFFFFFFu, gid = 0;
+    __shared__ WarpTileWork s_work[8];
+    uint32_t touched = 0, key = 0xFFFFFFFFu, gid = 0, nTiles = 0, keyIn = 0;
+    uint4 rd = make_uint4(0, 0, 0, 0);
+    int minTX = 0, maxTX = -1, minTY = 0, maxTY = -1;
+    QuantSplat q = {};
     if (inRange) {
         const uint4* s = reinterpret_cast<const uint4*>(records + j);
-        const uint4 rd = __ldg(s);
+        rd = __ldg(s);
         const uint4 bw = __ldg(s + 1);
         const uint4 kw = __ldg(s + 2);
         gid = kw.z;
-        int minTX = (int)bw.x, maxTX = (int)bw.y, minTY = max((int)bw.z, rowFirst), maxTY = min((int)bw.w, rowLast);
-        const __half hMeanX = __ushort_as_half((unsigned short)(rd.x & 0xFFFFu)), hMeanY = __ushort_as_half((unsigned short)(rd.x >> 16));
-        const __half hS1 = __ushort_as_half((unsigned short)(rd.y >> 16)), hS2 = __ushort_as_half((unsigned short)(rd.z & 0xFFFFu));
-        const __half hDepth = __ushort_as_half((unsigned short)(rd.z >> 16));
-        const uint8_t cR = (uint8_t)rd.w, cG = (uint8_t)(rd.w >> 8), cB = (uint8_t)(rd.w >> 16), cO = (uint8_t)(rd.w >> 24);
-        QuantSplat q = makeQuantSplat(hMeanX, hMeanY, (uint16_t)(rd.y & 0xFFFFu), hS1, hS2, cO);
-        uint32_t cnt = 0;
-        if (q.d2Cutoff >= 0.0f && minTX <= maxTX) {
-            for (int ty = minTY; ty <= maxTY; ++ty)
-                for (int tx = minTX; tx <= maxTX; ++tx)
-                    if (tileHit(q, tx, ty)) cnt++;
-        }
-        if (cnt > 0) {
-            reinterpret_cast<uint4*>(o.renderData)[gid] = rd;
-            reinterpret_cast<int4*>(o.bounds)[gid] = make_int4(minTX, maxTX, minTY, maxTY);
-            o.nTouched[gid] = cnt;
-            storeBlendSplat(o.blendSplats + gid, q, hMeanX, hMeanY, cR, cG, cB, cO, hDepth);
-            touched = cnt;
-            key = kw.x;
-        }
+        keyIn = kw.x;
+        minTX = (int)bw.x; maxTX = (int)bw.y; minTY = max((int)bw.z, rowFirst); maxTY = min((int)bw.w, rowLast);
+        q = makeQuantSplat(__ushort_as_half((unsigned short)(rd.x & 0xFFFFu)), __ushort_as_half((unsigned short)(rd.x >> 16)),
+                           (uint16_t)(rd.y & 0xFFFFu), __ushort_as_half((unsigned short)(rd.y >> 16)),
+                           __ushort_as_half((unsigned short)(rd.z & 0xFFFFu)), (uint8_t)(rd.w >> 24));
+        if (q.d2Cutoff >= 0.0f && minTX <= maxTX && minTY <= maxTY) nTiles = (uint32_t)((maxTX - minTX + 1) * (maxTY - minTY + 1));
+    }
+    const uint32_t cnt = warpCountTiles(s_work[threadIdx.x >> 5], nTiles, q, minTX, minTY, maxTX - minTX + 1);
+    if (inRange && cnt > 0) {
+        reinterpret_cast<uint4*>(o.renderData)[gid] = rd;
+        reinterpret_cast<int4*>(o.bounds)[gid] = make_int4(minTX, maxTX, minTY, maxTY);
+        o.nTouched[gid] = cnt;
+        storeBlendSplat(o.blendSplats + gid, q, __ushort_as_half((unsigned short)(rd.x & 0xFFFFu)),
+                        __ushort_as_half((unsigned short)(rd.x >> 16)), (uint8_t)rd.w, (uint8_t)(rd.w >> 8), (uint8_t)(rd.w >> 16),
+                        (uint8_t)(rd.w >> 24), __ushort_as_half((unsigned short)(rd.z >> 16)));
+        touched = cnt;
+        key = keyIn;
     }
     compactAndCount(inRange, gid, touched, key, tile, numTiles, o);
 }

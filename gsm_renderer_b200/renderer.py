@@ -287,7 +287,7 @@ def probe_math(op: int, a, b=None, device: int = -1) -> np.ndarray:
     """gsm_probe_math: device restatement of the canonical math (0 sin, 1 cos, 2 log, 3 atan2, 4 powr 2.4,
     5 half exp, 6 float->half, 7 packed half exp)."""
     a = np.ascontiguousarray(a)
-    out = np.empty(a.shape, np.uint16 if op in (5, 6, 7) else np.float32)
+    out = np.empty(a.shape, np.uint16 if op in (5, 6, 7, 8) else np.float32)
     bp = None if b is None else N.ptr(np.ascontiguousarray(b))
     _check(N.lib().gsm_probe_math(device, op, N.ptr(a), bp, N.ptr(out), a.size))
     return out

@@ -39,7 +39,9 @@ def test_math_probes_bit_exact(oracle):
     bits = np.arange(65536, dtype=np.uint16)
     ref = oracle.probe_hexp(bits)
     assert np.array_equal(probe_math(5, bits), ref)          # scalar half exp, all 65536 inputs
-    assert np.array_equal(probe_math(7, bits), ref)          # packed half2 variant used by the blend
+    assert np.array_equal(probe_math(7, bits), ref)          # packed half2 variant
+    notnan = ~np.isnan(bits.view(np.float16))
+    assert np.array_equal(probe_math(8, bits)[notnan], ref[notnan])  # FFMA2 form used by the blend kernel
     xf = np.concatenate([rng.normal(0, 300, 200_000), [65504, 65520, 1e10, -1e10, 6e-8, 2.9e-8, 0.0]]).astype(np.float32)
     assert np.array_equal(probe_math(6, xf), oracle.probe_f2h(xf))
 
