@@ -1,0 +1,148 @@
+// DepthFirstRenderer.hpp -- header-only C++ facade over the C ABI (gsm.h), mirroring the reference's Swift
+// surface name for name so host code reads like the reference's:
+//   RendererConfig / GaussianInput / CameraParams / StereoCameraParams / StereoRenderTarget / RendererError
+//     <- Sources/Renderer/Shared/GaussianRendererProtocol.swift:9-67,195-239,274-324
+//   DepthFirstRenderer(init, render, renderStereo, lastGPUTime)
+//     <- Sources/Renderer/DepthFirstRenderer/DepthFirstRenderer.swift:45-101,166-235
+//   debugRead*  <- Tests/RendererTests/DepthFirstUnitTests.swift:911-1252
+// The Swift toolchain is absent in this image, so this facade (compiled, reference is compiled code) and the
+// Python mirror (gsm_renderer_b200/renderer.py) are the executable hosts; swift/ holds the same facade as
+// Swift source.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gsm.h"
+#include "gsm_types.h"
+
+namespace gsm {
+
+enum class RenderPrecision : uint32_t { float32 = GSM_PRECISION_FLOAT32, float16 = GSM_PRECISION_FLOAT16 };
+enum class GaussianColorSpace : uint32_t { linear = GSM_COLORSPACE_LINEAR, srgb = GSM_COLORSPACE_SRGB };
+enum class RadixSortKeyPrecision : uint32_t { bits16 = GSM_KEY_BITS16, bits32 = GSM_KEY_BITS32 };
+
+// RendererError: one exception type, `status` is the case.
+class RendererError : public std::runtime_error {
+public:
+    RendererError(gsm_status s, const std::string& detail)
+        : std::runtime_error(std::string(gsm_status_string(s)) + (detail.empty() ? "" : ": " + detail)), status(s) {}
+    gsm_status status;
+};
+
+inline void check(gsm_status s) {
+    if (s != GSM_OK) throw RendererError(s, gsm_last_error_string());
+}
+
+struct RendererConfig {
+    int maxGaussians = 6000000;
+    int maxWidth = 1920;
+    int maxHeight = 1080;
+    RenderPrecision precision = RenderPrecision::float16;
+    GaussianColorSpace gaussianColorSpace = GaussianColorSpace::srgb;
+    bool backToFront = false;  // ignored by DepthFirst (as is colorFormat)
+};
+
+// MTLBuffer -> device pointer
+struct GaussianInput {
+    const void* gaussians;   // PackedWorldGaussian (48 B) or PackedWorldGaussianHalf (32 B)
+    const void* harmonics;
+    int gaussianCount;
+    int shComponents;
+};
+
+struct CameraParams {
+    std::array<float, 16> viewMatrix;        // column-major (simd_float4x4)
+    std::array<float, 16> projectionMatrix;
+    std::array<float, 3> position;
+    float focalX = 0, focalY = 0;
+    float near = 0.1f, far = 10.0f;
+    gsm_camera native() const {
+        gsm_camera c{};
+        for (int i = 0; i < 16; ++i) { c.viewMatrix[i] = viewMatrix[i]; c.projectionMatrix[i] = projectionMatrix[i]; }
+        for (int i = 0; i < 3; ++i) c.position[i] = position[i];
+        c.focalX = focalX; c.focalY = focalY; c.nearPlane = near; c.farPlane = far;
+        return c;
+    }
+};
+
+struct StereoCameraParams { CameraParams leftEye, rightEye; };
+
+// StereoRenderTarget.sideBySide(colorTexture:depthTexture:) -- rgba16f (2*width) x height
+struct StereoRenderTarget {
+    void* colorTexture;
+    void* depthTexture = nullptr;  // ignored by the reference too (DepthFirstRenderer.swift:472)
+    static StereoRenderTarget sideBySide(void* color, void* depth = nullptr) { return StereoRenderTarget{color, depth}; }
+};
+
+class DepthFirstRenderer {
+public:
+    explicit DepthFirstRenderer(int device = -1, RendererConfig config = RendererConfig(),
+                                RadixSortKeyPrecision depthSortKeyPrecision = RadixSortKeyPrecision::bits32,
+                                RadixSortKeyPrecision tileIdPrecision = RadixSortKeyPrecision::bits16) {
+        gsm_config c;
+        gsm_config_default(&c);
+        c.maxGaussians = (uint32_t)config.maxGaussians;
+        c.maxWidth = (uint32_t)config.maxWidth;
+        c.maxHeight = (uint32_t)config.maxHeight;
+        c.precision = (uint32_t)config.precision;
+        c.gaussianColorSpace = (uint32_t)config.gaussianColorSpace;
+        c.depthSortKeyPrecision = (uint32_t)depthSortKeyPrecision;
+        c.tileIdPrecision = (uint32_t)tileIdPrecision;
+        c.device = device;
+        check(gsm_renderer_create(&c, &h_));
+    }
+    ~DepthFirstRenderer() { gsm_renderer_destroy(h_); }
+    DepthFirstRenderer(const DepthFirstRenderer&) = delete;
+    DepthFirstRenderer& operator=(const DepthFirstRenderer&) = delete;
+
+    // commandBuffer = cudaStream_t; the caller synchronises it (commit + waitUntilCompleted)
+    void render(void* commandBuffer, void* colorTexture, void* depthTexture, const GaussianInput& input,
+                const CameraParams& camera, int width, int height) {
+        gsm_camera c = camera.native();
+        check(gsm_render(h_, commandBuffer, colorTexture, depthTexture, input.gaussians, input.harmonics,
+                         (uint32_t)input.gaussianCount, (uint32_t)input.shComponents, &c, (uint32_t)width, (uint32_t)height));
+    }
+    void renderStereo(void* commandBuffer, const StereoRenderTarget& target, const GaussianInput& input,
+                      const StereoCameraParams& camera, int width, int height) {
+        gsm_camera l = camera.leftEye.native(), r = camera.rightEye.native();
+        check(gsm_render_stereo(h_, commandBuffer, target.colorTexture, input.gaussians, input.harmonics,
+                                (uint32_t)input.gaussianCount, (uint32_t)input.shComponents, &l, &r, (uint32_t)width,
+                                (uint32_t)height));
+    }
+    double lastGPUTime() const { return gsm_last_gpu_time_ms(h_) * 1e-3; }
+
+    // white-box reads
+    GSMDepthFirstHeader debugReadHeader() {
+        GSMDepthFirstHeader h{};
+        check(gsm_debug_read(h_, nullptr, GSM_DBG_HEADER, &h, 0, 1));
+        return h;
+    }
+    uint32_t debugReadActiveTileCount() {
+        uint32_t v = 0;
+        check(gsm_debug_read(h_, nullptr, GSM_DBG_ACTIVE_TILE_COUNT, &v, 0, 1));
+        return v;
+    }
+    template <typename T>
+    std::vector<T> debugRead(gsm_debug_buffer which, size_t count, size_t first = 0) {
+        if (sizeof(T) != gsm_debug_element_size(h_, which)) throw RendererError(GSM_ERR_INVALID_ARGUMENT, "element size mismatch");
+        std::vector<T> v(count);
+        if (count) check(gsm_debug_read(h_, nullptr, which, v.data(), first, count));
+        return v;
+    }
+    std::vector<int32_t> debugReadSortedPrimitiveIndices(size_t n) { return debugRead<int32_t>(GSM_DBG_SORTED_PRIMITIVE_INDICES, n); }
+    std::vector<uint32_t> debugReadDepthKeys(size_t n) { return debugRead<uint32_t>(GSM_DBG_DEPTH_KEYS, n); }
+    std::vector<uint32_t> debugReadNTouchedTiles(size_t n) { return debugRead<uint32_t>(GSM_DBG_N_TOUCHED_TILES, n); }
+    std::vector<uint32_t> debugReadInstanceOffsets(size_t n) { return debugRead<uint32_t>(GSM_DBG_INSTANCE_OFFSETS, n); }
+    std::vector<int32_t> debugReadInstanceGaussianIndices(size_t n) { return debugRead<int32_t>(GSM_DBG_INSTANCE_GAUSSIAN_INDICES, n); }
+    std::vector<GSMGaussianHeader> debugReadTileHeaders(size_t n) { return debugRead<GSMGaussianHeader>(GSM_DBG_TILE_HEADERS, n); }
+
+    gsm_renderer* handle() const { return h_; }
+
+private:
+    gsm_renderer* h_ = nullptr;
+};
+
+}  // namespace gsm
