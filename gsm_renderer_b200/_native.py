@@ -42,6 +42,9 @@ EXPORTS = {
     "gsm_render_stereo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_uint32, C.c_uint32, C.POINTER(gsm_camera), C.POINTER(gsm_camera),
                                     C.c_uint32, C.c_uint32]),
+    "gsm_render_stereo_eyes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint32, C.c_uint32, C.POINTER(gsm_camera), C.POINTER(gsm_camera),
+                                         C.c_uint32, C.c_uint32, C.c_uint32]),
     "gsm_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                   C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_last_gpu_time_ms": (C.c_double, [C.c_void_p]),

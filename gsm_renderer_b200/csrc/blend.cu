@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
                                                                      const GSMStereoTiledRenderData* __restrict__ splats,
                                                                      const int32_t* __restrict__ instanceIdx, uint32_t width,
                                                                      uint32_t height, uint32_t tilesX,
-                                                                     __half* __restrict__ dstSideBySide, int flipY) {
+                                                                     __half* __restrict__ dstSideBySide, int flipY, int eyeMask) {
     __shared__ uint4 s_rec[kBlendChunk][2];
     __shared__ uint32_t s_valid[kBlendChunk];
+    const bool doL = (eyeMask & 1) != 0, doR = (eyeMask & 2) != 0;  // one-eye-per-GPU split
     const unsigned tid = threadIdx.x;
     const uint32_t tileX = blockIdx.x % tilesX, tileY = blockIdx.x / tilesX;
     const uint32_t tile = tileY * tilesX + tileX;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
         __syncthreads();
         if (!done) {
             for (uint32_t j = 0; j < n; ++j) {
-                const bool closedL = quadClosed(qL.T0, qL.T1, thr), closedR = quadClosed(qR.T0, qR.T1, thr);
+                const bool closedL = !doL || quadClosed(qL.T0, qL.T1, thr), closedR = !doR || quadClosed(qR.T0, qR.T1, thr);
                 if (closedL && closedR) { done = true; break; }  // DFS.metal:1868-1871
                 if (!s_valid[j]) continue;
                 const uint4 ra = s_rec[j][0], rb = s_rec[j][1];
@@ -246,13 +247,19 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
             const __half2 Lr = row ? qL.r1 : qL.r0, Lg = row ? qL.g1 : qL.g0, Lb = row ? qL.b1 : qL.b0;
             const __half2 Rr = row ? qR.r1 : qR.r0, Rg = row ? qR.g1 : qR.g0, Rb = row ? qR.b1 : qR.b0;
             uint2 v;
-            v.x = h2bits(__halves2half2(__low2half(Lr), __low2half(Lg))); v.y = h2bits(__halves2half2(__low2half(Lb), __low2half(aL)));
-            *reinterpret_cast<uint2*>(l) = v;
-            v.x = h2bits(__halves2half2(__low2half(Rr), __low2half(Rg))); v.y = h2bits(__halves2half2(__low2half(Rb), __low2half(aR)));
-            *reinterpret_cast<uint2*>(r) = v;
-            if (two) {
+            if (doL) {
+                v.x = h2bits(__halves2half2(__low2half(Lr), __low2half(Lg))); v.y = h2bits(__halves2half2(__low2half(Lb), __low2half(aL)));
+                *reinterpret_cast<uint2*>(l) = v;
+            }
+            if (doR) {
+                v.x = h2bits(__halves2half2(__low2half(Rr), __low2half(Rg))); v.y = h2bits(__halves2half2(__low2half(Rb), __low2half(aR)));
+                *reinterpret_cast<uint2*>(r) = v;
+            }
+            if (two && doL) {
                 v.x = h2bits(__halves2half2(__high2half(Lr), __high2half(Lg))); v.y = h2bits(__halves2half2(__high2half(Lb), __high2half(aL)));
                 *reinterpret_cast<uint2*>(l + 4) = v;
+            }
+            if (two && doR) {
                 v.x = h2bits(__halves2half2(__high2half(Rr), __high2half(Rg))); v.y = h2bits(__halves2half2(__high2half(Rb), __high2half(aR)));
                 *reinterpret_cast<uint2*>(r + 4) = v;
             }
@@ -272,10 +279,9 @@ cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const B
 
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
-                              __half* dstSideBySide, __half* intermediate, int flipY) {
-    (void)intermediate;
+                              __half* dstSideBySide, int eyeMask, int flipY) {
     blend_stereo_kernel<<<tilesX * tilesY, kBlendThreads, 0, s>>>(lowerBounds, splats, instanceIdx, width, height, tilesX,
-                                                                   dstSideBySide, flipY);
+                                                                   dstSideBySide, flipY, eyeMask);
     return cudaGetLastError();
 }
 

@@ -373,7 +373,15 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
 gsm_status gsm_render_stereo(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians, const void* harmonics,
                              uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* leftEye, const gsm_camera* rightEye,
                              uint32_t width, uint32_t height) {
+    return gsm_render_stereo_eyes(r, stream, colorSideBySide, gaussians, harmonics, gaussianCount, shComponents, leftEye, rightEye,
+                                  width, height, 3u);
+}
+
+gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians,
+                                  const void* harmonics, uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* leftEye,
+                                  const gsm_camera* rightEye, uint32_t width, uint32_t height, uint32_t eyeMask) {
     if (!r || !leftEye || !rightEye) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if ((eyeMask & 3u) == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "eyeMask selects no eye");
     if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;  // DFR.swift:478,607
     gsm_status st = validateFrame(r, width, height, gaussians, harmonics, colorSideBySide);
     if (st != GSM_OK) return st;
@@ -412,7 +420,7 @@ gsm_status gsm_render_stereo(gsm_renderer* r, void* stream, void* colorSideBySid
     if (st != GSM_OK) return st;
     // steps 9+10: clear, blend both eyes, copy into the side-by-side target (DFR.swift:789-830), fused
     GSM_CUDA(launchBlendStereo(s, res.lowerBounds, (const GSMStereoTiledRenderData*)res.renderData, res.instIdx[0], width, height,
-                               tilesX, tilesY, (__half*)colorSideBySide, nullptr, r->cfg.stereoCopyFlipY ? 1 : 0), "stereo blend");
+                               tilesX, tilesY, (__half*)colorSideBySide, (int)(eyeMask & 3u), r->cfg.stereoCopyFlipY ? 1 : 0), "stereo blend");
     recordStage(r, s, 7);
     recordStage(r, s, 8);
     if (r->profiling) r->evRecorded = true;

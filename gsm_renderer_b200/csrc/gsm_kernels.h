@@ -60,7 +60,7 @@ cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const B
                             uint32_t tileRowCount, __half* color, __half* depth);
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
-                              __half* dstSideBySide, __half* intermediate, int flipY);
+                              __half* dstSideBySide, int eyeMask, int flipY);
 
 // strip-sharded frame (strip.cu)
 cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,

@@ -187,15 +187,33 @@ class DepthFirstRenderer:
         self._stereo_last = False
 
     def renderStereo(self, commandBuffer, target: StereoRenderTarget, input: GaussianInput,
-                     camera: StereoCameraParams, width: int, height: int) -> None:
+                     camera: StereoCameraParams, width: int, height: int, eyeMask: int = 3) -> None:
+        """eyeMask (bit 0 left, bit 1 right) is the one-eye-per-GPU extension; 3 is the reference behaviour."""
         if target.kind != "sideBySide":
             raise NotImplementedError("StereoRenderTarget.foveated needs a rasterization-rate map (visionOS only)")
         l, r = camera.leftEye.to_native(), camera.rightEye.to_native()
-        _check(self._lib.gsm_render_stereo(self._h, N.stream_handle(commandBuffer), N.ptr(target.colorTexture),
-                                           N.ptr(input.gaussians), N.ptr(input.harmonics),
-                                           int(input.gaussianCount), int(input.shComponents), C.byref(l),
-                                           C.byref(r), int(width), int(height)))
+        _check(self._lib.gsm_render_stereo_eyes(self._h, N.stream_handle(commandBuffer), N.ptr(target.colorTexture),
+                                                N.ptr(input.gaussians), N.ptr(input.harmonics),
+                                                int(input.gaussianCount), int(input.shComponents), C.byref(l),
+                                                C.byref(r), int(width), int(height), int(eyeMask)))
         self._stereo_last = True
+
+    # -- strip-sharded single frame (multi-GPU helper; gsm_strip_project / gsm_strip_render)
+    def stripProject(self, commandBuffer, gaussiansShard, harmonicsShard, gidFirst: int, gidCount: int, shComponents: int,
+                     camera: CameraParams, width: int, height: int, recordsOut) -> int:
+        cam = camera.to_native()
+        n = C.c_uint32(0)
+        _check(self._lib.gsm_strip_project(self._h, N.stream_handle(commandBuffer), N.ptr(gaussiansShard), N.ptr(harmonicsShard),
+                                           int(gidFirst), int(gidCount), int(shComponents), C.byref(cam), int(width),
+                                           int(height), N.ptr(recordsOut), C.byref(n)))
+        return int(n.value)
+
+    def stripRender(self, commandBuffer, colorTexture, depthTexture, records, recordCount: int, width: int, height: int,
+                    tileRowFirst: int, tileRowCount: int) -> None:
+        _check(self._lib.gsm_strip_render(self._h, N.stream_handle(commandBuffer), N.ptr(colorTexture), N.ptr(depthTexture),
+                                          N.ptr(records), int(recordCount), int(width), int(height), int(tileRowFirst),
+                                          int(tileRowCount)))
+        self._stereo_last = False
 
     def renderHost(self, hostGaussians, hostHarmonics, gaussianCount, shComponents, camera: CameraParams,
                    width, height, hostColor, hostDepth=None) -> None:

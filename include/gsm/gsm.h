@@ -92,6 +92,14 @@ gsm_status gsm_render_stereo(gsm_renderer* r, void* stream, void* colorSideBySid
                              const gsm_camera* leftEye, const gsm_camera* rightEye, uint32_t width,
                              uint32_t height);
 
+/* One-eye-per-GPU split of the joint stereo frame (no reference counterpart): runs the identical
+ * joint stages 1-7 and blends only the eyes in eyeMask (bit 0 = left, bit 1 = right) into their half of the
+ * side-by-side target; the other half is left untouched. eyeMask 3 == gsm_render_stereo. */
+gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians,
+                                  const void* harmonics, uint32_t gaussianCount, uint32_t shComponents,
+                                  const gsm_camera* leftEye, const gsm_camera* rightEye, uint32_t width,
+                                  uint32_t height, uint32_t eyeMask);
+
 /* Same frame as gsm_render but with HOST buffers: copies inputs host->device, renders, copies the images
  * device->host and synchronises. This is what a host with no device allocator of its own calls (and what
  * bench.py times as `e2e`). hostDepth may be NULL. */
