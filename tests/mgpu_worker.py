@@ -22,7 +22,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    cl = syn.synthetic_cloud(200_000, 3, seed=17, scale_median=0.02)
+    cl = syn.synthetic_cloud(200_000, 3, seed=17, scale_median=0.015)
     W, H = 1920, 1080
     g, h = pu.make_scene_inputs(cl, "float16")
     cam = pu.default_camera(W, H)
