@@ -67,7 +67,8 @@ class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region (NVML every 2 ms; nvidia-smi as fallback)."""
 
     def __init__(self, gpu_index=0):
-        self.gpu, self.sm, self.mx, self.reasons, self.power = gpu_index, [], None, set(), []
+        self.gpu, self.sm, self.mx, self.reasons, self.power = gpu_index, [], None, [], []
+        self.ts = []
         self._stop = threading.Event()
         self.t = None
         self.src = "nvml"
@@ -86,15 +87,14 @@ class ClockSampler:
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self._stop.is_set():
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                c = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = int(get_reasons(h))
-                for b, n in bits.items():
-                    if r & b:
-                        self.reasons.add(n)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.ts.append(time.perf_counter()); self.sm.append(c); self.power.append(pw)
+                self.reasons.append([n for b, n in bits.items() if r & b])
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def _loop_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -104,11 +104,9 @@ class ClockSampler:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.sm.append(float(out[0]))
+                self.ts.append(time.perf_counter()); self.sm.append(float(out[0])); self.power.append(0.0)
                 self.mx = float(out[1])
-                for n, v in zip(names, out[2:6]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                self.reasons.append([n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")])
             except Exception:
                 time.sleep(0.05)
 
@@ -121,13 +119,17 @@ class ClockSampler:
         self.t = threading.Thread(target=target, daemon=True)
         self.t.start()
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         self._stop.set()
         if self.t:
             self.t.join(timeout=3)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.src,
-                "power_w_max": max(self.power) if self.power else None}
+        idx = [i for i, t in enumerate(self.ts) if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        sm = [self.sm[i] for i in idx]
+        reasons = sorted({n for i in idx for n in self.reasons[i]})
+        pw = [self.power[i] for i in idx]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(sm), "samples_total": len(self.ts), "source": self.src,
+                "power_w_max": max(pw) if pw else None}
 
 
 def build_workload(name, seed=42):
@@ -243,8 +245,16 @@ def main():
     def step():
         r.render(stream, color, depth, inp, cam, W, H)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    extra = 0
+    while time.perf_counter() - t_w < 0.3:  # let clocks settle under load before timing (untimed extra warm-up)
+        step()
+        extra += 1
     torch.cuda.synchronize()
     hd = r.debugReadHeader()
     V, I = hd.visibleCount, hd.totalInstances
@@ -254,11 +264,9 @@ def main():
 
     # ---- timed region: per-step CUDA events on the launching stream, L2 flushed between steps
     r.setProfiling(True)
-    sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stage_acc = {}
@@ -273,8 +281,9 @@ def main():
         for k, v in r.stageTimesMs().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     torch.cuda.synchronize()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    wall1 = time.perf_counter()
+    wall = wall1 - wall0
+    clocks = sampler.stop(wall0, wall1)
     r.setProfiling(False)
     step_ms = [ev0[i].elapsed_time(ev1[i]) for i in range(args.steps)]
     total_ms = float(sum(step_ms))
@@ -361,7 +370,8 @@ def main():
                    "tiles": T, "maxInstancesPerTile": max_per_tile, "overflow": hd.overflow,
                    "parallelism": f"views sharded over {world} GPU(s), no collective",
                    "l2": "inputs+arena > L2 and " + ("no flush" if args.no_flush else "L2 flushed between steps (256 MiB write, untimed)"),
-                   "timing": "per-step CUDA events on the launching stream, summed; max over ranks"},
+                   "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
+                   "warmup_extra_steps": extra},
         "mtile_instances_per_s": (I / (sort_blend_ms * 1e-3) / 1e6) if sort_blend_ms > 0 else None,
         "stage_ms": stage_ms,
         "roofline": roofline,

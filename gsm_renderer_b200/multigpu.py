@@ -55,6 +55,12 @@ def partition_tile_rows(tiles_y: int, world: int, row_weights: Sequence[float] |
     return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(world)]
 
 
+def _bytes(t):
+    """Contiguous uint8 copy of a tensor (NCCL has no int16; images travel as raw bytes)."""
+    import torch
+    return t.contiguous().view(-1).view(torch.uint8)
+
+
 def all_gather_records(dist, local_records, local_count: int, world: int, device):
     """All-gather-v of compacted splat records in rank order. local_records: uint8 tensor [>= local_count*48].
     Returns (records uint8 [total*48], counts list). One small all-gather of counts + one padded all-gather."""
@@ -108,11 +114,11 @@ def gather_strips(dist, rank: int, world: int, color, strips: List[Tuple[int, in
         if y1 <= y0:
             continue
         if rank == r:
-            dist.send(color[y0:y1].contiguous(), dst=root)
+            dist.send(_bytes(color[y0:y1]), dst=root)
         elif rank == root:
-            buf = color[y0:y1].contiguous()
+            buf = _bytes(color[y0:y1])
             dist.recv(buf, src=r)
-            color[y0:y1] = buf
+            color[y0:y1] = buf.view(color.dtype).view(color[y0:y1].shape)
     return color
 
 
@@ -125,9 +131,9 @@ def render_stereo_split(renderer, dist, rank: int, world: int, stream, target, g
     eye = rank % 2
     renderer.renderStereo(stream, StereoRenderTarget.sideBySide(target), gaussian_input, cameras, width, height, eyeMask=1 << eye)
     if rank == 1:
-        dist.send(target[:, width:].contiguous(), dst=0)
+        dist.send(_bytes(target[:, width:]), dst=0)
     elif rank == 0:
-        buf = target[:, width:].contiguous()
+        buf = _bytes(target[:, width:])
         dist.recv(buf, src=1)
-        target[:, width:] = buf
+        target[:, width:] = buf.view(target.dtype).view(target[:, width:].shape)
     return target
