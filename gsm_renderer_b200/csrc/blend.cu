@@ -73,24 +73,42 @@ __device__ __forceinline__ void storePixelRow(__half* color, __half* depth, uint
     }
 }
 
+// Staged form of one splat for one tile. p = (dx*dx*cxx + dy*dy*cyy) + dx*dy*cxy2 (DFS.metal:1770) splits into a
+// per-COLUMN term T0 = (dx*dx)*cxx, a per-ROW term T1 = (dy*dy)*cyy and the per-pixel cross term; T0/T1/dx/dy are
+// the same half operations on the same operands whichever thread evaluates them, so they are computed once
+// per (splat, column pair) and (splat, row pair) by the staging thread instead of once per pixel (ncu r1_v2:
+// the kernel was FMA-pipe bound at 73 %, 19 packed half ops per far pixel quad; this form needs 8).
+struct StagedSplat {
+    uint2 col[8];  // per x pair k: {T0(x=2k), T0(2k+1)} , {dx(2k), dx(2k+1)}
+    uint2 row[8];  // per y pair k: {T1(y=2k), T1(2k+1)} , {dy(2k), dy(2k+1)}
+    uint4 m0;      // cxy2|cxy2, op|op, r|r, g|g
+    uint4 m1;      // b|b, depth|depth, valid, -
+};
+
 __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_t* __restrict__ lowerBounds,
                                                                    const BlendSplat* __restrict__ splats,
                                                                    const int32_t* __restrict__ instanceIdx, uint32_t width,
                                                                    uint32_t height, uint32_t tilesX, uint32_t tileRowFirst,
                                                                    __half* __restrict__ color, __half* __restrict__ depth) {
-    __shared__ uint4 s_rec[kBlendChunk][2];
+    __shared__ StagedSplat s_sp[kBlendChunk];
     const unsigned tid = threadIdx.x;
+    const unsigned lx = tid & 7u, ly = tid >> 3;
     const uint32_t tileX = blockIdx.x % tilesX, tileY = tileRowFirst + blockIdx.x / tilesX;
     const uint32_t tile = tileY * tilesX + tileX;
     const uint32_t start = lowerBounds[tile];
     const uint32_t end = lowerBounds[tile + 1];
     const uint32_t count = end > start ? end - start : 0u;
 
-    const uint32_t baseX = tileX * 16u + (tid & 7u) * 2u, baseY = tileY * 16u + (tid >> 3) * 2u;
-    const __half2 px = __halves2half2(__uint2half_rn(baseX), __uint2half_rn(baseX + 1u));  // half(baseX+k), quirk Q7
-    const __half2 py0 = __half2half2(__uint2half_rn(baseY)), py1 = __half2half2(__uint2half_rn(baseY + 1u));
+    const uint32_t baseX = tileX * 16u + lx * 2u, baseY = tileY * 16u + ly * 2u;
     const __half thr = __float2half_rn(1.0f / 255.0f);  // half(1.0h/255.0h): both roundings agree (0x1C04)
     const __half2 h099 = h2(0.99f), negHalf = h2(-0.5f), zero = h2(0.0f), one = h2(1.0f), farP = h2(35.0f);
+    // pixel coordinates of the tile as half (quirk Q7): pair k = (16*tile + 2k, +1)
+    __half2 pxs[8], pys[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        pxs[k] = __halves2half2(__uint2half_rn(tileX * 16u + 2u * k), __uint2half_rn(tileX * 16u + 2u * k + 1u));
+        pys[k] = __halves2half2(__uint2half_rn(tileY * 16u + 2u * k), __uint2half_rn(tileY * 16u + 2u * k + 1u));
+    }
 
     QuadState q;
     q.T0 = one; q.T1 = one;
@@ -101,20 +119,10 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
         const uint32_t n = min((uint32_t)kBlendChunk, count - base);
         if (tid < n) {
             const int32_t gi = __ldg(instanceIdx + start + base + tid);
+            StagedSplat& sp = s_sp[tid];
             if (gi >= 0) {
                 const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
-                s_rec[tid][0] = __ldg(src);
-                s_rec[tid][1] = __ldg(src + 1);
-            } else {
-                s_rec[tid][1] = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
-            }
-        }
-        __syncthreads();
-        if (!done) {
-            for (uint32_t j = 0; j < n; ++j) {
-                if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
-                const uint4 ra = s_rec[j][0], rb = s_rec[j][1];
-                if (rb.y == 0u) continue;
+                const uint4 ra = __ldg(src), rb = __ldg(src + 1);
                 const __half2 mean = *reinterpret_cast<const __half2*>(&ra.x);
                 const __half2 cxx_cyy = *reinterpret_cast<const __half2*>(&ra.y);
                 const __half2 cxy2_op = *reinterpret_cast<const __half2*>(&ra.z);
@@ -122,17 +130,46 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                 const __half2 b_d = *reinterpret_cast<const __half2*>(&rb.x);
                 const __half2 mx = __low2half2(mean), my = __high2half2(mean);
                 const __half2 cxx = __low2half2(cxx_cyy), cyy = __high2half2(cxx_cyy);
-                const __half2 cxy2 = __low2half2(cxy2_op), op = __high2half2(cxy2_op);
-                const __half2 dx = __hsub2_rn(px, mx);
-                const __half2 dy0 = __hsub2_rn(py0, my), dy1 = __hsub2_rn(py1, my);
-                const __half2 p0 = power(dx, dy0, cxx, cyy, cxy2), p1 = power(dx, dy1, cxx, cyy, cxy2);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const __half2 dx = __hsub2_rn(pxs[k], mx);
+                    const __half2 t0 = __hmul2_rn(__hmul2_rn(dx, dx), cxx);
+                    sp.col[k] = make_uint2(h2bits(t0), h2bits(dx));
+                    const __half2 dy = __hsub2_rn(pys[k], my);
+                    const __half2 t1 = __hmul2_rn(__hmul2_rn(dy, dy), cyy);
+                    sp.row[k] = make_uint2(h2bits(t1), h2bits(dy));
+                }
+                sp.m0 = make_uint4(h2bits(__low2half2(cxy2_op)), h2bits(__high2half2(cxy2_op)), h2bits(__low2half2(rg)),
+                                   h2bits(__high2half2(rg)));
+                sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 1u, 0u);
+            } else {
+                sp.m1 = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
+            }
+        }
+        __syncthreads();
+        if (!done) {
+            for (uint32_t j = 0; j < n; ++j) {
+                if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
+                const StagedSplat& sp = s_sp[j];
+                const uint4 m1 = sp.m1;
+                if (m1.z == 0u) continue;
+                const uint2 c = sp.col[lx], r = sp.row[ly];
+                const uint4 m0 = sp.m0;
+                const __half2 t0 = *reinterpret_cast<const __half2*>(&c.x), dx = *reinterpret_cast<const __half2*>(&c.y);
+                const __half2 t1p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
+                const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x);
+                // (t0 + t1) + (dx*dy)*cxy2 for the two rows of the quad
+                const __half2 p0 = __hadd2_rn(__hadd2_rn(t0, __low2half2(t1p)), __hmul2_rn(__hmul2_rn(dx, __low2half2(dyp)), cxy2));
+                const __half2 p1 = __hadd2_rn(__hadd2_rn(t0, __high2half2(t1p)), __hmul2_rn(__hmul2_rn(dx, __high2half2(dyp)), cxy2));
                 // p > 35 on all four pixels => -0.5h*p < -17.5 => exp() is exactly +0 => alphas are 0 => "continue"
                 // (NaN compares false and takes the full path)
                 if (__hbgt2(p0, farP) && __hbgt2(p1, farP)) continue;
+                const __half2 op = *reinterpret_cast<const __half2*>(&m0.y);
                 const __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p0))), h099);
                 const __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p1))), h099);
                 if (((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) == 0u) continue;  // all(alphas == 0), DFS.metal:1781
-                accumulate(q, a0, a1, __low2half2(rg), __high2half2(rg), __low2half2(b_d), __high2half2(b_d), true);
+                accumulate(q, a0, a1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
+                           *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
             }
         }
         if (__syncthreads_and(done ? 1 : 0)) break;

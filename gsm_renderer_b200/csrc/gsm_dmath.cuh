@@ -16,16 +16,10 @@ namespace gsm {
 #define GSM_THETA_PACK 0x1.45f1c0p+14f              // binary32(65535.0f / kPiF), GaussianShared.h:438
 #define GSM_THETA_UNPACK 0x1.922148p-15f            // binary32(kPiF / 65535.0f), GaussianShared.h:443
 
-__device__ __forceinline__ float dmax(float a, float b) {  // NaN operand loses; ties return b
-    if (a != a) return b;
-    if (b != b) return a;
-    return (a > b) ? a : b;
-}
-__device__ __forceinline__ float dmin(float a, float b) {
-    if (a != a) return b;
-    if (b != b) return a;
-    return (a < b) ? a : b;
-}
+// min/max: a NaN operand loses, -0 orders below +0 -- exactly PTX min.f32/max.f32, one FMNMX each
+// (the oracle states the same rule in gsmo_fmin/gsmo_fmax; probe ops 9/10 compare them bit for bit).
+__device__ __forceinline__ float dmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float dmin(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ float dclamp(float x, float lo, float hi) { return dmin(dmax(x, lo), hi); }
 __device__ __forceinline__ bool dfinite(float x) { return (__float_as_uint(x) & 0x7F800000u) != 0x7F800000u; }
 

@@ -32,6 +32,8 @@ __global__ void probe_kernel(int op, const void* a, const void* b, void* out, ui
             ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2_packed(v)));
             break;
         }
+        case 9: fo[i] = dmin(fa[i], fb[i]); break;
+        case 10: fo[i] = dmax(fa[i], fb[i]); break;
         default: break;
     }
 }

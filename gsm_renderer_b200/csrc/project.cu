@@ -12,6 +12,8 @@
 
 namespace gsm {
 
+constexpr uint32_t kProjThreads = 128;  // small CTAs: a slow warp (large splat) pins fewer sibling warp slots
+
 struct V3 { float x, y, z; };
 struct V4 { float x, y, z, w; };
 struct M3 { V3 c0, c1, c2; };
@@ -402,7 +404,7 @@ __device__ __forceinline__ V3 computeSHColor(const void* harmonics, uint32_t gid
 
 // ---------------------------------------------------------------- mono kernel
 template <bool HALF, int DEG>
-__global__ void __launch_bounds__(256) project_cull_mono_kernel(const void* __restrict__ gaussians,
+__global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const void* __restrict__ gaussians,
                                                                 const void* __restrict__ harmonics,
                                                                 const __grid_constant__ MonoCam cam, ProjectOut o) {
     __shared__ uint32_t s_tile;
@@ -410,12 +412,14 @@ __global__ void __launch_bounds__(256) project_cull_mono_kernel(const void* __re
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t N = cam.gaussianCount;
-    const uint32_t numTiles = (N + 255u) / 256u;
-    const uint32_t lid = tile * 256u + threadIdx.x;  // index into the (possibly sharded) input arrays
+    const uint32_t numWarpTiles = (N + 31u) / 32u;
+    const uint32_t warpTile = tile * (kProjThreads / 32) + (threadIdx.x >> 5);
+    if (warpTile >= numWarpTiles) return;  // whole warp past the end
+    const uint32_t lid = tile * kProjThreads + threadIdx.x;  // index into the (possibly sharded) input arrays
     const uint32_t gid = o.gidFirst + lid;            // global Gaussian id: what every output is keyed by
     const bool inRange = lid < N;
 
-    __shared__ WarpTileWork s_work[8];
+    __shared__ WarpTileWork s_work[kProjThreads / 32];
     uint32_t touched = 0, key = 0xFFFFFFFFu;
     // state carried from the per-lane projection to the warp-cooperative tile walk
     bool alive = false;
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(256) project_cull_mono_kernel(const void* __re
             writeCulled(o, gid);
         }
     }
-    compactAndCount(inRange, gid, touched, key, tile, numTiles, o);
+    compactAndCount(inRange, gid, touched, key, warpTile, numWarpTiles, o);
 }
 
 // ---------------------------------------------------------------- stereo
@@ -575,7 +579,7 @@ __device__ __forceinline__ void conicFromThetaSigmasF(float theta, float sigma1,
 }
 
 template <bool HALF, int DEG>
-__global__ void __launch_bounds__(256) project_cull_stereo_kernel(const void* __restrict__ gaussians,
+__global__ void __launch_bounds__(kProjThreads) project_cull_stereo_kernel(const void* __restrict__ gaussians,
                                                                   const void* __restrict__ harmonics,
                                                                   const __grid_constant__ StereoCam cam, ProjectOut o) {
     __shared__ uint32_t s_tile;
@@ -583,8 +587,10 @@ __global__ void __launch_bounds__(256) project_cull_stereo_kernel(const void* __
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t N = cam.gaussianCount;
-    const uint32_t numTiles = (N + 255u) / 256u;
-    const uint32_t lid = tile * 256u + threadIdx.x;  // index into the (possibly sharded) input arrays
+    const uint32_t numWarpTiles = (N + 31u) / 32u;
+    const uint32_t warpTile = tile * (kProjThreads / 32) + (threadIdx.x >> 5);
+    if (warpTile >= numWarpTiles) return;  // whole warp past the end
+    const uint32_t lid = tile * kProjThreads + threadIdx.x;  // index into the (possibly sharded) input arrays
     const uint32_t gid = o.gidFirst + lid;            // global Gaussian id: what every output is keyed by
     const bool inRange = lid < N;
     uint32_t touched = 0, key = 0xFFFFFFFFu;
@@ -669,7 +675,7 @@ __global__ void __launch_bounds__(256) project_cull_stereo_kernel(const void* __
         } while (false);
         if (touched == 0) writeCulled(o, gid);
     }
-    compactAndCount(inRange, gid, touched, key, tile, numTiles, o);
+    compactAndCount(inRange, gid, touched, key, warpTile, numWarpTiles, o);
 }
 
 // DFS.metal:2184-2203 (+ reset :1372-1385)
@@ -694,10 +700,10 @@ template <bool HALF>
 static cudaError_t launchMono(int deg, dim3 grid, cudaStream_t s, const void* g, const void* h, const MonoCam& cam,
                               const ProjectOut& o) {
     switch (deg) {
-        case 0: project_cull_mono_kernel<HALF, 0><<<grid, 256, 0, s>>>(g, h, cam, o); break;
-        case 1: project_cull_mono_kernel<HALF, 1><<<grid, 256, 0, s>>>(g, h, cam, o); break;
-        case 2: project_cull_mono_kernel<HALF, 2><<<grid, 256, 0, s>>>(g, h, cam, o); break;
-        default: project_cull_mono_kernel<HALF, 3><<<grid, 256, 0, s>>>(g, h, cam, o); break;
+        case 0: project_cull_mono_kernel<HALF, 0><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        case 1: project_cull_mono_kernel<HALF, 1><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        case 2: project_cull_mono_kernel<HALF, 2><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        default: project_cull_mono_kernel<HALF, 3><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
     }
     return cudaGetLastError();
 }
@@ -705,10 +711,10 @@ template <bool HALF>
 static cudaError_t launchStereo(int deg, dim3 grid, cudaStream_t s, const void* g, const void* h, const StereoCam& cam,
                                 const ProjectOut& o) {
     switch (deg) {
-        case 0: project_cull_stereo_kernel<HALF, 0><<<grid, 256, 0, s>>>(g, h, cam, o); break;
-        case 1: project_cull_stereo_kernel<HALF, 1><<<grid, 256, 0, s>>>(g, h, cam, o); break;
-        case 2: project_cull_stereo_kernel<HALF, 2><<<grid, 256, 0, s>>>(g, h, cam, o); break;
-        default: project_cull_stereo_kernel<HALF, 3><<<grid, 256, 0, s>>>(g, h, cam, o); break;
+        case 0: project_cull_stereo_kernel<HALF, 0><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        case 1: project_cull_stereo_kernel<HALF, 1><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        case 2: project_cull_stereo_kernel<HALF, 2><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        default: project_cull_stereo_kernel<HALF, 3><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
     }
     return cudaGetLastError();
 }
@@ -718,13 +724,13 @@ int shDegreeFromComponents(uint32_t n) { return n <= 1 ? 0 : (n <= 4 ? 1 : (n <=
 
 cudaError_t launchProjectMono(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam,
                               const ProjectOut& o) {
-    dim3 grid((cam.gaussianCount + 255u) / 256u);
+    dim3 grid((cam.gaussianCount + kProjThreads - 1) / kProjThreads);
     int deg = shDegreeFromComponents(cam.shComponents);
     return halfInput ? launchMono<true>(deg, grid, s, g, h, cam, o) : launchMono<false>(deg, grid, s, g, h, cam, o);
 }
 cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, const void* h, const StereoCam& cam,
                                 const ProjectOut& o) {
-    dim3 grid((cam.gaussianCount + 255u) / 256u);
+    dim3 grid((cam.gaussianCount + kProjThreads - 1) / kProjThreads);
     int deg = shDegreeFromComponents(cam.shComponents);
     return halfInput ? launchStereo<true>(deg, grid, s, g, h, cam, o) : launchStereo<false>(deg, grid, s, g, h, cam, o);
 }

@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(256) ingest_records_kernel(const SplatRecord* 
     if (threadIdx.x == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t numTiles = (recordCount + 255u) / 256u;
+    const uint32_t numWarpTiles = (recordCount + 31u) / 32u;
+    const uint32_t warpTile = tile * 8u + (threadIdx.x >> 5);
+    if (warpTile >= numWarpTiles) return;
     const uint32_t j = tile * 256u + threadIdx.x;
     const bool inRange = j < recordCount;
     __shared__ WarpTileWork s_work[8];
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) ingest_records_kernel(const SplatRecord* 
         touched = cnt;
         key = keyIn;
     }
-    compactAndCount(inRange, gid, touched, key, tile, numTiles, o);
+    compactAndCount(inRange, gid, touched, key, warpTile, numWarpTiles, o);
 }
 
 cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,

@@ -174,6 +174,14 @@ def probe_hexp(xbits):
     return y
 
 
+def probe_minmax(a, b):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    mn, mx = np.empty_like(a), np.empty_like(a)
+    lib().gsmo_probe_minmax(_p(a), _p(b), _p(mn), _p(mx), C.c_int(a.size))
+    return mn, mx
+
+
 def probe_f2h(x):
     x = np.ascontiguousarray(x, np.float32)
     y = np.empty(x.shape, np.uint16)

@@ -29,6 +29,7 @@ void gsmo_probe_atan2(const float* y, const float* x, float* r, int n) { for (in
 void gsmo_probe_powr(const float* x, float yexp, float* r, int n) { for (int i = 0; i < n; ++i) r[i] = gsmo_powr(x[i], yexp); }
 void gsmo_probe_hexp(const gsmo_half* x, gsmo_half* y, int n) { for (int i = 0; i < n; ++i) y[i] = gsmo_hexp(x[i]); }
 void gsmo_probe_f2h(const float* x, gsmo_half* y, int n) { for (int i = 0; i < n; ++i) y[i] = gsmo_f2h(x[i]); }
+void gsmo_probe_minmax(const float* a, const float* b, float* mn, float* mx, int n) { for (int i = 0; i < n; ++i) { mn[i] = gsmo_fmin(a[i], b[i]); mx[i] = gsmo_fmax(a[i], b[i]); } }
 void gsmo_probe_h2f(const gsmo_half* x, float* y, int n) { for (int i = 0; i < n; ++i) y[i] = gsmo_h2f(x[i]); }
 
 /* ---------------------------------------------------------------- small linear algebra */

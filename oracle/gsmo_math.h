@@ -43,27 +43,33 @@ static inline gsmo_half gsmo_hsub(gsmo_half a, gsmo_half b) { return gsmo_f2h(gs
 static inline gsmo_half gsmo_hmul(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) * gsmo_h2f(b)); }
 static inline gsmo_half gsmo_hdiv(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) / gsmo_h2f(b)); }
 static inline int gsmo_hisnan(gsmo_half a) { return (a & 0x7FFFu) > 0x7C00u; }
-/* min/max with IEEE-754-2008 minNum/maxNum NaN rule (a NaN operand loses); ties return b. */
+/* min/max: a NaN operand loses (IEEE-754-2008 minNum/maxNum, MSL fmin/fmax); -0 orders below +0
+ * (the rule of PTX min/max, so the device uses one FMNMX / HMNMX2 instruction). */
 static inline gsmo_half gsmo_hmin(gsmo_half a, gsmo_half b) {
     if (gsmo_hisnan(a)) return b;
     if (gsmo_hisnan(b)) return a;
-    return (gsmo_h2f(a) < gsmo_h2f(b)) ? a : b;
+    float fa = gsmo_h2f(a), fb = gsmo_h2f(b);
+    if (fa == fb) return (a & 0x8000u) ? a : b;
+    return (fa < fb) ? a : b;
 }
 static inline gsmo_half gsmo_hmax(gsmo_half a, gsmo_half b) {
     if (gsmo_hisnan(a)) return b;
     if (gsmo_hisnan(b)) return a;
-    return (gsmo_h2f(a) > gsmo_h2f(b)) ? a : b;
+    float fa = gsmo_h2f(a), fb = gsmo_h2f(b);
+    if (fa == fb) return (a & 0x8000u) ? b : a;
+    return (fa > fb) ? a : b;
 }
 
-/* float min/max/clamp: NaN operand loses (MSL fmin/fmax rule); ties return b. */
 static inline float gsmo_fmax(float a, float b) {
     if (a != a) return b;
     if (b != b) return a;
+    if (a == b) return (gsmo_f2u(a) & 0x80000000u) ? b : a;
     return (a > b) ? a : b;
 }
 static inline float gsmo_fmin(float a, float b) {
     if (a != a) return b;
     if (b != b) return a;
+    if (a == b) return (gsmo_f2u(a) & 0x80000000u) ? a : b;
     return (a < b) ? a : b;
 }
 static inline float gsmo_clamp(float x, float lo, float hi) { return gsmo_fmin(gsmo_fmax(x, lo), hi); }

@@ -36,6 +36,16 @@ def test_math_probes_bit_exact(oracle):
     assert np.array_equal(probe_math(3, ay, ax).view(np.uint32), oracle.probe_atan2(ay, ax).view(np.uint32))
     xp = rng.uniform(0.03, 1.0, 300_000).astype(np.float32)
     assert np.array_equal(probe_math(4, xp).view(np.uint32), oracle.probe_powr(xp, 2.4).view(np.uint32))
+    # min/max: NaN operand loses, -0 < +0 (one FMNMX on the device)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.nan, np.inf, -np.inf, 1e-45, -1e-45, 3.5], np.float32)
+    ma, mb = [x.ravel() for x in np.meshgrid(sp, sp)]
+    ma = np.concatenate([ma, rng.normal(0, 1, 10000).astype(np.float32)])
+    mb = np.concatenate([mb, rng.normal(0, 1, 10000).astype(np.float32)])
+    omn, omx = oracle.probe_minmax(ma, mb)
+    gmn, gmx = probe_math(9, ma, mb), probe_math(10, ma, mb)
+    nn = ~(np.isnan(ma) & np.isnan(mb))  # both NaN: payload unspecified
+    assert np.array_equal(gmn.view(np.uint32)[nn], omn.view(np.uint32)[nn])
+    assert np.array_equal(gmx.view(np.uint32)[nn], omx.view(np.uint32)[nn])
     bits = np.arange(65536, dtype=np.uint16)
     ref = oracle.probe_hexp(bits)
     assert np.array_equal(probe_math(5, bits), ref)          # scalar half exp, all 65536 inputs
