@@ -354,9 +354,10 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians;
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
+    GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
     GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
     recordStage(r, s, 1);
     st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);
@@ -411,9 +412,10 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians;
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
+    GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
     GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
     recordStage(r, s, 1);
     st = encodeSortExpandRange(r, res, s, true, tilesX, tilesY);
@@ -487,9 +489,10 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians;
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "strip project+cull");
+    GSM_CUDA(launchCompactVisible(s, gidCount, po, r->numSMs), "visibility compaction");
     GSM_CUDA(launchPackRecords(s, res.fs, res.depthKeys[0], res.primIdx[0], res.renderData, res.bounds, res.nTouched, recordsOut,
                                gidCount, r->numSMs), "pack records");
     GSM_CUDA(cudaMemcpyAsync(hostCount, &res.fs->visibleCountRaw, 4, cudaMemcpyDeviceToHost, s), "count readback");
@@ -515,7 +518,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.depthKey16 = 0; po.gidFirst = 0;
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1]; po.depthKey16 = 0; po.gidFirst = 0;
     GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po), "ingest records");
     GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
     st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);

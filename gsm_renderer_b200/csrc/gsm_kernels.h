@@ -11,6 +11,7 @@ struct ProjectOut {
     int32_t* bounds;              // int4 per Gaussian
     uint32_t* nTouched;
     BlendSplat* blendSplats;      // mono only (may be null)
+    uint32_t* preDepthKeys;       // per gid, before compaction (the reference aliases the sort scratch for it, DFR.swift:282)
     uint32_t* depthKeys;          // compacted, ascending gid
     int32_t* primitiveIndices;
     uint32_t maxOut;
@@ -22,6 +23,7 @@ int shDegreeFromComponents(uint32_t n);
 const void* finalize_header_probe();  // a kernel symbol, to test that the sm_100a image loads
 cudaError_t launchProjectMono(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam, const ProjectOut& o);
 cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, const void* h, const StereoCam& cam, const ProjectOut& o);
+cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o, int numSMs);
 cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians, uint32_t maxInstances);
 
 // Onesweep radix sort (sort.cu). keys/vals ping-pong between (k0,v0) and (k1,v1); after numPasses the

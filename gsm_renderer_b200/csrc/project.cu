@@ -407,10 +407,7 @@ template <bool HALF, int DEG>
 __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const void* __restrict__ gaussians,
                                                                 const void* __restrict__ harmonics,
                                                                 const __grid_constant__ MonoCam cam, ProjectOut o) {
-    __shared__ uint32_t s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const uint32_t N = cam.gaussianCount;
     const uint32_t numWarpTiles = (N + 31u) / 32u;
     const uint32_t warpTile = tile * (kProjThreads / 32) + (threadIdx.x >> 5);
@@ -515,7 +512,7 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const v
             writeCulled(o, gid);
         }
     }
-    compactAndCount(inRange, gid, touched, key, warpTile, numWarpTiles, o);
+    if (inRange) o.preDepthKeys[gid] = key;  // compacted by compact_visible_kernel (no inter-warp wait in this kernel)
 }
 
 // ---------------------------------------------------------------- stereo
@@ -582,10 +579,7 @@ template <bool HALF, int DEG>
 __global__ void __launch_bounds__(kProjThreads) project_cull_stereo_kernel(const void* __restrict__ gaussians,
                                                                   const void* __restrict__ harmonics,
                                                                   const __grid_constant__ StereoCam cam, ProjectOut o) {
-    __shared__ uint32_t s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const uint32_t N = cam.gaussianCount;
     const uint32_t numWarpTiles = (N + 31u) / 32u;
     const uint32_t warpTile = tile * (kProjThreads / 32) + (threadIdx.x >> 5);
@@ -675,7 +669,84 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_stereo_kernel(const
         } while (false);
         if (touched == 0) writeCulled(o, gid);
     }
-    compactAndCount(inRange, gid, touched, key, warpTile, numWarpTiles, o);
+    if (inRange) o.preDepthKeys[gid] = key;  // compacted by compact_visible_kernel (no inter-warp wait in this kernel)
+}
+
+// ---------------------------------------------------------------- stage 1.25: visibility compaction
+// Replaces the 8-pass VisibilityCompactionEncoder (DFS.metal:518-621): one pass, 2048 gids per CTA, decoupled
+// look-back carrying (visible count, sum of nTouched), so it also yields totalInstances (the atomic of
+// DFS.metal:218). It is a separate kernel on purpose: fused into the projection kernel, every warp had to wait
+// for all earlier warps' tile walks before it could retire (ncu r1_v3: 36 % of that kernel's instructions were
+// look-back spins). Here the work per element is uniform, so the chain never stalls.
+constexpr int kCompactItems = 8;
+__global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, ProjectOut o) {
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_touched[8];
+    __shared__ uint32_t s_tile, s_baseVisible;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t numTiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= numTiles) break;
+        const uint32_t first = tile * 256u * kCompactItems + tid * kCompactItems;  // blocked: 8 consecutive gids per thread
+        uint32_t nt[kCompactItems];
+        uint32_t cnt = 0, tsum = 0;
+#pragma unroll
+        for (int i = 0; i < kCompactItems; ++i) {
+            const uint32_t l = first + i;
+            nt[i] = (l < N) ? o.nTouched[o.gidFirst + l] : 0u;
+            cnt += nt[i] > 0u ? 1u : 0u;
+            tsum += nt[i];
+        }
+        uint32_t blockVisible;
+        const uint32_t excl = block_exclusive_scan_256(cnt, s_scan, blockVisible);
+        for (int off = 16; off > 0; off >>= 1) tsum += __shfl_xor_sync(0xFFFFFFFFu, tsum, off);
+        if (lane == 0) s_touched[warp] = tsum;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t bt = (lane < 8) ? s_touched[lane] : 0u;
+            for (int off = 4; off > 0; off >>= 1) bt += __shfl_xor_sync(0xFFFFFFFFu, bt, off);
+            bt = __shfl_sync(0xFFFFFFFFu, bt, 0);
+            uint32_t ev, et;
+            lookback_exclusive2(o.status, tile, blockVisible, bt, ev, et);
+            if (lane == 0) {
+                s_baseVisible = ev;
+                if (tile == numTiles - 1) {
+                    o.fs->visibleCountRaw = ev + blockVisible;  // DFS.metal:618-620
+                    o.fs->totalInstancesRaw = et + bt;          // DFS.metal:218
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t dst = s_baseVisible + excl;
+#pragma unroll
+        for (int i = 0; i < kCompactItems; ++i) {
+            if (nt[i] > 0u) {
+                if (dst < o.maxOut) {  // DFS.metal:605
+                    const uint32_t gid = o.gidFirst + first + i;
+                    uint32_t key = o.preDepthKeys[gid];
+                    if (o.depthKey16) {  // DFS.metal:607-612; key is float_to_sortable_uint of a depth > 0
+                        uint32_t bits = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
+                        key = (uint32_t)(__half_as_ushort(__float2half_rn(__uint_as_float(bits))) ^ 0x8000u);
+                    }
+                    o.depthKeys[dst] = key;
+                    o.primitiveIndices[dst] = (int32_t)gid;
+                }
+                dst++;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o, int numSMs) {
+    if (N == 0) return cudaSuccess;
+    uint32_t tiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
+    uint32_t grid = tiles < (uint32_t)numSMs * 8u ? tiles : (uint32_t)numSMs * 8u;
+    compact_visible_kernel<<<grid, 256, 0, s>>>(N, o);
+    return cudaGetLastError();
 }
 
 // DFS.metal:2184-2203 (+ reset :1372-1385)
