@@ -64,6 +64,8 @@ struct Resources {
     // zeroed by the sort's histogram kernel
     uint32_t* depthSortStatus = nullptr;
     uint32_t* tileSortStatus = nullptr;
+    uint32_t* depthSortGStatus = nullptr;
+    uint32_t* tileSortGStatus = nullptr;
 };
 
 }  // namespace
@@ -138,6 +140,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t zeroEnd = off;
     const size_t oDepthStatus = take((size_t)4 * res.depthTilesCap * 256 * 4);
     const size_t oTileStatus = take((size_t)4 * res.tileTilesCap * 256 * 4);
+    const size_t oDepthGStatus = take((size_t)4 * ((res.depthTilesCap + 15) / 16) * 256 * 4);
+    const size_t oTileGStatus = take((size_t)4 * ((res.tileTilesCap + 15) / 16) * 256 * 4);
     res.bytes = off;
 
     cudaError_t e = cudaMalloc((void**)&res.arena, res.bytes);
@@ -167,6 +171,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     res.zeroBytes = zeroEnd - oZero;
     res.depthSortStatus = (uint32_t*)(a + oDepthStatus);
     res.tileSortStatus = (uint32_t*)(a + oTileStatus);
+    res.depthSortGStatus = (uint32_t*)(a + oDepthGStatus);
+    res.tileSortGStatus = (uint32_t*)(a + oTileGStatus);
     e = cudaMemset(res.arena, 0, res.bytes);
     if (e != cudaSuccess) return fail(GSM_ERR_RENDER_FAILED, "arena memset", e);
     return GSM_OK;
@@ -201,7 +207,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     dp.k0 = res.depthKeys[0]; dp.k1 = res.depthKeys[1];
     dp.v0 = (uint32_t*)res.primIdx[0]; dp.v1 = (uint32_t*)res.primIdx[1];
     dp.countPtr = &res.header->visibleCount; dp.countCap = res.maxGaussians;
-    dp.hist = &res.fs->hist[0][0]; dp.status = res.depthSortStatus; dp.tickets = &res.fs->ticketSort[0];
+    dp.hist = &res.fs->hist[0][0]; dp.status = res.depthSortStatus; dp.gstatus = res.depthSortGStatus; dp.tickets = &res.fs->ticketSort[0];
     dp.tilesCap = res.depthTilesCap; dp.keyBits = 32; dp.numPasses = key16 ? 2 : 4; dp.numSMs = r->numSMs;
     GSM_CUDA(launchSort(s, dp), "depth sort");
     recordStage(r, s, 2);
@@ -218,7 +224,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     tp.k0 = res.tileIds[0]; tp.k1 = res.tileIds[1];
     tp.v0 = (uint32_t*)res.instIdx[0]; tp.v1 = (uint32_t*)res.instIdx[1];
     tp.countPtr = &res.header->totalInstances; tp.countCap = res.maxInstances;
-    tp.hist = &res.fs->hist[4][0]; tp.status = res.tileSortStatus; tp.tickets = &res.fs->ticketSort[4];
+    tp.hist = &res.fs->hist[4][0]; tp.status = res.tileSortStatus; tp.gstatus = res.tileSortGStatus; tp.tickets = &res.fs->ticketSort[4];
     tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tileSortPasses(tilesX * tilesY);
     tp.numSMs = r->numSMs;
     GSM_CUDA(launchSort(s, tp), "tile sort");
@@ -667,7 +673,8 @@ gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* paylo
     const size_t keyBytes = (size_t)count * (keyBits / 8);
     // scratch: [count u32][hist 4*256][tickets 4][status passes*tiles*256][k1][v1]
     const size_t oHist = 256, oTickets = oHist + 4 * 256 * 4, oStatus = alignUp(oTickets + 16, 256);
-    const size_t oK1 = alignUp(oStatus + (size_t)numPasses * tiles * 256 * 4, 256), oV1 = alignUp(oK1 + keyBytes, 256);
+    const size_t oGStatus = alignUp(oStatus + (size_t)numPasses * tiles * 256 * 4, 256);
+    const size_t oK1 = alignUp(oGStatus + (size_t)numPasses * ((tiles + 15) / 16) * 256 * 4, 256), oV1 = alignUp(oK1 + keyBytes, 256);
     const size_t total = oV1 + (size_t)count * 4;
     char* scratch = nullptr;
     cudaError_t e = cudaMalloc((void**)&scratch, total);
@@ -679,7 +686,7 @@ gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* paylo
         SortPlan p;
         p.k0 = keys; p.k1 = scratch + oK1; p.v0 = (uint32_t*)payload; p.v1 = (uint32_t*)(scratch + oV1);
         p.countPtr = (const uint32_t*)scratch; p.countCap = count;
-        p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.tickets = (uint32_t*)(scratch + oTickets);
+        p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.gstatus = (uint32_t*)(scratch + oGStatus); p.tickets = (uint32_t*)(scratch + oTickets);
         p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = r->numSMs;
         if ((e = launchSort(s, p)) != cudaSuccess) break;
         e = cudaStreamSynchronize(s);

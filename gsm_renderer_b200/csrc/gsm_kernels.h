@@ -32,7 +32,8 @@ struct SortPlan {
     void* k0; void* k1; uint32_t* v0; uint32_t* v1;
     const uint32_t* countPtr; uint32_t countCap;
     uint32_t* hist;      // [numPasses][256] zeroed
-    uint32_t* status;    // [numPasses][tilesCap][256] zeroed
+    uint32_t* status;    // [numPasses][tilesCap][256] tile look-back words (zeroed by the histogram kernel)
+    uint32_t* gstatus;   // [numPasses][ceil(tilesCap/16)][256] group look-back words
     uint32_t* tickets;   // [numPasses] zeroed
     uint32_t tilesCap;
     int keyBits;         // 16 or 32

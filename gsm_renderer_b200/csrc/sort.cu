@@ -21,6 +21,7 @@ constexpr uint32_t kStatusValueMask = 0x3FFFFFFFu;
 constexpr uint32_t kStatusAggregate = 0x40000000u;
 constexpr uint32_t kStatusInclusive = 0x80000000u;
 constexpr int kLookBatch = 8;
+constexpr uint32_t kLookGroup = 16;
 
 template <typename KeyT> struct SortCfg;
 template <> struct SortCfg<uint32_t> { static constexpr int ITEMS = 8; };   // 2048 keys / tile
@@ -34,7 +35,8 @@ uint32_t sortTileSize(int keyBits) {
 template <typename KeyT, int NPASS>
 __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ countPtr,
                                                               uint32_t countCap, uint32_t* __restrict__ hist,
-                                                              uint32_t* __restrict__ status, uint32_t tilesCap) {
+                                                              uint32_t* __restrict__ status, uint32_t* __restrict__ gstatus,
+                                                              uint32_t tilesCap) {
     __shared__ uint32_t s_hist[NPASS][256];
     for (int i = threadIdx.x; i < NPASS * 256; i += 256) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -42,9 +44,14 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
     {   // reset the look-back words this frame's passes will use (sized by the device-side count, not the capacity)
         constexpr uint32_t TILE = kSortThreads * SortCfg<KeyT>::ITEMS;
         const uint32_t words = ((count + TILE - 1) / TILE) * 256u;
-        for (int p = 0; p < NPASS; ++p)
+        const uint32_t gwords = ((words / 256u + kLookGroup - 1) / kLookGroup) * 256u;
+        const uint32_t groupsCap = (tilesCap + kLookGroup - 1) / kLookGroup;
+        for (int p = 0; p < NPASS; ++p) {
             for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < words; i += gridDim.x * 256u)
                 status[(size_t)p * tilesCap * 256u + i] = 0u;
+            for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < gwords; i += gridDim.x * 256u)
+                gstatus[(size_t)p * groupsCap * 256u + i] = 0u;
+        }
     }
     for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < count; i += gridDim.x * 256u) {
         uint32_t k = (uint32_t)keys[i];
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
                                                                      KeyT* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
                                                                      const uint32_t* __restrict__ countPtr, uint32_t countCap,
                                                                      const uint32_t* __restrict__ digitHist, uint32_t* status,
-                                                                     uint32_t* ticket, int shift) {
+                                                                     uint32_t* gstatus, uint32_t* ticket, int shift) {
     constexpr int ITEMS = SortCfg<KeyT>::ITEMS;
     constexpr int TILE = kSortThreads * ITEMS;
     constexpr KeyT SENTINEL = (KeyT)~(KeyT)0;
@@ -137,33 +144,67 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
         // decoupled look-back, one thread per digit
         uint32_t* myStatus = status + (size_t)tile * 256u + tid;
         uint32_t exclusive = 0;
+        // Two-level decoupled look-back, one thread per digit. Level 1 walks the tiles of the own group of
+        // kLookGroup tiles; level 2 walks per-GROUP words published by each group's last tile. With every tile
+        // resident at once nothing is inclusive yet, so a flat walk costs one step per predecessor batch
+        // (ncu r1_v3: tile 346 needed 43 dependent L2 round trips, ~17 of the pass's 21 us); two levels bound it
+        // by kLookGroup/kLookBatch + groups/kLookBatch steps and make the status traffic linear, not quadratic.
+        const uint32_t group = tile / kLookGroup;
+        const bool groupLeader = (tile % kLookGroup) == kLookGroup - 1;
+        uint32_t* myGroup = gstatus + (size_t)group * 256u + tid;
         if (tile == 0) {
             st_status32(myStatus, kStatusInclusive | validCount);
+            if (groupLeader) st_status32(myGroup, kStatusInclusive | validCount);
         } else {
             st_status32(myStatus, kStatusAggregate | validCount);
-            // batched look-back: kLookBatch independent loads in flight per step instead of one L2 round trip per
-            // predecessor (ncu r1_v1: the serial walk made the pass latency-bound at ~19% issue utilisation)
-            int look = (int)tile - 1;
             bool done = false;
-            while (!done) {
-                uint32_t sv[kLookBatch];
+            {   // level 1: predecessors inside the group
+                const int groupStart = (int)(group * kLookGroup);
+                int look = (int)tile - 1;
+                while (!done && look >= groupStart) {
+                    uint32_t sv[kLookBatch];
 #pragma unroll
-                for (int k = 0; k < kLookBatch; ++k) {
-                    const int t = look - k;
-                    sv[k] = (t >= 0) ? ld_status32(status + (size_t)t * 256u + tid) : kStatusInclusive;
-                }
-                int consumed = 0;
-#pragma unroll
-                for (int k = 0; k < kLookBatch; ++k) {
-                    if (!done && consumed == k) {  // only a contiguous run of published words may be consumed
-                        const uint32_t sw = sv[k];
-                        if (sw & kStatusInclusive) { exclusive += sw & kStatusValueMask; done = true; }
-                        else if (sw & kStatusAggregate) { exclusive += sw & kStatusValueMask; consumed++; }
+                    for (int k = 0; k < kLookBatch; ++k) {
+                        const int t = look - k;
+                        sv[k] = (t >= groupStart) ? ld_status32(status + (size_t)t * 256u + tid) : 0u;
                     }
+                    int consumed = 0;
+#pragma unroll
+                    for (int k = 0; k < kLookBatch; ++k) {
+                        if (!done && consumed == k && look - k >= groupStart) {  // only a contiguous run of published words
+                            const uint32_t sw = sv[k];
+                            if (sw & kStatusInclusive) { exclusive += sw & kStatusValueMask; done = true; }
+                            else if (sw & kStatusAggregate) { exclusive += sw & kStatusValueMask; consumed++; }
+                        }
+                    }
+                    look -= consumed;
                 }
-                look -= consumed;
+            }
+            if (!done && group > 0) {
+                // the group's last tile now knows the group aggregate: publish it before walking on
+                if (groupLeader) st_status32(myGroup, kStatusAggregate | (exclusive + validCount));
+                int look = (int)group - 1;  // level 2: earlier groups
+                while (!done && look >= 0) {
+                    uint32_t sv[kLookBatch];
+#pragma unroll
+                    for (int k = 0; k < kLookBatch; ++k) {
+                        const int g = look - k;
+                        sv[k] = (g >= 0) ? ld_status32(gstatus + (size_t)g * 256u + tid) : 0u;
+                    }
+                    int consumed = 0;
+#pragma unroll
+                    for (int k = 0; k < kLookBatch; ++k) {
+                        if (!done && consumed == k && look - k >= 0) {
+                            const uint32_t sw = sv[k];
+                            if (sw & kStatusInclusive) { exclusive += sw & kStatusValueMask; done = true; }
+                            else if (sw & kStatusAggregate) { exclusive += sw & kStatusValueMask; consumed++; }
+                        }
+                    }
+                    look -= consumed;
+                }
             }
             st_status32(myStatus, kStatusInclusive | (exclusive + validCount));
+            if (groupLeader) st_status32(myGroup, kStatusInclusive | (exclusive + validCount));
         }
         uint32_t total;
         uint32_t binExcl = block_exclusive_scan_256(binCount, s_scan, total);
@@ -210,10 +251,10 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
     KeyT* k0 = (KeyT*)p.k0;
     KeyT* k1 = (KeyT*)p.k1;
     switch (p.numPasses) {
-        case 1: radix_histogram_kernel<KeyT, 1><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
-        case 2: radix_histogram_kernel<KeyT, 2><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
-        case 3: radix_histogram_kernel<KeyT, 3><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
-        default: radix_histogram_kernel<KeyT, 4><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.tilesCap); break;
+        case 1: radix_histogram_kernel<KeyT, 1><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 2: radix_histogram_kernel<KeyT, 2><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 3: radix_histogram_kernel<KeyT, 3><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        default: radix_histogram_kernel<KeyT, 4><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
     }
     int blocksPerSM = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, onesweep_pass_kernel<KeyT>, kSortThreads, 0);
@@ -223,7 +264,8 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
         const bool even = (pass & 1) == 0;
         onesweep_pass_kernel<KeyT><<<grid, kSortThreads, 0, s>>>(
             even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
-            p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u, p.tickets + pass, 8 * pass);
+            p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u,
+            p.gstatus + (size_t)pass * ((p.tilesCap + kLookGroup - 1) / kLookGroup) * 256u, p.tickets + pass, 8 * pass);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
