@@ -198,7 +198,8 @@ void recordStage(gsm_renderer* r, cudaStream_t s, int idx) {
 }
 
 // stages 2-7 shared by the mono and stereo frames (DFR.swift:325-430, :683-787)
-gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s, bool stereo, uint32_t tilesX, uint32_t tilesY) {
+gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s, bool stereo, uint32_t tilesX, uint32_t tilesY,
+                                 bool depthHistReady = true) {
     const gsm_config& c = r->cfg;
     const bool tile16 = c.tileIdPrecision == GSM_KEY_BITS16;
     const bool key16 = c.depthSortKeyPrecision == GSM_KEY_BITS16;
@@ -209,15 +210,22 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     dp.countPtr = &res.header->visibleCount; dp.countCap = res.maxGaussians;
     dp.hist = &res.fs->hist[0][0]; dp.status = res.depthSortStatus; dp.gstatus = res.depthSortGStatus; dp.tickets = &res.fs->ticketSort[0];
     dp.tilesCap = res.depthTilesCap; dp.keyBits = 32; dp.numPasses = key16 ? 2 : 4; dp.numSMs = r->numSMs;
+    dp.histogramReady = depthHistReady;  // compact_visible_kernel filled hist[0..3] and reset the look-back words
     GSM_CUDA(launchSort(s, dp), "depth sort");
     recordStage(r, s, 2);
     // stages 3+4
+    const int tilePasses = tileSortPasses(tilesX * tilesY);
+    SortReset reset;
+    reset.status = res.tileSortStatus; reset.statusStride = res.tileTilesCap * 256u;
+    reset.gstatus = res.tileSortGStatus; reset.gstatusStride = ((res.tileTilesCap + 15u) / 16u) * 256u;
+    reset.passes = (uint32_t)tilePasses; reset.tileSize = sortTileSize(tile16 ? 16 : 32);
     GSM_CUDA(launchApplyOrderScan(s, res.primIdx[0], res.nTouched, res.offsets, res.header, res.scanStatus, &res.fs->ticketScan,
-                                  r->numSMs), "apply order + scan");
+                                  r->numSMs, reset), "apply order + scan");
     recordStage(r, s, 3);
     // stage 5
     GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.offsets, res.bounds, res.renderData, res.tileIds[0],
-                                   res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians), "create instances");
+                                   res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians, &res.fs->hist[4][0],
+                                   (uint32_t)tilePasses, r->numSMs), "create instances");
     recordStage(r, s, 4);
     // stage 6
     SortPlan tp;
@@ -225,8 +233,8 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     tp.v0 = (uint32_t*)res.instIdx[0]; tp.v1 = (uint32_t*)res.instIdx[1];
     tp.countPtr = &res.header->totalInstances; tp.countCap = res.maxInstances;
     tp.hist = &res.fs->hist[4][0]; tp.status = res.tileSortStatus; tp.gstatus = res.tileSortGStatus; tp.tickets = &res.fs->ticketSort[4];
-    tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tileSortPasses(tilesX * tilesY);
-    tp.numSMs = r->numSMs;
+    tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tilePasses;
+    tp.numSMs = r->numSMs; tp.histogramReady = true;  // create_instances_kernel filled hist[4..7], the scan kernel reset the words
     GSM_CUDA(launchSort(s, tp), "tile sort");
     recordStage(r, s, 5);
     // stage 7
@@ -361,6 +369,9 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
@@ -419,6 +430,9 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
@@ -496,6 +510,9 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "strip project+cull");
     GSM_CUDA(launchCompactVisible(s, gidCount, po, r->numSMs), "visibility compaction");
@@ -524,10 +541,13 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1]; po.depthKey16 = 0; po.gidFirst = 0;
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u; po.depthKey16 = 0; po.gidFirst = 0;
     GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po), "ingest records");
     GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
-    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);
+    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, /*depthHistReady=*/false);  // records were compacted by the ingest kernel
     if (st != GSM_OK) return st;
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
                              tileRowCount, (__half*)color, (__half*)depth), "strip blend");
@@ -687,7 +707,7 @@ gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* paylo
         p.k0 = keys; p.k1 = scratch + oK1; p.v0 = (uint32_t*)payload; p.v1 = (uint32_t*)(scratch + oV1);
         p.countPtr = (const uint32_t*)scratch; p.countCap = count;
         p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.gstatus = (uint32_t*)(scratch + oGStatus); p.tickets = (uint32_t*)(scratch + oTickets);
-        p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = r->numSMs;
+        p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = r->numSMs; p.histogramReady = false;
         if ((e = launchSort(s, p)) != cudaSuccess) break;
         e = cudaStreamSynchronize(s);
     } while (false);

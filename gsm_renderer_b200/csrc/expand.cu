@@ -15,8 +15,12 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
                                                                const void* __restrict__ renderData,
                                                                TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx,
                                                                const GSMDepthFirstHeader* __restrict__ header, uint32_t tilesX,
-                                                               uint32_t maxAssignments) {
+                                                               uint32_t maxAssignments, uint32_t* __restrict__ tileHist,
+                                                               uint32_t tilePasses) {
     __shared__ WarpTileWork s_work[8];
+    __shared__ uint32_t s_hist[4][256];  // digit histograms of the emitted tile ids (the tile sort's histogram pass, fused)
+    for (int i = threadIdx.x; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
+    __syncthreads();
     __shared__ uint32_t s_base[8][32];
     __shared__ int32_t s_idx[8][32];
     const uint32_t visibleCount = header->visibleCount;
@@ -54,16 +58,23 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
             q.d2Cutoff = __uint_as_float(0x7F800000u);  // d2min <= +inf always (d2min is never NaN for a = b = c = 0)
         }
         warpEmitTiles<TileT>(s_work[warp], n, q, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
-                             tileIds, instanceIdx, s_base[warp], s_idx[warp]);
+                             tileIds, instanceIdx, s_base[warp], s_idx[warp], &s_hist[0][0], tilePasses);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tilePasses * 256u; i += 256u) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&tileHist[i], v);
     }
 }
 
 cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* offsets,
                                   const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
-                                  const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible) {
+                                  const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
+                                  uint32_t* tileHist, uint32_t tilePasses, int numSMs) {
     uint32_t grid = (capVisible + 255u) / 256u;
+    if (grid > (uint32_t)numSMs * 6u) grid = (uint32_t)numSMs * 6u;  // persistent: few CTAs flush the fused histograms
     if (grid == 0) grid = 1;
-#define GSM_LAUNCH(T, ST) create_instances_kernel<T, ST><<<grid, 256, 0, s>>>(sortedIdx, offsets, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments)
+#define GSM_LAUNCH(T, ST) create_instances_kernel<T, ST><<<grid, 256, 0, s>>>(sortedIdx, offsets, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
     if (tileId16) { if (stereo) GSM_LAUNCH(uint16_t, true); else GSM_LAUNCH(uint16_t, false); }
     else { if (stereo) GSM_LAUNCH(uint32_t, true); else GSM_LAUNCH(uint32_t, false); }
 #undef GSM_LAUNCH

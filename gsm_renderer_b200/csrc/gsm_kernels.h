@@ -17,6 +17,12 @@ struct ProjectOut {
     uint32_t maxOut;
     uint32_t depthKey16;
     uint32_t gidFirst;
+    // fused into the compaction kernel: digit histograms of the compacted depth keys and the reset of the depth
+    // sort's look-back words (bounded by N, known on the host)
+    uint32_t* depthHist;          // [4][256], zeroed with the frame state
+    uint32_t depthPasses;
+    uint32_t* depthStatus; uint32_t depthStatusStride;   // words per pass (tilesCap*256)
+    uint32_t* depthGStatus; uint32_t depthGStatusStride;
 };
 
 int shDegreeFromComponents(uint32_t n);
@@ -39,18 +45,24 @@ struct SortPlan {
     int keyBits;         // 16 or 32
     int numPasses;
     int numSMs;
+    bool histogramReady; // hist filled and status/gstatus zeroed by earlier kernels of the frame (fused); else a histogram kernel runs
 };
 uint32_t sortTileSize(int keyBits);
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p);
 
 // apply depth order + exclusive scan (scan.cu)
+struct SortReset {  // look-back words of the tile sort, reset by the scan kernel (it knows totalInstances exactly)
+    uint32_t* status; uint32_t statusStride; uint32_t* gstatus; uint32_t gstatusStride; uint32_t passes; uint32_t tileSize;
+};
 cudaError_t launchApplyOrderScan(cudaStream_t s, const int32_t* sortedIdx, const uint32_t* nTouched, uint32_t* offsetsOut,
-                                 const GSMDepthFirstHeader* header, unsigned long long* status, uint32_t* ticket, int numSMs);
+                                 const GSMDepthFirstHeader* header, unsigned long long* status, uint32_t* ticket, int numSMs,
+                                 const SortReset& reset);
 
 // instance expansion (expand.cu)
 cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* offsets,
                                   const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
-                                  const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible);
+                                  const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
+                                  uint32_t* tileHist, uint32_t tilePasses, int numSMs);
 
 // tile ranges (ranges.cu)
 cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,

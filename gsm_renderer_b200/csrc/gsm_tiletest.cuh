@@ -172,7 +172,7 @@ template <typename TileT>
 __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const QuantSplat& q, int minTX, int minTY, int w,
                                               uint32_t writeBase, int32_t originalIdx, uint32_t tilesX, uint32_t maxAssignments,
                                               TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx, uint32_t* sBase,
-                                              int32_t* sIdx) {
+                                              int32_t* sIdx, uint32_t* sHist, uint32_t histPasses) {
     const unsigned lane = threadIdx.x & 31u;
     uint32_t total;
     const uint32_t excl = warpExclusiveScan(n, total);
@@ -207,6 +207,7 @@ __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const
             if (pos < maxAssignments) {  // DFS.metal:707
                 tileIds[pos] = (TileT)tileId;
                 instanceIdx[pos] = sIdx[o];
+                for (uint32_t p = 0; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], 1u);
             }
         }
     }

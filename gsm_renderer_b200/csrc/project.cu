@@ -683,8 +683,18 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_touched[8];
     __shared__ uint32_t s_tile, s_baseVisible;
+    __shared__ uint32_t s_hist[4][256];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t numTiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
+    for (int i = tid; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
+    {   // reset the depth sort's look-back words for this frame: ceil(N / sortTile) tiles per pass bound V <= N
+        const uint32_t words = ((N + 2047u) / 2048u) * 256u, gwords = ((words / 256u + 15u) / 16u) * 256u;
+        for (uint32_t p = 0; p < o.depthPasses; ++p) {
+            for (uint32_t i = blockIdx.x * 256u + tid; i < words; i += gridDim.x * 256u) o.depthStatus[(size_t)p * o.depthStatusStride + i] = 0u;
+            for (uint32_t i = blockIdx.x * 256u + tid; i < gwords; i += gridDim.x * 256u) o.depthGStatus[(size_t)p * o.depthGStatusStride + i] = 0u;
+        }
+    }
+    __syncthreads();
     while (true) {
         if (tid == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);
         __syncthreads();
@@ -733,11 +743,16 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
                     }
                     o.depthKeys[dst] = key;
                     o.primitiveIndices[dst] = (int32_t)gid;
+                    for (uint32_t p = 0; p < o.depthPasses; ++p) atomicAdd(&s_hist[p][(key >> (8u * p)) & 0xFFu], 1u);  // the sort's digit histograms
                 }
                 dst++;
             }
         }
         __syncthreads();
+    }
+    for (uint32_t i = tid; i < o.depthPasses * 256u; i += 256u) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&o.depthHist[i], v);
     }
 }
 

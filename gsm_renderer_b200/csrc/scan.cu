@@ -14,11 +14,19 @@ __global__ void __launch_bounds__(256) apply_order_scan_kernel(const int32_t* __
                                                                const uint32_t* __restrict__ nTouched,
                                                                uint32_t* __restrict__ offsetsOut,
                                                                const GSMDepthFirstHeader* __restrict__ header,
-                                                               unsigned long long* status, uint32_t* ticket) {
+                                                               unsigned long long* status, uint32_t* ticket, SortReset reset) {
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_tile, s_base;
     const unsigned tid = threadIdx.x;
     const uint32_t count = header->visibleCount;
+    {   // reset the tile sort's look-back words for exactly the tiles this frame's totalInstances needs
+        const uint32_t words = ((header->totalInstances + reset.tileSize - 1u) / reset.tileSize) * 256u;
+        const uint32_t gwords = ((words / 256u + 15u) / 16u) * 256u;
+        for (uint32_t p = 0; p < reset.passes; ++p) {
+            for (uint32_t i = blockIdx.x * 256u + tid; i < words; i += gridDim.x * 256u) reset.status[(size_t)p * reset.statusStride + i] = 0u;
+            for (uint32_t i = blockIdx.x * 256u + tid; i < gwords; i += gridDim.x * 256u) reset.gstatus[(size_t)p * reset.gstatusStride + i] = 0u;
+        }
+    }
     const uint32_t numTiles = (count + kScanTile - 1) / kScanTile;
     while (true) {
         if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -67,8 +75,9 @@ __global__ void __launch_bounds__(256) apply_order_scan_kernel(const int32_t* __
 }
 
 cudaError_t launchApplyOrderScan(cudaStream_t s, const int32_t* sortedIdx, const uint32_t* nTouched, uint32_t* offsetsOut,
-                                 const GSMDepthFirstHeader* header, unsigned long long* status, uint32_t* ticket, int numSMs) {
-    apply_order_scan_kernel<<<numSMs * 4, 256, 0, s>>>(sortedIdx, nTouched, offsetsOut, header, status, ticket);
+                                 const GSMDepthFirstHeader* header, unsigned long long* status, uint32_t* ticket, int numSMs,
+                                 const SortReset& reset) {
+    apply_order_scan_kernel<<<numSMs * 4, 256, 0, s>>>(sortedIdx, nTouched, offsetsOut, header, status, ticket, reset);
     return cudaGetLastError();
 }
 

@@ -114,16 +114,31 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
             uint32_t j = warpBase + i * 32u;
             key[i] = (j < tileValid) ? keysIn[base + j] : SENTINEL;
         }
-        // rank inside the warp, in index order
+        // payload loads are issued now so their latency hides behind the ranking
+        uint32_t val[ITEMS];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            uint32_t d = ((uint32_t)key[i] >> shift) & 0xFFu;
-            unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
-            uint32_t lower = __popc(peers & ((1u << lane) - 1u));
-            uint32_t pre = s_warpHist[warp][d];
-            __syncwarp();
-            if (lower == 0) s_warpHist[warp][d] = pre + __popc(peers);
-            __syncwarp();
+            uint32_t j = warpBase + i * 32u;
+            val[i] = (j < tileValid) ? valsIn[base + j] : 0u;
+        }
+        // rank inside the warp, in index order. Peers of a lane = lanes holding the same digit, found with 8
+        // ballots (one per digit bit; independent across items, so they pipeline) -- MATCH.ANY made this loop
+        // latency-bound (ncu r1_v3: 39 % short-scoreboard stalls on its result). The lowest peer bumps the warp's
+        // private counter with one shared-memory atomic and broadcasts the old value.
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = ((uint32_t)key[i] >> shift) & 0xFFu;
+            unsigned peers = 0xFFFFFFFFu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
+                peers &= bit ? bal : ~bal;
+            }
+            const uint32_t lower = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pre = 0;
+            if (lower == 0) pre = atomicAdd(&s_warpHist[warp][d], (uint32_t)__popc(peers));
+            pre = __shfl_sync(0xFFFFFFFFu, pre, __ffs(peers) - 1);
             rank[i] = pre + lower;
         }
         __syncthreads();
@@ -219,13 +234,8 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
             rank[i] += s_binExcl[d] + s_warpHist[warp][d];  // position inside the tile
             s_keys[rank[i]] = key[i];
         }
-        // payload of the same elements
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            uint32_t j = warpBase + i * 32u;
-            uint32_t v = (j < tileValid) ? valsIn[base + j] : 0u;
-            s_vals[rank[i]] = v;
-        }
+        for (int i = 0; i < ITEMS; ++i) s_vals[rank[i]] = val[i];
         __syncthreads();
         // valid elements occupy tile positions [0, tileValid) except that sentinel padding sits at the end of
         // the sentinel digit's bin; bins after it (none: the sentinel digit is 0xFF) would shift.
@@ -250,7 +260,7 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
     const int gridHist = p.numSMs * 4;
     KeyT* k0 = (KeyT*)p.k0;
     KeyT* k1 = (KeyT*)p.k1;
-    switch (p.numPasses) {
+    if (!p.histogramReady) switch (p.numPasses) {
         case 1: radix_histogram_kernel<KeyT, 1><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
         case 2: radix_histogram_kernel<KeyT, 2><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
         case 3: radix_histogram_kernel<KeyT, 3><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
