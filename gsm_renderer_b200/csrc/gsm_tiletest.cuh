@@ -202,12 +202,30 @@ __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const
         __syncwarp();
         if (active && (peers & ((1u << lane) - 1u)) == 0u) s.counter[o] = before + __popc(hits);
         __syncwarp();
+        if (histPasses > 1) {
+            // higher digits are equal along a tile row, so one shared-memory atomic per lane would serialise; lanes
+            // that hit and share the upper bits with their left neighbour form a run and only its head adds the run length
+            const bool counted = hit && (sBase[o] + before + __popc(hits & ((1u << lane) - 1u)) < maxAssignments);
+            const uint32_t hi = tileId >> 8;
+            const uint32_t hiPrev = __shfl_up_sync(0xFFFFFFFFu, hi, 1);
+            const unsigned cmask = __ballot_sync(0xFFFFFFFFu, counted);
+            const bool head = counted && (lane == 0 || !((cmask >> (lane - 1)) & 1u) || hiPrev != hi);
+            const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+            if (head) {
+                const unsigned after = heads & ~((2u << lane) - 1u);           // heads to my right
+                const unsigned breaks = (~cmask) & ~((2u << lane) - 1u);       // first uncounted lane to my right ends the run too
+                const unsigned stop = after | breaks;
+                const uint32_t endLane = stop ? (uint32_t)(__ffs(stop) - 1) : 32u;
+                const uint32_t runLen = endLane - lane;
+                for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], runLen);
+            }
+        }
         if (hit) {
             const uint32_t pos = sBase[o] + before + __popc(hits & ((1u << lane) - 1u));
             if (pos < maxAssignments) {  // DFS.metal:707
                 tileIds[pos] = (TileT)tileId;
                 instanceIdx[pos] = sIdx[o];
-                for (uint32_t p = 0; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], 1u);
+                atomicAdd(&sHist[tileId & 0xFFu], 1u);  // low digit: neighbouring lanes hold consecutive tiles, no conflict
             }
         }
     }
