@@ -191,6 +191,15 @@ int tileSortPasses(uint32_t tileCount) {  // TileSortEncoder.swift:61-62
     return (bits + 7) / 8;
 }
 
+SortReset tileSortReset(const gsm_renderer* r, const Resources& res, uint32_t tilesX, uint32_t tilesY) {
+    const bool tile16 = r->cfg.tileIdPrecision == GSM_KEY_BITS16;
+    SortReset reset;
+    reset.status = res.tileSortStatus; reset.statusStride = res.tileTilesCap * 256u;
+    reset.gstatus = res.tileSortGStatus; reset.gstatusStride = ((res.tileTilesCap + 15u) / 16u) * 256u;
+    reset.passes = (uint32_t)tileSortPasses(tilesX * tilesY); reset.tileSize = sortTileSize(tile16 ? 16 : 32);
+    return reset;
+}
+
 bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 void recordStage(gsm_renderer* r, cudaStream_t s, int idx) {
@@ -215,15 +224,9 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     recordStage(r, s, 2);
     // stages 3+4
     const int tilePasses = tileSortPasses(tilesX * tilesY);
-    SortReset reset;
-    reset.status = res.tileSortStatus; reset.statusStride = res.tileTilesCap * 256u;
-    reset.gstatus = res.tileSortGStatus; reset.gstatusStride = ((res.tileTilesCap + 15u) / 16u) * 256u;
-    reset.passes = (uint32_t)tilePasses; reset.tileSize = sortTileSize(tile16 ? 16 : 32);
-    GSM_CUDA(launchApplyOrderScan(s, res.primIdx[0], res.nTouched, res.offsets, res.header, res.scanStatus, &res.fs->ticketScan,
-                                  r->numSMs, reset), "apply order + scan");
     recordStage(r, s, 3);
     // stage 5
-    GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.offsets, res.bounds, res.renderData, res.tileIds[0],
+    GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.nTouched, res.offsets, res.scanStatus, &res.fs->ticketScan, res.bounds, res.renderData, res.tileIds[0],
                                    res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians, &res.fs->hist[4][0],
                                    (uint32_t)tilePasses, r->numSMs), "create instances");
     recordStage(r, s, 4);
@@ -239,7 +242,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     recordStage(r, s, 5);
     // stage 7
     GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.tileHeaders,
-                              res.activeTiles, &res.fs->activeTileCount, r->numSMs), "tile ranges");
+                              res.activeTiles, &res.fs->activeTileCount, &res.fs->rangesDone, r->numSMs), "tile ranges");
     recordStage(r, s, 6);
     return GSM_OK;
 }
@@ -375,7 +378,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
-    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
+    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances, tileSortReset(r, res, tilesX, tilesY), r->numSMs), "finalize header");
     recordStage(r, s, 1);
     st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);
     if (st != GSM_OK) return st;
@@ -436,7 +439,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
-    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
+    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances, tileSortReset(r, res, tilesX, tilesY), r->numSMs), "finalize header");
     recordStage(r, s, 1);
     st = encodeSortExpandRange(r, res, s, true, tilesX, tilesY);
     if (st != GSM_OK) return st;
@@ -546,7 +549,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u; po.depthKey16 = 0; po.gidFirst = 0;
     GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po), "ingest records");
-    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances), "finalize header");
+    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances, tileSortReset(r, res, tilesX, tilesY), r->numSMs), "finalize header");
     st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, /*depthHistReady=*/false);  // records were compacted by the ingest kernel
     if (st != GSM_OK) return st;
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,

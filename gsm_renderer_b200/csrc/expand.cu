@@ -1,7 +1,10 @@
-// expand.cu -- stage 5: per depth-sorted Gaussian, re-run the exact tile test on the quantised record and
-// emit (tileId, originalIdx) at the scan offset, row-major ty -> tx, bounded by maxAssignments.
-// Replaces createInstancesKernel / ...32 (DFS.metal:642-788) and createInstancesStereoKernel / ...32
-// (DFS.metal:790-864).
+// expand.cu -- stages 3+4+5 in one kernel: ordered[i] = nTouched[sortedIdx[i]] (applyDepthOrderingKernel,
+// DFS.metal:623-640), its exclusive scan (5-kernel prefix sum, DFS.metal:2036-2139, driver
+// InstanceExpansionEncoder.swift:83-176) by a single-pass decoupled look-back over 256-Gaussian tiles, and the
+// instance expansion itself: re-run the exact tile test on the quantised record and emit (tileId, originalIdx) at
+// the scan offset, row-major ty -> tx, bounded by maxAssignments (createInstancesKernel / ...32 DFS.metal:642-788,
+// createInstancesStereoKernel / ...32 DFS.metal:790-864). A tile publishes its aggregate before it starts walking,
+// so nobody waits on a neighbour's tile walk. The tile sort's digit histograms are accumulated on the way out.
 #include "gsm_common.cuh"
 #include "gsm_kernels.h"
 #include "gsm_tiletest.cuh"
@@ -10,8 +13,9 @@ namespace gsm {
 
 template <typename TileT, bool STEREO>
 __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __restrict__ sortedIdx,
-                                                               const uint32_t* __restrict__ offsets,
-                                                               const int32_t* __restrict__ bounds,
+                                                               const uint32_t* __restrict__ nTouched,
+                                                               uint32_t* __restrict__ offsets, unsigned long long* scanStatus,
+                                                               uint32_t* ticket, const int32_t* __restrict__ bounds,
                                                                const void* __restrict__ renderData,
                                                                TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx,
                                                                const GSMDepthFirstHeader* __restrict__ header, uint32_t tilesX,
@@ -23,22 +27,40 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
     __syncthreads();
     __shared__ uint32_t s_base[8][32];
     __shared__ int32_t s_idx[8][32];
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_tile, s_tileBase;
     const uint32_t visibleCount = header->visibleCount;
     const unsigned warp = threadIdx.x >> 5;
+    const uint32_t numTiles = (visibleCount + 255u) / 256u;
     // whole warps stay together: the tile walk is warp-cooperative
-    for (uint32_t i0 = blockIdx.x * 256u; i0 < visibleCount; i0 += gridDim.x * 256u) {
-        const uint32_t i = i0 + threadIdx.x;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= numTiles) break;
+        const uint32_t i = tile * 256u + threadIdx.x;
         int32_t originalIdx = -1;
         int minTX = 0, maxTX = -1, minTY = 0, maxTY = -1;
         uint32_t writeOffset = 0, n = 0;
         QuantSplat q = {};
+        if (i < visibleCount) originalIdx = sortedIdx[i];
+        {   // stages 3+4: gather the tile count in depth order, scan, publish the tile aggregate, look back
+            const uint32_t cnt = (originalIdx >= 0) ? __ldg(nTouched + originalIdx) : 0u;  // DFS.metal:633-639
+            uint32_t total;
+            const uint32_t excl = block_exclusive_scan_256(cnt, s_scan, total);
+            if (threadIdx.x < 32) {
+                const uint32_t b = lookback_exclusive(scanStatus, tile, total);
+                if (threadIdx.x == 0) s_tileBase = b;
+            }
+            __syncthreads();
+            writeOffset = s_tileBase + excl;
+            if (i < visibleCount) offsets[i] = writeOffset;  // the in-place scan result (debugReadInstanceOffsets)
+        }
         if (i < visibleCount) {
-            originalIdx = sortedIdx[i];
             if (originalIdx >= 0) {
                 const int4 b = __ldg(reinterpret_cast<const int4*>(bounds) + originalIdx);
                 minTX = b.x; maxTX = b.y; minTY = b.z; maxTY = b.w;
                 if (minTX <= maxTX && minTY <= maxTY) {
-                    writeOffset = offsets[i];
                     n = (uint32_t)((maxTX - minTX + 1) * (maxTY - minTY + 1));
                     if (!STEREO) {
                         const uint4 rd = __ldg(reinterpret_cast<const uint4*>(renderData) + originalIdx);
@@ -67,14 +89,14 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
     }
 }
 
-cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* offsets,
-                                  const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
+cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* nTouched,
+                                  uint32_t* offsets, unsigned long long* scanStatus, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
                                   uint32_t* tileHist, uint32_t tilePasses, int numSMs) {
     uint32_t grid = (capVisible + 255u) / 256u;
     if (grid > (uint32_t)numSMs * 6u) grid = (uint32_t)numSMs * 6u;  // persistent: few CTAs flush the fused histograms
     if (grid == 0) grid = 1;
-#define GSM_LAUNCH(T, ST) create_instances_kernel<T, ST><<<grid, 256, 0, s>>>(sortedIdx, offsets, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
+#define GSM_LAUNCH(T, ST) create_instances_kernel<T, ST><<<grid, 256, 0, s>>>(sortedIdx, nTouched, offsets, scanStatus, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
     if (tileId16) { if (stereo) GSM_LAUNCH(uint16_t, true); else GSM_LAUNCH(uint16_t, false); }
     else { if (stereo) GSM_LAUNCH(uint32_t, true); else GSM_LAUNCH(uint32_t, false); }
 #undef GSM_LAUNCH

@@ -24,7 +24,8 @@ struct FrameState {
     uint32_t ticketProject;      // dynamic tile ids => look-back forward progress
     uint32_t ticketScan;
     uint32_t ticketSort[8];      // depth passes 0-3, tile passes 4-7
-    uint32_t _pad[3];
+    uint32_t rangesDone;         // CTAs of the tile-range kernel that finished their boundary scan
+    uint32_t _pad[2];
     uint32_t hist[8][256];       // global digit histograms: depth passes 0-3, tile passes 4-7
 };
 

@@ -25,12 +25,14 @@ struct ProjectOut {
     uint32_t* depthGStatus; uint32_t depthGStatusStride;
 };
 
+struct SortReset;
 int shDegreeFromComponents(uint32_t n);
 const void* finalize_header_probe();  // a kernel symbol, to test that the sm_100a image loads
 cudaError_t launchProjectMono(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam, const ProjectOut& o);
 cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, const void* h, const StereoCam& cam, const ProjectOut& o);
 cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o, int numSMs);
-cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians, uint32_t maxInstances);
+cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians, uint32_t maxInstances,
+                                 const SortReset& reset, int numSMs);
 
 // Onesweep radix sort (sort.cu). keys/vals ping-pong between (k0,v0) and (k1,v1); after numPasses the
 // result is in (k0,v0) if numPasses is even, else it is copied back. countPtr is read on the device.
@@ -51,23 +53,20 @@ uint32_t sortTileSize(int keyBits);
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p);
 
 // apply depth order + exclusive scan (scan.cu)
-struct SortReset {  // look-back words of the tile sort, reset by the scan kernel (it knows totalInstances exactly)
+struct SortReset {  // look-back words of the tile sort, reset by the header kernel (it knows totalInstances exactly)
     uint32_t* status; uint32_t statusStride; uint32_t* gstatus; uint32_t gstatusStride; uint32_t passes; uint32_t tileSize;
 };
-cudaError_t launchApplyOrderScan(cudaStream_t s, const int32_t* sortedIdx, const uint32_t* nTouched, uint32_t* offsetsOut,
-                                 const GSMDepthFirstHeader* header, unsigned long long* status, uint32_t* ticket, int numSMs,
-                                 const SortReset& reset);
 
 // instance expansion (expand.cu)
-cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* offsets,
-                                  const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
+cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* nTouched,
+                                  uint32_t* offsets, unsigned long long* scanStatus, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
                                   uint32_t* tileHist, uint32_t tilePasses, int numSMs);
 
 // tile ranges (ranges.cu)
 cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,
                              uint32_t tileCount, uint32_t* lowerBounds, GSMGaussianHeader* tileHeaders, uint32_t* activeTiles,
-                             uint32_t* activeTileCount, int numSMs);
+                             uint32_t* activeTileCount, uint32_t* doneCounter, int numSMs);
 
 // blend (blend.cu)
 cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,

@@ -765,18 +765,26 @@ cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o
 }
 
 // DFS.metal:2184-2203 (+ reset :1372-1385)
-__global__ void finalize_header_kernel(const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians,
-                                       uint32_t maxInstances) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) finalize_header_kernel(const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians,
+                                                              uint32_t maxInstances, SortReset reset) {
     uint32_t v = fs->visibleCountRaw, i = fs->totalInstancesRaw, overflow = 0;
     if (v > maxGaussians) { v = maxGaussians; overflow = 1u; }
     if (i > maxInstances) { i = maxInstances; overflow = 1u; }
-    header->visibleCount = v;
-    header->totalInstances = i;
-    header->paddedVisibleCount = ((v + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
-    header->paddedInstanceCount = ((i + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
-    header->overflow = overflow;
-    header->padding0 = 0; header->padding1 = 0; header->padding2 = 0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        header->visibleCount = v;
+        header->totalInstances = i;
+        header->paddedVisibleCount = ((v + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
+        header->paddedInstanceCount = ((i + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
+        header->overflow = overflow;
+        header->padding0 = 0; header->padding1 = 0; header->padding2 = 0;
+    }
+    // reset the tile sort's look-back words for exactly the tiles this frame's totalInstances needs
+    const uint32_t words = ((i + reset.tileSize - 1u) / reset.tileSize) * 256u;
+    const uint32_t gwords = ((words / 256u + 15u) / 16u) * 256u;
+    for (uint32_t p = 0; p < reset.passes; ++p) {
+        for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < words; k += gridDim.x * 256u) reset.status[(size_t)p * reset.statusStride + k] = 0u;
+        for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < gwords; k += gridDim.x * 256u) reset.gstatus[(size_t)p * reset.gstatusStride + k] = 0u;
+    }
 }
 
 const void* finalize_header_probe() { return (const void*)finalize_header_kernel; }
@@ -821,8 +829,8 @@ cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, c
     return halfInput ? launchStereo<true>(deg, grid, s, g, h, cam, o) : launchStereo<false>(deg, grid, s, g, h, cam, o);
 }
 cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians,
-                                 uint32_t maxInstances) {
-    finalize_header_kernel<<<1, 32, 0, s>>>(fs, header, maxGaussians, maxInstances);
+                                 uint32_t maxInstances, const SortReset& reset, int numSMs) {
+    finalize_header_kernel<<<numSMs, 256, 0, s>>>(fs, header, maxGaussians, maxInstances, reset);
     return cudaGetLastError();
 }
 

@@ -176,6 +176,11 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
             {   // level 1: predecessors inside the group
                 const int groupStart = (int)(group * kLookGroup);
                 int look = (int)tile - 1;
+                if (look >= groupStart) {  // streaming steady state: the predecessor is usually already inclusive -- one load
+                    const uint32_t sw = ld_status32(status + (size_t)look * 256u + tid);
+                    if (sw & kStatusInclusive) { exclusive += sw & kStatusValueMask; done = true; }
+                    else if (sw & kStatusAggregate) { exclusive += sw & kStatusValueMask; look--; }
+                }
                 while (!done && look >= groupStart) {
                     uint32_t sv[kLookBatch];
 #pragma unroll
