@@ -73,6 +73,15 @@ __device__ __forceinline__ void storePixelRow(__half* color, __half* depth, uint
     }
 }
 
+// DFS.metal:1304-1312: the tile's {offset,count} header and, for a non-empty tile, one atomic append to the active list
+__device__ __forceinline__ void publishTile(const TileOut& tout, uint32_t tile, uint32_t start, uint32_t count) {
+    GSMGaussianHeader h;
+    h.offset = start;
+    h.count = count;
+    tout.tileHeaders[tile] = h;
+    if (count > 0) tout.activeTiles[atomicAdd(tout.activeTileCount, 1u)] = tile;
+}
+
 // Staged form of one splat for one tile. p = (dx*dx*cxx + dy*dy*cyy) + dx*dy*cxy2 (DFS.metal:1770) splits into a
 // per-COLUMN term T0 = (dx*dx)*cxx, a per-ROW term T1 = (dy*dy)*cyy and the per-pixel cross term; T0/T1/dx/dy are
 // the same half operations on the same operands whichever thread evaluates them, so they are computed once
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                                                                    const BlendSplat* __restrict__ splats,
                                                                    const int32_t* __restrict__ instanceIdx, uint32_t width,
                                                                    uint32_t height, uint32_t tilesX, uint32_t tileRowFirst,
-                                                                   __half* __restrict__ color, __half* __restrict__ depth) {
+                                                                   __half* __restrict__ color, __half* __restrict__ depth, TileOut tout) {
     __shared__ StagedSplat s_sp[kBlendChunk];
     const unsigned tid = threadIdx.x;
     const unsigned lx = tid & 7u, ly = tid >> 3;
@@ -181,6 +190,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
     else { al0 = one; al1 = one; }
     storePixelRow(color, depth, width, height, baseX, baseY, q.r0, q.g0, q.b0, al0, q.d0);
     storePixelRow(color, depth, width, height, baseX, baseY + 1u, q.r1, q.g1, q.b1, al1, q.d1);
+    if (tid == 0) publishTile(tout, tile, start, count);
 }
 
 // one eye of depthFirstStereoRender for one splat (DFS.metal:1881-1920)
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
                                                                      const GSMStereoTiledRenderData* __restrict__ splats,
                                                                      const int32_t* __restrict__ instanceIdx, uint32_t width,
                                                                      uint32_t height, uint32_t tilesX,
-                                                                     __half* __restrict__ dstSideBySide, int flipY, int eyeMask) {
+                                                                     __half* __restrict__ dstSideBySide, int flipY, int eyeMask, TileOut tout) {
     __shared__ uint4 s_rec[kBlendChunk][2];
     __shared__ uint32_t s_valid[kBlendChunk];
     const bool doL = (eyeMask & 1) != 0, doR = (eyeMask & 2) != 0;  // one-eye-per-GPU split
@@ -302,23 +312,24 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
             }
         }
     }
+    if (tid == 0) publishTile(tout, tile, start, count);
 }
 
 cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,
                             uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY, uint32_t tileRowFirst,
-                            uint32_t tileRowCount, __half* color, __half* depth) {
+                            uint32_t tileRowCount, __half* color, __half* depth, TileOut tout) {
     (void)tilesY;
     if (tileRowCount == 0) return cudaSuccess;
     blend_mono_kernel<<<tilesX * tileRowCount, kBlendThreads, 0, s>>>(lowerBounds, splats, instanceIdx, width, height, tilesX,
-                                                                       tileRowFirst, color, depth);
+                                                                       tileRowFirst, color, depth, tout);
     return cudaGetLastError();
 }
 
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
-                              __half* dstSideBySide, int eyeMask, int flipY) {
+                              __half* dstSideBySide, int eyeMask, int flipY, TileOut tout) {
     blend_stereo_kernel<<<tilesX * tilesY, kBlendThreads, 0, s>>>(lowerBounds, splats, instanceIdx, width, height, tilesX,
-                                                                   dstSideBySide, flipY, eyeMask);
+                                                                   dstSideBySide, flipY, eyeMask, tout);
     return cudaGetLastError();
 }
 

@@ -241,8 +241,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     GSM_CUDA(launchSort(s, tp), "tile sort");
     recordStage(r, s, 5);
     // stage 7
-    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.tileHeaders,
-                              res.activeTiles, &res.fs->activeTileCount, &res.fs->rangesDone, r->numSMs), "tile ranges");
+    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, r->numSMs), "tile ranges");
     recordStage(r, s, 6);
     return GSM_OK;
 }
@@ -384,7 +383,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     if (st != GSM_OK) return st;
     // step 8: clear + blend (DFR.swift:433-464), fused
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, 0, tilesY,
-                             (__half*)color, (__half*)depth), "blend");
+                             (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "blend");
     recordStage(r, s, 7);
     recordStage(r, s, 8);
     if (r->profiling) r->evRecorded = true;
@@ -445,7 +444,8 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     if (st != GSM_OK) return st;
     // steps 9+10: clear, blend both eyes, copy into the side-by-side target (DFR.swift:789-830), fused
     GSM_CUDA(launchBlendStereo(s, res.lowerBounds, (const GSMStereoTiledRenderData*)res.renderData, res.instIdx[0], width, height,
-                               tilesX, tilesY, (__half*)colorSideBySide, (int)(eyeMask & 3u), r->cfg.stereoCopyFlipY ? 1 : 0), "stereo blend");
+                               tilesX, tilesY, (__half*)colorSideBySide, (int)(eyeMask & 3u), r->cfg.stereoCopyFlipY ? 1 : 0,
+                               TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "stereo blend");
     recordStage(r, s, 7);
     recordStage(r, s, 8);
     if (r->profiling) r->evRecorded = true;
@@ -553,7 +553,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, /*depthHistReady=*/false);  // records were compacted by the ingest kernel
     if (st != GSM_OK) return st;
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
-                             tileRowCount, (__half*)color, (__half*)depth), "strip blend");
+                             tileRowCount, (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "strip blend");
     return GSM_OK;
 }
 

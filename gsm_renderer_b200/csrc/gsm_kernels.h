@@ -65,16 +65,16 @@ cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, co
 
 // tile ranges (ranges.cu)
 cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,
-                             uint32_t tileCount, uint32_t* lowerBounds, GSMGaussianHeader* tileHeaders, uint32_t* activeTiles,
-                             uint32_t* activeTileCount, uint32_t* doneCounter, int numSMs);
+                             uint32_t tileCount, uint32_t* lowerBounds, int numSMs);
 
-// blend (blend.cu)
+// blend (blend.cu). Each tile's CTA also writes its GaussianHeader and appends itself to the active list.
+struct TileOut { GSMGaussianHeader* tileHeaders; uint32_t* activeTiles; uint32_t* activeTileCount; };
 cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,
                             uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY, uint32_t tileRowFirst,
-                            uint32_t tileRowCount, __half* color, __half* depth);
+                            uint32_t tileRowCount, __half* color, __half* depth, TileOut tout);
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
-                              __half* dstSideBySide, int eyeMask, int flipY);
+                              __half* dstSideBySide, int eyeMask, int flipY, TileOut tout);
 
 // strip-sharded frame (strip.cu)
 cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,

@@ -132,7 +132,7 @@ typedef enum {
     GSM_DBG_DEPTH_KEYS = 8,           /* debugReadDepthKeys: u32 per visible, sorted */
     GSM_DBG_RENDER_DATA = 9,          /* debugReadRenderData: GSMGaussianRenderData (mono) / GSMStereoTiledRenderData */
     GSM_DBG_TILE_HEADERS = 10,        /* debugReadTileHeaders: GSMGaussianHeader per tile */
-    GSM_DBG_ACTIVE_TILES = 11,        /* activeTiles list (ascending here; atomic order in the reference) */
+    GSM_DBG_ACTIVE_TILES = 11,        /* activeTiles list (atomic append order, nondeterministic as in the reference) */
     GSM_DBG_SCRATCH_DEPTH_KEYS = 12,  /* debugReadScratchDepthKeys: ping-pong buffer, content unspecified */
     GSM_DBG_SCRATCH_PRIMITIVE_INDICES = 13, /* debugReadScratchPrimitiveIndices: same */
     GSM_DBG_COUNT_
