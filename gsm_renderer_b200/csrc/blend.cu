@@ -32,22 +32,23 @@ __device__ __forceinline__ void accumulate(QuadState& q, __half2 a0, __half2 a1,
                                            bool withDepth) {
     const __half2 one = h2(1.0f);
     __half2 w0 = __hmul2_rn(a0, q.T0), w1 = __hmul2_rn(a1, q.T1);
-    q.r0 = __hadd2_rn(q.r0, __hmul2_rn(cr, w0)); q.r1 = __hadd2_rn(q.r1, __hmul2_rn(cr, w1));
-    q.g0 = __hadd2_rn(q.g0, __hmul2_rn(cg, w0)); q.g1 = __hadd2_rn(q.g1, __hmul2_rn(cg, w1));
-    q.b0 = __hadd2_rn(q.b0, __hmul2_rn(cb, w0)); q.b1 = __hadd2_rn(q.b1, __hmul2_rn(cb, w1));
+    // color += gColor * (a*T): contracted to one fused half FMA (canonical semantics)
+    q.r0 = __hfma2(cr, w0, q.r0); q.r1 = __hfma2(cr, w1, q.r1);
+    q.g0 = __hfma2(cg, w0, q.g0); q.g1 = __hfma2(cg, w1, q.g1);
+    q.b0 = __hfma2(cb, w0, q.b0); q.b1 = __hfma2(cb, w1, q.b1);
     if (withDepth) {
-        q.d0 = __hadd2_rn(q.d0, __hmul2_rn(cd, w0)); q.d1 = __hadd2_rn(q.d1, __hmul2_rn(cd, w1));
+        q.d0 = __hfma2(cd, w0, q.d0); q.d1 = __hfma2(cd, w1, q.d1);
     }
     q.T0 = __hmul2_rn(q.T0, __hsub2_rn(one, a0));
     q.T1 = __hmul2_rn(q.T1, __hsub2_rn(one, a1));
 }
 
-// p = dx*dx*cxx + dy*dy*cyy + dx*dy*cxy2 for one row (two pixels), one rounding per op (DFS.metal:1770)
+// p = dx*dx*cxx + dy*dy*cyy + dx*dy*cxy2 for one row (two pixels) (DFS.metal:1770), contracted as
+// fma(dx*dy, cxy2, fma(dy*dy, cyy, (dx*dx)*cxx))
 __device__ __forceinline__ __half2 power(__half2 dx, __half2 dy, __half2 cxx, __half2 cyy, __half2 cxy2) {
     __half2 t0 = __hmul2_rn(__hmul2_rn(dx, dx), cxx);
-    __half2 t1 = __hmul2_rn(__hmul2_rn(dy, dy), cyy);
-    __half2 t2 = __hmul2_rn(__hmul2_rn(dx, dy), cxy2);
-    return __hadd2_rn(__hadd2_rn(t0, t1), t2);
+    __half2 in = __hfma2(__hmul2_rn(dy, dy), cyy, t0);
+    return __hfma2(__hmul2_rn(dx, dy), cxy2, in);
 }
 
 __device__ __forceinline__ bool quadClosed(const __half2& T0, const __half2& T1, __half thr) {
@@ -82,16 +83,16 @@ __device__ __forceinline__ void publishTile(const TileOut& tout, uint32_t tile, 
     if (count > 0) tout.activeTiles[atomicAdd(tout.activeTileCount, 1u)] = tile;
 }
 
-// Staged form of one splat for one tile. p = (dx*dx*cxx + dy*dy*cyy) + dx*dy*cxy2 (DFS.metal:1770) splits into a
-// per-COLUMN term T0 = (dx*dx)*cxx, a per-ROW term T1 = (dy*dy)*cyy and the per-pixel cross term; T0/T1/dx/dy are
-// the same half operations on the same operands whichever thread evaluates them, so they are computed once
-// per (splat, column pair) and (splat, row pair) by the staging thread instead of once per pixel (ncu r1_v2:
-// the kernel was FMA-pipe bound at 73 %, 19 packed half ops per far pixel quad; this form needs 8).
+// Staged form of one splat for one tile. p = fma(dx*dy, cxy2, fma(dy*dy, cyy, (dx*dx)*cxx)) (DFS.metal:1770) has a
+// per-COLUMN part T0 = (dx*dx)*cxx and a per-ROW part dy*dy; T0, dy*dy, dx, dy are the same half operations on the
+// same operands whichever thread evaluates them, so they are computed once per (splat, column pair) and (splat,
+// row pair) by the staging thread instead of once per pixel (ncu r1_v2: the kernel was FMA-pipe bound at 73 %,
+// 19 packed half ops per pixel quad for p; this form needs 6).
 struct StagedSplat {
     uint2 col[8];  // per x pair k: {T0(x=2k), T0(2k+1)} , {dx(2k), dx(2k+1)}
-    uint2 row[8];  // per y pair k: {T1(y=2k), T1(2k+1)} , {dy(2k), dy(2k+1)}
+    uint2 row[8];  // per y pair k: {dy*dy(y=2k), dy*dy(2k+1)} , {dy(2k), dy(2k+1)}
     uint4 m0;      // cxy2|cxy2, op|op, r|r, g|g
-    uint4 m1;      // b|b, depth|depth, valid, -
+    uint4 m1;      // b|b, depth|depth, valid, cyy|cyy
 };
 
 __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_t* __restrict__ lowerBounds,
@@ -145,12 +146,11 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                     const __half2 t0 = __hmul2_rn(__hmul2_rn(dx, dx), cxx);
                     sp.col[k] = make_uint2(h2bits(t0), h2bits(dx));
                     const __half2 dy = __hsub2_rn(pys[k], my);
-                    const __half2 t1 = __hmul2_rn(__hmul2_rn(dy, dy), cyy);
-                    sp.row[k] = make_uint2(h2bits(t1), h2bits(dy));
+                    sp.row[k] = make_uint2(h2bits(__hmul2_rn(dy, dy)), h2bits(dy));
                 }
                 sp.m0 = make_uint4(h2bits(__low2half2(cxy2_op)), h2bits(__high2half2(cxy2_op)), h2bits(__low2half2(rg)),
                                    h2bits(__high2half2(rg)));
-                sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 1u, 0u);
+                sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 1u, h2bits(cyy));
             } else {
                 sp.m1 = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
             }
@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                 const uint2 c = sp.col[lx], r = sp.row[ly];
                 const uint4 m0 = sp.m0;
                 const __half2 t0 = *reinterpret_cast<const __half2*>(&c.x), dx = *reinterpret_cast<const __half2*>(&c.y);
-                const __half2 t1p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
-                const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x);
-                // (t0 + t1) + (dx*dy)*cxy2 for the two rows of the quad
-                const __half2 p0 = __hadd2_rn(__hadd2_rn(t0, __low2half2(t1p)), __hmul2_rn(__hmul2_rn(dx, __low2half2(dyp)), cxy2));
-                const __half2 p1 = __hadd2_rn(__hadd2_rn(t0, __high2half2(t1p)), __hmul2_rn(__hmul2_rn(dx, __high2half2(dyp)), cxy2));
+                const __half2 dy2p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
+                const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x), cyy = *reinterpret_cast<const __half2*>(&m1.w);
+                // fma(dx*dy, cxy2, fma(dy*dy, cyy, t0)) for the two rows of the quad
+                const __half2 p0 = __hfma2(__hmul2_rn(dx, __low2half2(dyp)), cxy2, __hfma2(__low2half2(dy2p), cyy, t0));
+                const __half2 p1 = __hfma2(__hmul2_rn(dx, __high2half2(dyp)), cxy2, __hfma2(__high2half2(dy2p), cyy, t0));
                 // p > 35 on all four pixels => -0.5h*p < -17.5 => exp() is exactly +0 => alphas are 0 => "continue"
                 // (NaN compares false and takes the full path)
                 if (__hbgt2(p0, farP) && __hbgt2(p1, farP)) continue;

@@ -32,6 +32,11 @@ __global__ void probe_kernel(int op, const void* a, const void* b, void* out, ui
             ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2_packed(v)));
             break;
         }
+        case 11: {  // fused half FMA: a holds (x, y, z) triples
+            const unsigned short* ha = (const unsigned short*)a;
+            ((unsigned short*)out)[i] = __half_as_ushort(__hfma(__ushort_as_half(ha[3 * i]), __ushort_as_half(ha[3 * i + 1]), __ushort_as_half(ha[3 * i + 2])));
+            break;
+        }
         case 9: fo[i] = dmin(fa[i], fb[i]); break;
         case 10: fo[i] = dmax(fa[i], fb[i]); break;
         default: break;

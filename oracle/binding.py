@@ -174,6 +174,13 @@ def probe_hexp(xbits):
     return y
 
 
+def probe_hfma(a, b, c):
+    a, b, c = (np.ascontiguousarray(x, np.uint16) for x in (a, b, c))
+    r = np.empty_like(a)
+    lib().gsmo_probe_hfma(_p(a), _p(b), _p(c), _p(r), C.c_int(a.size))
+    return r
+
+
 def probe_minmax(a, b):
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)

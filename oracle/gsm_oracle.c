@@ -30,6 +30,7 @@ void gsmo_probe_powr(const float* x, float yexp, float* r, int n) { for (int i =
 void gsmo_probe_hexp(const gsmo_half* x, gsmo_half* y, int n) { for (int i = 0; i < n; ++i) y[i] = gsmo_hexp(x[i]); }
 void gsmo_probe_f2h(const float* x, gsmo_half* y, int n) { for (int i = 0; i < n; ++i) y[i] = gsmo_f2h(x[i]); }
 void gsmo_probe_minmax(const float* a, const float* b, float* mn, float* mx, int n) { for (int i = 0; i < n; ++i) { mn[i] = gsmo_fmin(a[i], b[i]); mx[i] = gsmo_fmax(a[i], b[i]); } }
+void gsmo_probe_hfma(const gsmo_half* a, const gsmo_half* b, const gsmo_half* c, gsmo_half* r, int n) { for (int i = 0; i < n; ++i) r[i] = gsmo_hfma(a[i], b[i], c[i]); }
 void gsmo_probe_h2f(const gsmo_half* x, float* y, int n) { for (int i = 0; i < n; ++i) y[i] = gsmo_h2f(x[i]); }
 
 /* ---------------------------------------------------------------- small linear algebra */
@@ -1015,12 +1016,12 @@ static inline int h_gt(gsmo_half a, gsmo_half b) { return gsmo_h2f(a) > gsmo_h2f
 static inline int h_ge(gsmo_half a, gsmo_half b) { return gsmo_h2f(a) >= gsmo_h2f(b); }
 static inline int h_eq0(gsmo_half a) { return gsmo_h2f(a) == 0.0f; }
 
-/* d.x*d.x*cxx + d.y*d.y*cyy + d.x*d.y*cxy2, each op rounded to half (DFS.metal:1770) */
+/* d.x*d.x*cxx + d.y*d.y*cyy + d.x*d.y*cxy2 (DFS.metal:1770) with the contraction a fast-math compiler applies
+ * to (m0 + m1) + m2: fma(dx*dy, cxy2, fma(dy*dy, cyy, (dx*dx)*cxx)); every other product is a rounded half mul */
 static inline gsmo_half h_power(gsmo_half dx, gsmo_half dy, gsmo_half cxx, gsmo_half cyy, gsmo_half cxy2) {
     gsmo_half t0 = gsmo_hmul(gsmo_hmul(dx, dx), cxx);
-    gsmo_half t1 = gsmo_hmul(gsmo_hmul(dy, dy), cyy);
-    gsmo_half t2 = gsmo_hmul(gsmo_hmul(dx, dy), cxy2);
-    return gsmo_hadd(gsmo_hadd(t0, t1), t2);
+    gsmo_half in = gsmo_hfma(gsmo_hmul(dy, dy), cyy, t0);
+    return gsmo_hfma(gsmo_hmul(dx, dy), cxy2, in);
 }
 
 /* DFS.metal:1703-1811 */
@@ -1073,8 +1074,8 @@ void gsmo_blend(const gsmo_tile_header* headers, const gsmo_render_data* gaussia
                     if (allZero) continue;
                     for (int k = 0; k < 4; ++k) {
                         gsmo_half w = gsmo_hmul(a[k], trans[k]);
-                        for (int c = 0; c < 3; ++c) col[k][c] = gsmo_hadd(col[k][c], gsmo_hmul(gc[c], w));
-                        dep[k] = gsmo_hadd(dep[k], gsmo_hmul(g.depth, w));
+                        for (int c = 0; c < 3; ++c) col[k][c] = gsmo_hfma(gc[c], w, col[k][c]);  /* color += gColor * (a*T), contracted */
+                        dep[k] = gsmo_hfma(g.depth, w, dep[k]);
                     }
                     for (int k = 0; k < 4; ++k) trans[k] = gsmo_hmul(trans[k], gsmo_hsub(H_ONE, a[k]));
                 }
@@ -1155,7 +1156,7 @@ void gsmo_blend_stereo(const gsmo_tile_header* headers, const gsmo_stereo_render
                         if (allZero) continue;
                         for (int k = 0; k < 4; ++k) {
                             gsmo_half w = gsmo_hmul(a[k], trans[e][k]);
-                            for (int c = 0; c < 3; ++c) col[e][k][c] = gsmo_hadd(col[e][k][c], gsmo_hmul(gc[c], w));
+                            for (int c = 0; c < 3; ++c) col[e][k][c] = gsmo_hfma(gc[c], w, col[e][k][c]);
                         }
                         for (int k = 0; k < 4; ++k) trans[e][k] = gsmo_hmul(trans[e][k], gsmo_hsub(H_ONE, a[k]));
                     }

@@ -115,6 +115,7 @@ void gsmo_probe_powr(const float* x, float yexp, float* r, int n);
 void gsmo_probe_hexp(const gsmo_half* x, gsmo_half* y, int n);
 void gsmo_probe_f2h(const float* x, gsmo_half* y, int n);
 void gsmo_probe_h2f(const gsmo_half* x, float* y, int n);
+void gsmo_probe_hfma(const gsmo_half* a, const gsmo_half* b, const gsmo_half* c, gsmo_half* r, int n);
 void gsmo_probe_minmax(const float* a, const float* b, float* mn, float* mx, int n);
 
 /* --- stages --- */

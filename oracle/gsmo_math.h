@@ -42,6 +42,16 @@ static inline gsmo_half gsmo_hadd(gsmo_half a, gsmo_half b) { return gsmo_f2h(gs
 static inline gsmo_half gsmo_hsub(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) - gsmo_h2f(b)); }
 static inline gsmo_half gsmo_hmul(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) * gsmo_h2f(b)); }
 static inline gsmo_half gsmo_hdiv(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) / gsmo_h2f(b)); }
+/* fused multiply-add in binary16: a*b + c rounded ONCE. The exact value spans at most 2^31 .. 2^-48, i.e. < 64
+ * significant bits, so x87 long double (64-bit significand) holds it exactly and the conversion rounds once
+ * (device: HFMA2). Used where the Metal compiler contracts a*b + c under -ffast-math. */
+static inline gsmo_half gsmo_hfma(gsmo_half a, gsmo_half b, gsmo_half c) {
+    long double r = (long double)gsmo_h2f(a) * (long double)gsmo_h2f(b) + (long double)gsmo_h2f(c);
+    _Float16 v = (_Float16)r;
+    gsmo_half h;
+    memcpy(&h, &v, 2);
+    return h;
+}
 static inline int gsmo_hisnan(gsmo_half a) { return (a & 0x7FFFu) > 0x7C00u; }
 /* min/max: a NaN operand loses (IEEE-754-2008 minNum/maxNum, MSL fmin/fmax); -0 orders below +0
  * (the rule of PTX min/max, so the device uses one FMNMX / HMNMX2 instruction). */

@@ -46,6 +46,14 @@ def test_math_probes_bit_exact(oracle):
     nn = ~(np.isnan(ma) & np.isnan(mb))  # both NaN: payload unspecified
     assert np.array_equal(gmn.view(np.uint32)[nn], omn.view(np.uint32)[nn])
     assert np.array_equal(gmx.view(np.uint32)[nn], omx.view(np.uint32)[nn])
+    # fused half fma (HFMA2) == the oracle's exact long-double fma, incl. subnormals, overflow, cancellation
+    tri = rng.integers(0, 65536, (400_000, 3)).astype(np.uint16)
+    small = (rng.normal(0, 1, (200_000, 3)) * np.array([300.0, 0.01, 3.0])).astype(np.float16).view(np.uint16)
+    tri = np.concatenate([tri, small])
+    got = probe_math(11, tri)
+    want = oracle.probe_hfma(tri[:, 0].copy(), tri[:, 1].copy(), tri[:, 2].copy())
+    isn = np.isnan(want.view(np.float16))
+    assert np.array_equal(np.isnan(got.view(np.float16)), isn) and np.array_equal(got[~isn], want[~isn])
     bits = np.arange(65536, dtype=np.uint16)
     ref = oracle.probe_hexp(bits)
     assert np.array_equal(probe_math(5, bits), ref)          # scalar half exp, all 65536 inputs
