@@ -136,7 +136,7 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t oZero = off;
     const size_t oFS = take(sizeof(FrameState));
     const size_t oProjStatus = take(((size_t)(G + 31) / 32 + 8) * 8);  // one look-back word per 32-gid warp tile
-    const size_t oScanStatus = take(((size_t)(G + 31) / 32 + 8) * 8);  // one look-back word per 32-Gaussian expansion tile
+    const size_t oScanStatus = take(((size_t)(G + 255) / 256 + 8) * 8);  // one look-back word per 256-Gaussian expansion tile
     const size_t zeroEnd = off;
     const size_t oDepthStatus = take((size_t)4 * res.depthTilesCap * 256 * 4);
     const size_t oTileStatus = take((size_t)4 * res.tileTilesCap * 256 * 4);

@@ -27,29 +27,33 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
     __syncthreads();
     __shared__ uint32_t s_base[8][32];
     __shared__ int32_t s_idx[8][32];
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_tile, s_tileBase;
     const uint32_t visibleCount = header->visibleCount;
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t numWarpTiles = (visibleCount + 31u) / 32u;
-    // Every WARP is its own worker: it claims a 32-Gaussian tile with a ticket (tickets are handed out in depth
-    // order, so a tile's predecessors are always claimed), scans, looks back and walks -- no __syncthreads in the
-    // loop, so a warp that drew a large splat never holds its siblings (ncu r1_v4: 35 % barrier stalls with CTA tiles).
+    const unsigned warp = threadIdx.x >> 5;
+    const uint32_t numTiles = (visibleCount + 255u) / 256u;
+    // whole warps stay together: the tile walk is warp-cooperative
     while (true) {
-        uint32_t wt = 0;
-        if (lane == 0) wt = atomicAdd(ticket, 1u);
-        wt = __shfl_sync(0xFFFFFFFFu, wt, 0);
-        if (wt >= numWarpTiles) break;
-        const uint32_t i = wt * 32u + lane;
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= numTiles) break;
+        const uint32_t i = tile * 256u + threadIdx.x;
         int32_t originalIdx = -1;
         int minTX = 0, maxTX = -1, minTY = 0, maxTY = -1;
         uint32_t writeOffset = 0, n = 0;
         QuantSplat q = {};
         if (i < visibleCount) originalIdx = sortedIdx[i];
-        {   // stages 3+4: gather the tile count in depth order, scan, publish the aggregate, look back
+        {   // stages 3+4: gather the tile count in depth order, scan, publish the tile aggregate, look back
             const uint32_t cnt = (originalIdx >= 0) ? __ldg(nTouched + originalIdx) : 0u;  // DFS.metal:633-639
             uint32_t total;
-            const uint32_t excl = warpExclusiveScan(cnt, total);
-            const uint32_t base = lookback_exclusive(scanStatus, wt, total);
-            writeOffset = base + excl;
+            const uint32_t excl = block_exclusive_scan_256(cnt, s_scan, total);
+            if (threadIdx.x < 32) {
+                const uint32_t b = lookback_exclusive(scanStatus, tile, total);
+                if (threadIdx.x == 0) s_tileBase = b;
+            }
+            __syncthreads();
+            writeOffset = s_tileBase + excl;
             if (i < visibleCount) offsets[i] = writeOffset;  // the in-place scan result (debugReadInstanceOffsets)
         }
         if (i < visibleCount) {
