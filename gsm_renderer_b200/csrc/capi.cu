@@ -39,6 +39,7 @@ struct Resources {
     bool stereo = false;
     uint32_t maxGaussians = 0, maxInstances = 0, maxTiles = 0;
     uint32_t depthTilesCap = 0, tileTilesCap = 0;
+    uint32_t frameGaussians = 0;  // gaussianCount of the frame being encoded (host-known bound on V; picks the sort tile size)
     // per Gaussian
     void* renderData = nullptr;
     int32_t* bounds = nullptr;
@@ -115,8 +116,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t tileIdBytes = tile16 ? 2 : 4;
     res.stereo = stereo;
     res.maxGaussians = G; res.maxInstances = I; res.maxTiles = T;
-    res.depthTilesCap = (G + sortTileSize(32) - 1) / sortTileSize(32);
-    res.tileTilesCap = (I + sortTileSize(tile16 ? 16 : 32) - 1) / sortTileSize(tile16 ? 16 : 32);
+    res.depthTilesCap = (G + sortTileSize(32, false) - 1) / sortTileSize(32, false);  // sized for the smaller tile
+    res.tileTilesCap = (I + sortTileSize(tile16 ? 16 : 32, false) - 1) / sortTileSize(tile16 ? 16 : 32, false);
 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = alignUp(off + bytes, 256); return o; };
@@ -183,6 +184,8 @@ void freeResources(Resources& res) {
     res = Resources();
 }
 
+bool largeSort(uint32_t frameGaussians) { return frameGaussians >= 3000000u; }  // see sort.cu: sortTileSize
+
 int tileSortPasses(uint32_t tileCount) {  // TileSortEncoder.swift:61-62
     uint32_t v = tileCount > 0 ? (tileCount - 1 > 1 ? tileCount - 1 : 1) : 1;
     int bits = 0;
@@ -196,7 +199,7 @@ SortReset tileSortReset(const gsm_renderer* r, const Resources& res, uint32_t ti
     SortReset reset;
     reset.status = res.tileSortStatus; reset.statusStride = res.tileTilesCap * 256u;
     reset.gstatus = res.tileSortGStatus; reset.gstatusStride = ((res.tileTilesCap + 15u) / 16u) * 256u;
-    reset.passes = (uint32_t)tileSortPasses(tilesX * tilesY); reset.tileSize = sortTileSize(tile16 ? 16 : 32);
+    reset.passes = (uint32_t)tileSortPasses(tilesX * tilesY); reset.tileSize = sortTileSize(tile16 ? 16 : 32, largeSort(res.frameGaussians));
     return reset;
 }
 
@@ -218,6 +221,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     dp.v0 = (uint32_t*)res.primIdx[0]; dp.v1 = (uint32_t*)res.primIdx[1];
     dp.countPtr = &res.header->visibleCount; dp.countCap = res.maxGaussians;
     dp.hist = &res.fs->hist[0][0]; dp.status = res.depthSortStatus; dp.gstatus = res.depthSortGStatus; dp.tickets = &res.fs->ticketSort[0];
+    dp.largeTiles = largeSort(res.frameGaussians);
     dp.tilesCap = res.depthTilesCap; dp.keyBits = 32; dp.numPasses = key16 ? 2 : 4; dp.numSMs = r->numSMs;
     dp.histogramReady = depthHistReady;  // compact_visible_kernel filled hist[0..3] and reset the look-back words
     GSM_CUDA(launchSort(s, dp), "depth sort");
@@ -236,6 +240,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     tp.v0 = (uint32_t*)res.instIdx[0]; tp.v1 = (uint32_t*)res.instIdx[1];
     tp.countPtr = &res.header->totalInstances; tp.countCap = res.maxInstances;
     tp.hist = &res.fs->hist[4][0]; tp.status = res.tileSortStatus; tp.gstatus = res.tileSortGStatus; tp.tickets = &res.fs->ticketSort[4];
+    tp.largeTiles = largeSort(res.frameGaussians);
     tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tilePasses;
     tp.numSMs = r->numSMs; tp.histogramReady = true;  // create_instances_kernel filled hist[4..7], the scan kernel reset the words
     GSM_CUDA(launchSort(s, tp), "tile sort");
@@ -357,6 +362,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     st = ensureResources(r, r->mono, false);
     if (st != GSM_OK) return st;  // the reference returns silently here (DFR.swift:189); we report
     Resources& res = r->mono;
+    res.frameGaussians = gaussianCount;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
     r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = false;
@@ -371,7 +377,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
-    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
@@ -409,6 +415,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     st = ensureResources(r, r->stereoRes, true);
     if (st != GSM_OK) return st;
     Resources& res = r->stereoRes;
+    res.frameGaussians = gaussianCount;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
     r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = true;
@@ -432,7 +439,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
-    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
@@ -504,6 +511,7 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     st = ensureResources(r, r->mono, false);
     if (st != GSM_OK) return st;
     Resources& res = r->mono;
+    res.frameGaussians = gidCount;
     cudaStream_t s = (cudaStream_t)stream;
     r->lastStereo = false;
     GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
@@ -513,7 +521,7 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
-    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
@@ -538,6 +546,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     gsm_status st = ensureResources(r, r->mono, false);
     if (st != GSM_OK) return st;
     Resources& res = r->mono;
+    res.frameGaussians = recordCount;
     cudaStream_t s = (cudaStream_t)stream;
     r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = false;
     GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
@@ -545,7 +554,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
-    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u; po.depthKey16 = 0; po.gidFirst = 0;
     GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po), "ingest records");
@@ -691,7 +700,8 @@ gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* paylo
     if (count == 0) return GSM_OK;
     DeviceGuard guard(r->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t tile = sortTileSize(keyBits);
+    const bool large = keyBits == 32 && count >= 3000000u;
+    const uint32_t tile = sortTileSize(keyBits, large);
     const uint32_t tiles = (count + tile - 1) / tile;
     const size_t keyBytes = (size_t)count * (keyBits / 8);
     // scratch: [count u32][hist 4*256][tickets 4][status passes*tiles*256][k1][v1]
@@ -710,7 +720,7 @@ gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* paylo
         p.k0 = keys; p.k1 = scratch + oK1; p.v0 = (uint32_t*)payload; p.v1 = (uint32_t*)(scratch + oV1);
         p.countPtr = (const uint32_t*)scratch; p.countCap = count;
         p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.gstatus = (uint32_t*)(scratch + oGStatus); p.tickets = (uint32_t*)(scratch + oTickets);
-        p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = r->numSMs; p.histogramReady = false;
+        p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = r->numSMs; p.histogramReady = false; p.largeTiles = large;
         if ((e = launchSort(s, p)) != cudaSuccess) break;
         e = cudaStreamSynchronize(s);
     } while (false);

@@ -21,6 +21,7 @@ struct ProjectOut {
     // sort's look-back words (bounded by N, known on the host)
     uint32_t* depthHist;          // [4][256], zeroed with the frame state
     uint32_t depthPasses;
+    uint32_t depthTileSize;       // keys per onesweep tile of the depth sort (sortTileSize(32))
     uint32_t* depthStatus; uint32_t depthStatusStride;   // words per pass (tilesCap*256)
     uint32_t* depthGStatus; uint32_t depthGStatusStride;
 };
@@ -47,9 +48,10 @@ struct SortPlan {
     int keyBits;         // 16 or 32
     int numPasses;
     int numSMs;
+    bool largeTiles;     // 32-bit keys only: 4096-key tiles (large inputs) instead of 2048
     bool histogramReady; // hist filled and status/gstatus zeroed by earlier kernels of the frame (fused); else a histogram kernel runs
 };
-uint32_t sortTileSize(int keyBits);
+uint32_t sortTileSize(int keyBits, bool large);
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p);
 
 // apply depth order + exclusive scan (scan.cu)

@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
     const uint32_t numTiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
     for (int i = tid; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
     {   // reset the depth sort's look-back words for this frame: ceil(N / sortTile) tiles per pass bound V <= N
-        const uint32_t words = ((N + 2047u) / 2048u) * 256u, gwords = ((words / 256u + 15u) / 16u) * 256u;
+        const uint32_t words = ((N + o.depthTileSize - 1u) / o.depthTileSize) * 256u, gwords = ((words / 256u + 15u) / 16u) * 256u;
         for (uint32_t p = 0; p < o.depthPasses; ++p) {
             for (uint32_t i = blockIdx.x * 256u + tid; i < words; i += gridDim.x * 256u) o.depthStatus[(size_t)p * o.depthStatusStride + i] = 0u;
             for (uint32_t i = blockIdx.x * 256u + tid; i < gwords; i += gridDim.x * 256u) o.depthGStatus[(size_t)p * o.depthGStatusStride + i] = 0u;

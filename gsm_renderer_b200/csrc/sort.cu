@@ -23,16 +23,15 @@ constexpr uint32_t kStatusInclusive = 0x80000000u;
 constexpr int kLookBatch = 8;
 constexpr uint32_t kLookGroup = 16;
 
-template <typename KeyT> struct SortCfg;
-template <> struct SortCfg<uint32_t> { static constexpr int ITEMS = 8; };   // 2048 keys / tile
-template <> struct SortCfg<uint16_t> { static constexpr int ITEMS = 16; };  // 4096 keys / tile
-
-uint32_t sortTileSize(int keyBits) {
-    return keyBits == 16 ? kSortThreads * SortCfg<uint16_t>::ITEMS : kSortThreads * SortCfg<uint32_t>::ITEMS;
+// Keys per thread: 8 (2048-key tiles) keeps enough tiles in flight when the whole input is a few hundred
+// thousand keys and the pass is latency-bound; 16 (4096-key tiles) halves the per-tile overhead (look-back, scans)
+// and lengthens the scatter runs once the input is large (profiles/r1_sort_sweep_*: +24 % at 48 M pairs, -35 % at 709 k).
+uint32_t sortTileSize(int keyBits, bool large) {
+    return kSortThreads * ((keyBits == 16 || large) ? 16u : 8u);
 }
 
 // ---- all digit histograms in one read of the keys
-template <typename KeyT, int NPASS>
+template <typename KeyT, int NPASS, int ITEMS>
 __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ countPtr,
                                                               uint32_t countCap, uint32_t* __restrict__ hist,
                                                               uint32_t* __restrict__ status, uint32_t* __restrict__ gstatus,
@@ -42,7 +41,7 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
     __syncthreads();
     const uint32_t count = min(*countPtr, countCap);
     {   // reset the look-back words this frame's passes will use (sized by the device-side count, not the capacity)
-        constexpr uint32_t TILE = kSortThreads * SortCfg<KeyT>::ITEMS;
+        constexpr uint32_t TILE = kSortThreads * ITEMS;
         const uint32_t words = ((count + TILE - 1) / TILE) * 256u;
         const uint32_t gwords = ((words / 256u + kLookGroup - 1) / kLookGroup) * 256u;
         const uint32_t groupsCap = (tilesCap + kLookGroup - 1) / kLookGroup;
@@ -66,13 +65,12 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
 }
 
 // ---- one digit pass
-template <typename KeyT>
+template <typename KeyT, int ITEMS>
 __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                                                                      KeyT* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
                                                                      const uint32_t* __restrict__ countPtr, uint32_t countCap,
                                                                      const uint32_t* __restrict__ digitHist, uint32_t* status,
                                                                      uint32_t* gstatus, uint32_t* ticket, int shift) {
-    constexpr int ITEMS = SortCfg<KeyT>::ITEMS;
     constexpr int TILE = kSortThreads * ITEMS;
     constexpr KeyT SENTINEL = (KeyT)~(KeyT)0;
 
@@ -259,25 +257,25 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
     }
 }
 
-template <typename KeyT>
+template <typename KeyT, int ITEMS>
 static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
     if (p.numPasses <= 0) return cudaSuccess;
     const int gridHist = p.numSMs * 4;
     KeyT* k0 = (KeyT*)p.k0;
     KeyT* k1 = (KeyT*)p.k1;
     if (!p.histogramReady) switch (p.numPasses) {
-        case 1: radix_histogram_kernel<KeyT, 1><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
-        case 2: radix_histogram_kernel<KeyT, 2><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
-        case 3: radix_histogram_kernel<KeyT, 3><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
-        default: radix_histogram_kernel<KeyT, 4><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 1: radix_histogram_kernel<KeyT, 1, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 2: radix_histogram_kernel<KeyT, 2, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 3: radix_histogram_kernel<KeyT, 3, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        default: radix_histogram_kernel<KeyT, 4, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
     }
     int blocksPerSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, onesweep_pass_kernel<KeyT>, kSortThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, onesweep_pass_kernel<KeyT, ITEMS>, kSortThreads, 0);
     if (blocksPerSM < 1) blocksPerSM = 1;
     const int grid = p.numSMs * blocksPerSM;  // every CTA is resident: the look-back cannot starve
     for (int pass = 0; pass < p.numPasses; ++pass) {
         const bool even = (pass & 1) == 0;
-        onesweep_pass_kernel<KeyT><<<grid, kSortThreads, 0, s>>>(
+        onesweep_pass_kernel<KeyT, ITEMS><<<grid, kSortThreads, 0, s>>>(
             even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
             p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u,
             p.gstatus + (size_t)pass * ((p.tilesCap + kLookGroup - 1) / kLookGroup) * 256u, p.tickets + pass, 8 * pass);
@@ -293,7 +291,8 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
 }
 
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p) {
-    return p.keyBits == 16 ? runSort<uint16_t>(s, p) : runSort<uint32_t>(s, p);
+    if (p.keyBits == 16) return runSort<uint16_t, 16>(s, p);
+    return p.largeTiles ? runSort<uint32_t, 16>(s, p) : runSort<uint32_t, 8>(s, p);
 }
 
 }  // namespace gsm
