@@ -42,15 +42,45 @@ static inline gsmo_half gsmo_hadd(gsmo_half a, gsmo_half b) { return gsmo_f2h(gs
 static inline gsmo_half gsmo_hsub(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) - gsmo_h2f(b)); }
 static inline gsmo_half gsmo_hmul(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) * gsmo_h2f(b)); }
 static inline gsmo_half gsmo_hdiv(gsmo_half a, gsmo_half b) { return gsmo_f2h(gsmo_h2f(a) / gsmo_h2f(b)); }
-/* fused multiply-add in binary16: a*b + c rounded ONCE. The exact value spans at most 2^31 .. 2^-48, i.e. < 64
- * significant bits, so x87 long double (64-bit significand) holds it exactly and the conversion rounds once
- * (device: HFMA2). Used where the Metal compiler contracts a*b + c under -ffast-math. */
-static inline gsmo_half gsmo_hfma(gsmo_half a, gsmo_half b, gsmo_half c) {
-    long double r = (long double)gsmo_h2f(a) * (long double)gsmo_h2f(b) + (long double)gsmo_h2f(c);
-    _Float16 v = (_Float16)r;
+/* One correctly rounded (nearest-even) conversion of a finite-or-not double to binary16, done by hand:
+ * going through float would round twice (53 -> 24 -> 11 bits), which is not innocuous for an arbitrary double. */
+static inline gsmo_half gsmo_d2h(double v) {
+    if (v != v) return 0x7FFFu;
+    const gsmo_half sign = (v < 0.0 || (v == 0.0 && 1.0 / v < 0.0)) ? 0x8000u : 0u;
+    double x = v < 0.0 ? -v : v;
+    if (x >= 65520.0) return (gsmo_half)(sign | 0x7C00u);      /* halfway to 2^16 and above: +-inf */
+    if (x < 0x1p-25) return sign;                               /* below half of the smallest subnormal */
+    int e;
+    (void)frexp(x, &e);                                        /* x = m * 2^e, m in [0.5, 1) */
+    int qe = (e - 1) - 10;                                      /* exponent of one ulp in x's binade */
+    if (qe < -24) qe = -24;                                     /* subnormal range: fixed quantum 2^-24 */
+    const double r = rint(ldexp(x, -qe));                       /* exact scaling; rint = nearest-even */
+    const float f = (float)ldexp(r, qe);                        /* exactly representable in binary16 */
+    _Float16 h16 = (_Float16)f;
     gsmo_half h;
-    memcpy(&h, &v, 2);
-    return h;
+    memcpy(&h, &h16, 2);
+    return (gsmo_half)(h | sign);
+}
+
+/* fused multiply-add in binary16: a*b + c rounded ONCE (device: HFMA2). Used where the Metal compiler contracts
+ * a*b + c under -ffast-math. a*b is exact in double (22 significant bits); the sum is exact in double unless the
+ * operands are more than 53 bits apart, which an error-free TwoSum detects -- only then the x87 long double
+ * (64-bit significand >= the 56-bit span of a half product plus a half addend) path is taken. */
+static inline gsmo_half gsmo_hfma(gsmo_half a, gsmo_half b, gsmo_half c) {
+    const double ab = (double)gsmo_h2f(a) * (double)gsmo_h2f(b);
+    const double cd = (double)gsmo_h2f(c);
+    const double s = ab + cd;
+    if (s - s == 0.0) {                                         /* finite */
+        const double bb = s - ab;
+        const double err = (ab - (s - bb)) + (cd - bb);
+        if (err == 0.0) return gsmo_d2h(s);
+        long double r = (long double)ab + (long double)cd;      /* exact */
+        _Float16 v = (_Float16)r;
+        gsmo_half h;
+        memcpy(&h, &v, 2);
+        return h;
+    }
+    return gsmo_f2h((float)s);                                  /* inf / NaN propagate */
 }
 static inline int gsmo_hisnan(gsmo_half a) { return (a & 0x7FFFu) > 0x7C00u; }
 /* min/max: a NaN operand loses (IEEE-754-2008 minNum/maxNum, MSL fmin/fmax); -0 orders below +0
