@@ -45,21 +45,22 @@ static inline gsmo_half gsmo_hdiv(gsmo_half a, gsmo_half b) { return gsmo_f2h(gs
 /* One correctly rounded (nearest-even) conversion of a finite-or-not double to binary16, done by hand:
  * going through float would round twice (53 -> 24 -> 11 bits), which is not innocuous for an arbitrary double. */
 static inline gsmo_half gsmo_d2h(double v) {
-    if (v != v) return 0x7FFFu;
-    const gsmo_half sign = (v < 0.0 || (v == 0.0 && 1.0 / v < 0.0)) ? 0x8000u : 0u;
-    double x = v < 0.0 ? -v : v;
-    if (x >= 65520.0) return (gsmo_half)(sign | 0x7C00u);      /* halfway to 2^16 and above: +-inf */
-    if (x < 0x1p-25) return sign;                               /* below half of the smallest subnormal */
-    int e;
-    (void)frexp(x, &e);                                        /* x = m * 2^e, m in [0.5, 1) */
-    int qe = (e - 1) - 10;                                      /* exponent of one ulp in x's binade */
-    if (qe < -24) qe = -24;                                     /* subnormal range: fixed quantum 2^-24 */
-    const double r = rint(ldexp(x, -qe));                       /* exact scaling; rint = nearest-even */
-    const float f = (float)ldexp(r, qe);                        /* exactly representable in binary16 */
-    _Float16 h16 = (_Float16)f;
-    gsmo_half h;
-    memcpy(&h, &h16, 2);
-    return (gsmo_half)(h | sign);
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    const gsmo_half sign = (gsmo_half)((u >> 48) & 0x8000u);
+    u &= 0x7FFFFFFFFFFFFFFFull;
+    if (u > 0x7FF0000000000000ull) return 0x7FFFu;                       /* NaN */
+    if (u >= 0x40EFFE0000000000ull) return (gsmo_half)(sign | 0x7C00u);  /* |v| >= 65520: +-inf */
+    const int E = (int)(u >> 52) - 1023;
+    if (E < -25) return sign;                                            /* |v| < 2^-25: +-0 */
+    const uint64_t m = (u & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+    const int shift = (E >= -14) ? 42 : 42 + (-14 - E);                  /* subnormal halfs keep fewer bits */
+    uint64_t q = m >> shift;
+    const uint64_t rem = m & ((1ull << shift) - 1ull), half = 1ull << (shift - 1);
+    if (rem > half || (rem == half && (q & 1ull))) q++;                  /* nearest, ties to even */
+    /* normal: biased exponent (E+15) with the implicit bit folded in, so a mantissa carry bumps the exponent */
+    const uint32_t h = (E >= -14) ? (uint32_t)(((uint32_t)(E + 14) << 10) + (uint32_t)q) : (uint32_t)q;
+    return (gsmo_half)(sign | (gsmo_half)h);
 }
 
 /* fused multiply-add in binary16: a*b + c rounded ONCE (device: HFMA2). Used where the Metal compiler contracts
@@ -67,8 +68,20 @@ static inline gsmo_half gsmo_d2h(double v) {
  * operands are more than 53 bits apart, which an error-free TwoSum detects -- only then the x87 long double
  * (64-bit significand >= the 56-bit span of a half product plus a half addend) path is taken. */
 static inline gsmo_half gsmo_hfma(gsmo_half a, gsmo_half b, gsmo_half c) {
-    const double ab = (double)gsmo_h2f(a) * (double)gsmo_h2f(b);
-    const double cd = (double)gsmo_h2f(c);
+    const float fa = gsmo_h2f(a), fb = gsmo_h2f(b), fc = gsmo_h2f(c);
+    {
+        /* Fast path. a*b is exact in fp32 (22 bits). t = RN32(a*b + c) then RN16(t) equals RN16(a*b + c) unless t
+         * sits exactly on a midpoint between two halfs: every such midpoint is an fp32 number and RN32 is monotonic,
+         * so t and the exact sum lie on the same side of every midpoint that t is not equal to. For a normal half
+         * result (|t| >= 2^-14) the midpoints are the fp32 values whose low 13 mantissa bits are 0x1000. */
+        const float t = fa * fb + fc;
+        uint32_t u;
+        memcpy(&u, &t, 4);
+        const uint32_t mag = u & 0x7FFFFFFFu;
+        if (mag >= 0x38800000u && mag < 0x7F800000u && (u & 0x1FFFu) != 0x1000u) return gsmo_f2h(t);
+    }
+    const double ab = (double)fa * (double)fb;
+    const double cd = (double)fc;
     const double s = ab + cd;
     if (s - s == 0.0) {                                         /* finite */
         const double bb = s - ab;
