@@ -47,6 +47,9 @@ EXPORTS = {
                                          C.c_uint32, C.c_uint32, C.c_uint32]),
     "gsm_render_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                   C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gsm_render_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                        C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gsm_render_host_wait": (C.c_int, [C.c_void_p]),
     "gsm_last_gpu_time_ms": (C.c_double, [C.c_void_p]),
     "gsm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gsm_get_stage_times_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -459,9 +459,9 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     return GSM_OK;
 }
 
-gsm_status gsm_render_host(gsm_renderer* r, const void* hostGaussians, const void* hostHarmonics, uint32_t gaussianCount,
-                           uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height, void* hostColor,
-                           void* hostDepth) {
+gsm_status gsm_render_host_async(gsm_renderer* r, const void* hostGaussians, const void* hostHarmonics, uint32_t gaussianCount,
+                                 uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height, void* hostColor,
+                                 void* hostDepth) {
     if (!r || !camera || !hostGaussians || !hostHarmonics || !hostColor) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
     if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;
     if (width == 0 || height == 0 || width > r->cfg.maxWidth || height > r->cfg.maxHeight)
@@ -494,8 +494,24 @@ gsm_status gsm_render_host(gsm_renderer* r, const void* hostGaussians, const voi
     if (st != GSM_OK) return st;
     GSM_CUDA(cudaMemcpyAsync(hostColor, r->stColor, cBytes, cudaMemcpyDeviceToHost, s), "D2H colour");
     if (hostDepth) GSM_CUDA(cudaMemcpyAsync(hostDepth, r->stDepth, dBytes, cudaMemcpyDeviceToHost, s), "D2H depth");
-    GSM_CUDA(cudaStreamSynchronize(s), "stream sync");
     return GSM_OK;
+}
+
+gsm_status gsm_render_host_wait(gsm_renderer* r) {
+    if (!r) return fail(GSM_ERR_INVALID_ARGUMENT, "null renderer");
+    if (!r->hostStream) return GSM_OK;
+    DeviceGuard guard(r->device);
+    GSM_CUDA(cudaStreamSynchronize(r->hostStream), "stream sync");
+    return GSM_OK;
+}
+
+gsm_status gsm_render_host(gsm_renderer* r, const void* hostGaussians, const void* hostHarmonics, uint32_t gaussianCount,
+                           uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height, void* hostColor,
+                           void* hostDepth) {
+    gsm_status st = gsm_render_host_async(r, hostGaussians, hostHarmonics, gaussianCount, shComponents, camera, width, height,
+                                          hostColor, hostDepth);
+    if (st != GSM_OK) return st;
+    return gsm_render_host_wait(r);
 }
 
 gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussians, const void* harmonics, uint32_t gidFirst,

@@ -22,6 +22,9 @@ constexpr uint32_t kStatusAggregate = 0x40000000u;
 constexpr uint32_t kStatusInclusive = 0x80000000u;
 constexpr int kLookBatch = 8;
 constexpr uint32_t kLookGroup = 16;
+constexpr uint32_t kFlatMaxTiles = 1024;       // <= 15 + 64 predecessor words per digit in the flat scheme
+constexpr uint32_t kGroupShift = 26;           // flat scheme group word: arrivals << 26 | sum of counts (<= 16 * 4096)
+constexpr uint32_t kGroupArrival = 1u << kGroupShift;
 
 // Keys per thread: 8 (2048-key tiles) keeps enough tiles in flight when the whole input is a few hundred
 // thousand keys and the pass is latency-bound; 16 (4096-key tiles) halves the per-tile overhead (look-back, scans)
@@ -86,22 +89,21 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t count = min(*countPtr, countCap);
     const uint32_t numTiles = (count + TILE - 1) / TILE;
+    // the first ticket's round trip overlaps the prologue
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
     {
         uint32_t total;
         uint32_t e = block_exclusive_scan_256(digitHist[tid], s_scan, total);
         s_histPrefix[tid] = e;
     }
+    __syncthreads();
 
     while (true) {
-        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= numTiles) break;
         const uint32_t base = tile * TILE;
         const uint32_t tileValid = min((uint32_t)TILE, count - base);
-
-        for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
-        __syncthreads();
 
         // warp-striped load: element (warp, item, lane) has index base + warp*ITEMS*32 + item*32 + lane
         KeyT key[ITEMS];
@@ -154,17 +156,52 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
         const uint32_t sentinelDigit = ((uint32_t)SENTINEL >> shift) & 0xFFu;
         uint32_t validCount = binCount - ((tid == sentinelDigit) ? (TILE - tileValid) : 0u);
 
-        // decoupled look-back, one thread per digit
         uint32_t* myStatus = status + (size_t)tile * 256u + tid;
         uint32_t exclusive = 0;
-        // Two-level decoupled look-back, one thread per digit. Level 1 walks the tiles of the own group of
-        // kLookGroup tiles; level 2 walks per-GROUP words published by each group's last tile. With every tile
-        // resident at once nothing is inclusive yet, so a flat walk costs one step per predecessor batch
-        // (ncu r1_v3: tile 346 needed 43 dependent L2 round trips, ~17 of the pass's 21 us); two levels bound it
-        // by kLookGroup/kLookBatch + groups/kLookBatch steps and make the status traffic linear, not quadratic.
         const uint32_t group = tile / kLookGroup;
-        const bool groupLeader = (tile % kLookGroup) == kLookGroup - 1;
         uint32_t* myGroup = gstatus + (size_t)group * 256u + tid;
+        if (numTiles <= kFlatMaxTiles) {
+            // Few tiles (every frame-sized sort): all of them are in flight at once, nothing is "inclusive" yet, and a
+            // chained look-back is a string of dependent L2 round trips (ncu r1_v3: ~17 of a 21 us pass). Instead each
+            // tile publishes its counts once -- a plain word per tile and a RED into its group's accumulator, whose
+            // top bits count arrivals -- and then sums every predecessor directly: the <= 15 earlier tiles of its own
+            // group plus every earlier group, all loads independent, re-polled until all have arrived. The chain is
+            // publish -> one round trip. Sums are order-independent, so no contiguity bookkeeping.
+            st_status32(myStatus, kStatusAggregate | validCount);
+            if ((group + 1u) * kLookGroup < numTiles) atomicAdd(myGroup, kGroupArrival | validCount);  // RED: result unused
+            const uint32_t groupStart = group * kLookGroup, nPred = tile - groupStart;
+            bool ok;
+            do {
+                ok = true;
+                exclusive = 0;
+                for (uint32_t b = 0; b < group; b += kLookBatch) {
+                    uint32_t sv[kLookBatch];
+#pragma unroll
+                    for (int k = 0; k < kLookBatch; ++k)
+                        sv[k] = (b + k < group) ? ld_status32(gstatus + (size_t)(b + k) * 256u + tid) : (kGroupArrival * kLookGroup);
+#pragma unroll
+                    for (int k = 0; k < kLookBatch; ++k) {
+                        ok &= (sv[k] >> kGroupShift) == kLookGroup;
+                        exclusive += sv[k] & (kGroupArrival - 1u);
+                    }
+                }
+                for (uint32_t b = 0; b < nPred; b += kLookBatch) {
+                    uint32_t sv[kLookBatch];
+#pragma unroll
+                    for (int k = 0; k < kLookBatch; ++k)
+                        sv[k] = (b + k < nPred) ? ld_status32(status + (size_t)(groupStart + b + k) * 256u + tid) : kStatusAggregate;
+#pragma unroll
+                    for (int k = 0; k < kLookBatch; ++k) {
+                        ok &= (sv[k] & kStatusAggregate) != 0u;
+                        exclusive += sv[k] & kStatusValueMask;
+                    }
+                }
+            } while (!ok);
+        } else {
+        // Many tiles (streaming): two-level decoupled look-back, one thread per digit. Level 1 walks the tiles of the
+        // own group of kLookGroup tiles; level 2 walks per-GROUP words published by each group's last tile. In the
+        // steady state the predecessor is already inclusive and the walk is one load.
+        const bool groupLeader = (tile % kLookGroup) == kLookGroup - 1;
         if (tile == 0) {
             st_status32(myStatus, kStatusInclusive | validCount);
             if (groupLeader) st_status32(myGroup, kStatusInclusive | validCount);
@@ -224,6 +261,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
             st_status32(myStatus, kStatusInclusive | (exclusive + validCount));
             if (groupLeader) st_status32(myGroup, kStatusInclusive | (exclusive + validCount));
         }
+        }
         uint32_t total;
         uint32_t binExcl = block_exclusive_scan_256(binCount, s_scan, total);
         s_binExcl[tid] = binExcl;
@@ -253,6 +291,9 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
                 valsOut[dst] = s_vals[j];
             }
         }
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
         __syncthreads();
     }
 }

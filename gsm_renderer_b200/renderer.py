@@ -224,6 +224,20 @@ class DepthFirstRenderer:
                                          N.ptr(hostColor), N.ptr(hostDepth)))
         self._stereo_last = False
 
+    def renderHostAsync(self, hostGaussians, hostHarmonics, gaussianCount, shComponents, camera: CameraParams,
+                        width, height, hostColor, hostDepth=None) -> None:
+        """gsm_render_host_async: enqueue H2D + frame + D2H and return (the reference's render() only encodes,
+        DFR.swift:196-330). The host buffers must stay alive until waitHost()."""
+        cam = camera.to_native()
+        _check(self._lib.gsm_render_host_async(self._h, N.ptr(hostGaussians), N.ptr(hostHarmonics), int(gaussianCount),
+                                               int(shComponents), C.byref(cam), int(width), int(height),
+                                               N.ptr(hostColor), N.ptr(hostDepth)))
+        self._stereo_last = False
+
+    def waitHost(self) -> None:
+        """gsm_render_host_wait: block until the frame enqueued by renderHostAsync is in the host buffers."""
+        _check(self._lib.gsm_render_host_wait(self._h))
+
     # -- profiling
     def setProfiling(self, enabled: bool) -> None:
         _check(self._lib.gsm_set_profiling(self._h, int(enabled)))

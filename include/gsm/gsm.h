@@ -107,6 +107,16 @@ gsm_status gsm_render_host(gsm_renderer* r, const void* hostGaussians, const voi
                            uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* camera,
                            uint32_t width, uint32_t height, void* hostColor, void* hostDepth);
 
+/* The reference's render() only ENCODES into the caller's MTLCommandBuffer (DFR.swift:196-330); the caller commits
+ * and waits, so several frames can be in flight. gsm_render_host_async is that shape for host buffers: it enqueues
+ * H2D + frame + D2H on the renderer's own stream and returns; gsm_render_host_wait blocks until the images are in
+ * hostColor / hostDepth. The host buffers must stay valid (and should be pinned) until the wait. One frame in
+ * flight per renderer: use two renderers to overlap a frame's upload with the previous frame's render + download. */
+gsm_status gsm_render_host_async(gsm_renderer* r, const void* hostGaussians, const void* hostHarmonics,
+                                 uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* camera,
+                                 uint32_t width, uint32_t height, void* hostColor, void* hostDepth);
+gsm_status gsm_render_host_wait(gsm_renderer* r);
+
 /* lastGPUTime (GRP.swift:245; declared but never assigned by the reference, DFR.swift:43). Here: device
  * time of the last frame in ms when profiling is on, else a negative number. */
 double gsm_last_gpu_time_ms(gsm_renderer* r);

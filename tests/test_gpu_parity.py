@@ -202,8 +202,14 @@ def test_render_host_matches_device_path(oracle, pu):
     hc = np.zeros((H, W, 4), np.uint16)
     hd = np.zeros((H, W), np.uint16)
     r.renderHost(g, h, cl.count, 16, cam, W, H, hc, hd)
-    r.close()
     assert np.array_equal(hc, c) and np.array_equal(hd, d)
+    # encode now, wait later (two frames queued back to back on the renderer's stream)
+    hc2 = np.zeros((H, W, 4), np.uint16)
+    hd2 = np.zeros((H, W), np.uint16)
+    r.renderHostAsync(g, h, cl.count, 16, cam, W, H, hc2, hd2)
+    r.waitHost()
+    r.close()
+    assert np.array_equal(hc2, c) and np.array_equal(hd2, d)
 
 
 # ---------------------------------------------------------------- stereo
