@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
     const unsigned lx = tid & 7u, ly = tid >> 3;
     const uint32_t tileX = blockIdx.x % tilesX, tileY = tileRowFirst + blockIdx.x / tilesX;
     const uint32_t tile = tileY * tilesX + tileX;
+    pdlLaunchDependents();
+    pdlWait();
     const uint32_t start = lowerBounds[tile];
     const uint32_t end = lowerBounds[tile + 1];
     const uint32_t count = end > start ? end - start : 0u;
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
     const unsigned tid = threadIdx.x;
     const uint32_t tileX = blockIdx.x % tilesX, tileY = blockIdx.x / tilesX;
     const uint32_t tile = tileY * tilesX + tileX;
+    pdlLaunchDependents();
+    pdlWait();
     const uint32_t start = lowerBounds[tile];
     const uint32_t end = lowerBounds[tile + 1];
     const uint32_t count = end > start ? end - start : 0u;
@@ -320,17 +324,15 @@ cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const B
                             uint32_t tileRowCount, __half* color, __half* depth, TileOut tout) {
     (void)tilesY;
     if (tileRowCount == 0) return cudaSuccess;
-    blend_mono_kernel<<<tilesX * tileRowCount, kBlendThreads, 0, s>>>(lowerBounds, splats, instanceIdx, width, height, tilesX,
-                                                                       tileRowFirst, color, depth, tout);
-    return cudaGetLastError();
+    return launchChained(blend_mono_kernel, tilesX * tileRowCount, kBlendThreads, s, lowerBounds, splats, instanceIdx, width, height,
+                         tilesX, tileRowFirst, color, depth, tout);
 }
 
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
                               __half* dstSideBySide, int eyeMask, int flipY, TileOut tout) {
-    blend_stereo_kernel<<<tilesX * tilesY, kBlendThreads, 0, s>>>(lowerBounds, splats, instanceIdx, width, height, tilesX,
-                                                                   dstSideBySide, flipY, eyeMask, tout);
-    return cudaGetLastError();
+    return launchChained(blend_stereo_kernel, tilesX * tilesY, kBlendThreads, s, lowerBounds, splats, instanceIdx, width, height,
+                         tilesX, dstSideBySide, flipY, eyeMask, tout);
 }
 
 }  // namespace gsm

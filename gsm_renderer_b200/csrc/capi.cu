@@ -6,6 +6,7 @@
 #include <new>
 #include <string>
 
+#include <cstdlib>
 #include "gsm_common.cuh"
 #include "gsm_kernels.h"
 
@@ -91,6 +92,13 @@ struct gsm_renderer {
     uint32_t lastTilesX = 0, lastTilesY = 0;
     bool lastStereo = false;
 };
+
+namespace gsm {
+bool pdlEnabled() {
+    static const bool on = [] { const char* e = getenv("GSM_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+}  // namespace gsm
 
 namespace {
 

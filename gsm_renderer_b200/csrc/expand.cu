@@ -23,8 +23,10 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
                                                                uint32_t tilePasses) {
     __shared__ WarpTileWork s_work[8];
     __shared__ uint32_t s_hist[4][256];  // digit histograms of the emitted tile ids (the tile sort's histogram pass, fused)
+    pdlLaunchDependents();
     for (int i = threadIdx.x; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
     __syncthreads();
+    pdlWait();
     __shared__ uint32_t s_base[8][32];
     __shared__ int32_t s_idx[8][32];
     __shared__ uint32_t s_scan[9];
@@ -96,7 +98,7 @@ cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, co
     uint32_t grid = (capVisible + 255u) / 256u;
     if (grid > (uint32_t)numSMs * 6u) grid = (uint32_t)numSMs * 6u;  // persistent: few CTAs flush the fused histograms
     if (grid == 0) grid = 1;
-#define GSM_LAUNCH(T, ST) create_instances_kernel<T, ST><<<grid, 256, 0, s>>>(sortedIdx, nTouched, offsets, scanStatus, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
+#define GSM_LAUNCH(T, ST) launchChained(create_instances_kernel<T, ST>, grid, 256, s, sortedIdx, nTouched, offsets, scanStatus, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
     if (tileId16) { if (stereo) GSM_LAUNCH(uint16_t, true); else GSM_LAUNCH(uint16_t, false); }
     else { if (stereo) GSM_LAUNCH(uint32_t, true); else GSM_LAUNCH(uint32_t, false); }
 #undef GSM_LAUNCH

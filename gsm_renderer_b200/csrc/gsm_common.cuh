@@ -10,6 +10,33 @@
 
 namespace gsm {
 
+// ---- programmatic dependent launch: the frame is a chain of ~12 short kernels, each a few microseconds of fixed
+// latency (launch, CTA ramp, first round trips). Every kernel of the chain is launched with the
+// programmatic-stream-serialization attribute, lets its successor start early (pdlLaunchDependents) and
+// touches global memory only after pdlWait(), which returns once the whole predecessor grid has completed and
+// its writes are visible. What runs before the wait (shared-memory clears, ticket atomics on words zeroed by the
+// frame's memset) overlaps the predecessor's tail. Every CTA must execute pdlWait() so that "this grid completed"
+// implies "its predecessor completed" down the chain.
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdlEnabled();  // capi.cu: GSM_PDL=0 in the environment turns the attribute off (A/B measurement)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launchChained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdlEnabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kTile = 16;               // DFR.swift:8-9
 constexpr float kAlphaThreshold = 0.005f;   // GlobalRenderer.swift:66
 constexpr float kTotalInkThreshold = 2.0f;  // GlobalRenderer.swift:67

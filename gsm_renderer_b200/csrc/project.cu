@@ -407,6 +407,8 @@ template <bool HALF, int DEG>
 __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const void* __restrict__ gaussians,
                                                                 const void* __restrict__ harmonics,
                                                                 const __grid_constant__ MonoCam cam, ProjectOut o) {
+    pdlLaunchDependents();
+    pdlWait();
     const uint32_t tile = blockIdx.x;
     const uint32_t N = cam.gaussianCount;
     const uint32_t numWarpTiles = (N + 31u) / 32u;
@@ -579,6 +581,8 @@ template <bool HALF, int DEG>
 __global__ void __launch_bounds__(kProjThreads) project_cull_stereo_kernel(const void* __restrict__ gaussians,
                                                                   const void* __restrict__ harmonics,
                                                                   const __grid_constant__ StereoCam cam, ProjectOut o) {
+    pdlLaunchDependents();
+    pdlWait();
     const uint32_t tile = blockIdx.x;
     const uint32_t N = cam.gaussianCount;
     const uint32_t numWarpTiles = (N + 31u) / 32u;
@@ -686,7 +690,9 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
     __shared__ uint32_t s_hist[4][256];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t numTiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
+    pdlLaunchDependents();
     for (int i = tid; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
+    pdlWait();
     {   // reset the depth sort's look-back words for this frame: ceil(N / sortTile) tiles per pass bound V <= N
         const uint32_t words = ((N + o.depthTileSize - 1u) / o.depthTileSize) * 256u, gwords = ((words / 256u + 15u) / 16u) * 256u;
         for (uint32_t p = 0; p < o.depthPasses; ++p) {
@@ -760,13 +766,15 @@ cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o
     if (N == 0) return cudaSuccess;
     uint32_t tiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
     uint32_t grid = tiles < (uint32_t)numSMs * 8u ? tiles : (uint32_t)numSMs * 8u;
-    compact_visible_kernel<<<grid, 256, 0, s>>>(N, o);
+    launchChained(compact_visible_kernel, grid, 256, s, N, o);
     return cudaGetLastError();
 }
 
 // DFS.metal:2184-2203 (+ reset :1372-1385)
 __global__ void __launch_bounds__(256) finalize_header_kernel(const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians,
                                                               uint32_t maxInstances, SortReset reset) {
+    pdlLaunchDependents();
+    pdlWait();
     uint32_t v = fs->visibleCountRaw, i = fs->totalInstancesRaw, overflow = 0;
     if (v > maxGaussians) { v = maxGaussians; overflow = 1u; }
     if (i > maxInstances) { i = maxInstances; overflow = 1u; }
@@ -794,10 +802,10 @@ template <bool HALF>
 static cudaError_t launchMono(int deg, dim3 grid, cudaStream_t s, const void* g, const void* h, const MonoCam& cam,
                               const ProjectOut& o) {
     switch (deg) {
-        case 0: project_cull_mono_kernel<HALF, 0><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
-        case 1: project_cull_mono_kernel<HALF, 1><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
-        case 2: project_cull_mono_kernel<HALF, 2><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
-        default: project_cull_mono_kernel<HALF, 3><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        case 0: launchChained(project_cull_mono_kernel<HALF, 0>, grid, kProjThreads, s, g, h, cam, o); break;
+        case 1: launchChained(project_cull_mono_kernel<HALF, 1>, grid, kProjThreads, s, g, h, cam, o); break;
+        case 2: launchChained(project_cull_mono_kernel<HALF, 2>, grid, kProjThreads, s, g, h, cam, o); break;
+        default: launchChained(project_cull_mono_kernel<HALF, 3>, grid, kProjThreads, s, g, h, cam, o); break;
     }
     return cudaGetLastError();
 }
@@ -805,10 +813,10 @@ template <bool HALF>
 static cudaError_t launchStereo(int deg, dim3 grid, cudaStream_t s, const void* g, const void* h, const StereoCam& cam,
                                 const ProjectOut& o) {
     switch (deg) {
-        case 0: project_cull_stereo_kernel<HALF, 0><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
-        case 1: project_cull_stereo_kernel<HALF, 1><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
-        case 2: project_cull_stereo_kernel<HALF, 2><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
-        default: project_cull_stereo_kernel<HALF, 3><<<grid, kProjThreads, 0, s>>>(g, h, cam, o); break;
+        case 0: launchChained(project_cull_stereo_kernel<HALF, 0>, grid, kProjThreads, s, g, h, cam, o); break;
+        case 1: launchChained(project_cull_stereo_kernel<HALF, 1>, grid, kProjThreads, s, g, h, cam, o); break;
+        case 2: launchChained(project_cull_stereo_kernel<HALF, 2>, grid, kProjThreads, s, g, h, cam, o); break;
+        default: launchChained(project_cull_stereo_kernel<HALF, 3>, grid, kProjThreads, s, g, h, cam, o); break;
     }
     return cudaGetLastError();
 }
@@ -830,7 +838,7 @@ cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, c
 }
 cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians,
                                  uint32_t maxInstances, const SortReset& reset, int numSMs) {
-    finalize_header_kernel<<<numSMs, 256, 0, s>>>(fs, header, maxGaussians, maxInstances, reset);
+    launchChained(finalize_header_kernel, numSMs, 256, s, fs, header, maxGaussians, maxInstances, reset);
     return cudaGetLastError();
 }
 

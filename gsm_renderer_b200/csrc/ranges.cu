@@ -17,6 +17,8 @@ template <typename TileT>
 __global__ void __launch_bounds__(256) tile_lower_bounds_kernel(const TileT* __restrict__ sortedTileIds,
                                                                 const GSMDepthFirstHeader* __restrict__ header,
                                                                 uint32_t tileCount, uint32_t* __restrict__ lowerBounds) {
+    pdlLaunchDependents();
+    pdlWait();
     const uint32_t total = header->totalInstances;
     // boundary i in [0, total]: i == total closes the last run
     for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i <= total; i += gridDim.x * 256u) {
@@ -30,9 +32,9 @@ cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTi
                              uint32_t tileCount, uint32_t* lowerBounds, int numSMs) {
     const int grid = numSMs * 8;
     if (tileId16)
-        tile_lower_bounds_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)sortedTileIds, header, tileCount, lowerBounds);
+        launchChained(tile_lower_bounds_kernel<uint16_t>, grid, 256, s, (const uint16_t*)sortedTileIds, header, tileCount, lowerBounds);
     else
-        tile_lower_bounds_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)sortedTileIds, header, tileCount, lowerBounds);
+        launchChained(tile_lower_bounds_kernel<uint32_t>, grid, 256, s, (const uint32_t*)sortedTileIds, header, tileCount, lowerBounds);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,22 @@
 
 namespace gsm {
 
+// tools/sort_trace.cu builds this file with GSM_SORT_TRACE to record a per-tile timeline (globaltimer ns at each
+// phase boundary, written by thread 0); the product build compiles the hooks out.
+#ifdef GSM_SORT_TRACE
+__device__ unsigned long long* g_sortTrace = nullptr;  // [tile][16]
+__device__ __forceinline__ unsigned long long traceNow() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GSM_TRACE(tile, slot) do { if (threadIdx.x == 0 && g_sortTrace) g_sortTrace[(traceBase + (tile)) * 16 + (slot)] = traceNow(); } while (0)
+#define GSM_TRACE_SET(tile, slot, v) do { if (threadIdx.x == 0 && g_sortTrace) g_sortTrace[(traceBase + (tile)) * 16 + (slot)] = (v); } while (0)
+#else
+#define GSM_TRACE(tile, slot) do { } while (0)
+#define GSM_TRACE_SET(tile, slot, v) do { } while (0)
+#endif
+
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr uint32_t kStatusValueMask = 0x3FFFFFFFu;
@@ -29,8 +45,14 @@ constexpr uint32_t kGroupArrival = 1u << kGroupShift;
 // Keys per thread: 8 (2048-key tiles) keeps enough tiles in flight when the whole input is a few hundred
 // thousand keys and the pass is latency-bound; 16 (4096-key tiles) halves the per-tile overhead (look-back, scans)
 // and lengthens the scatter runs once the input is large (profiles/r1_sort_sweep_*: +24 % at 48 M pairs, -35 % at 709 k).
+#ifndef GSM_SORT_ITEMS_SMALL
+#define GSM_SORT_ITEMS_SMALL 8
+#endif
+#ifndef GSM_SORT_ITEMS_U16
+#define GSM_SORT_ITEMS_U16 16
+#endif
 uint32_t sortTileSize(int keyBits, bool large) {
-    return kSortThreads * ((keyBits == 16 || large) ? 16u : 8u);
+    return kSortThreads * (keyBits == 16 ? (uint32_t)GSM_SORT_ITEMS_U16 : (large ? 16u : (uint32_t)GSM_SORT_ITEMS_SMALL));
 }
 
 // ---- all digit histograms in one read of the keys
@@ -40,8 +62,10 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
                                                               uint32_t* __restrict__ status, uint32_t* __restrict__ gstatus,
                                                               uint32_t tilesCap) {
     __shared__ uint32_t s_hist[NPASS][256];
+    pdlLaunchDependents();
     for (int i = threadIdx.x; i < NPASS * 256; i += 256) (&s_hist[0][0])[i] = 0;
     __syncthreads();
+    pdlWait();
     const uint32_t count = min(*countPtr, countCap);
     {   // reset the look-back words this frame's passes will use (sized by the device-side count, not the capacity)
         constexpr uint32_t TILE = kSortThreads * ITEMS;
@@ -87,23 +111,33 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
     __shared__ uint32_t s_vals[TILE];
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#ifdef GSM_SORT_TRACE
+    const unsigned long long traceT0 = traceNow();
+#endif
+    // Prologue: the ticket's atomic, the count and the digit histogram are three independent round trips; the
+    // histogram's prefix scan is only needed after the look-back, so it runs under the first tile's key loads.
+    pdlLaunchDependents();
+    uint32_t firstTicket = 0;
+    if (tid == 0) firstTicket = atomicAdd(ticket, 1u);  // zeroed by the frame's memset, not by the previous kernel
+    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
+    pdlWait();
+    const uint32_t digitTotal = digitHist[tid];
     const uint32_t count = min(*countPtr, countCap);
     const uint32_t numTiles = (count + TILE - 1) / TILE;
-    // the first ticket's round trip overlaps the prologue
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
-    {
-        uint32_t total;
-        uint32_t e = block_exclusive_scan_256(digitHist[tid], s_scan, total);
-        s_histPrefix[tid] = e;
-    }
+#ifdef GSM_SORT_TRACE
+    const size_t traceBase = (size_t)(shift >> 3) * numTiles;
+#endif
+    if (tid == 0) s_tile = firstTicket;
     __syncthreads();
+    bool firstTile = true;
 
     while (true) {
         const uint32_t tile = s_tile;
         if (tile >= numTiles) break;
         const uint32_t base = tile * TILE;
         const uint32_t tileValid = min((uint32_t)TILE, count - base);
+        GSM_TRACE_SET(tile, 0, traceT0);  // kernel entry of the CTA that took this tile
+        GSM_TRACE(tile, 1);               // prologue done, ticket known
 
         // warp-striped load: element (warp, item, lane) has index base + warp*ITEMS*32 + item*32 + lane
         KeyT key[ITEMS];
@@ -120,6 +154,11 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
         for (int i = 0; i < ITEMS; ++i) {
             uint32_t j = warpBase + i * 32u;
             val[i] = (j < tileValid) ? valsIn[base + j] : 0u;
+        }
+        if (firstTile) {  // uniform; under the loads just issued
+            uint32_t total;
+            s_histPrefix[tid] = block_exclusive_scan_256(digitTotal, s_scan, total);
+            firstTile = false;
         }
         // rank inside the warp, in index order. Peers of a lane = lanes holding the same digit, found with 8
         // ballots (one per digit bit; independent across items, so they pipeline) -- MATCH.ANY made this loop
@@ -141,7 +180,9 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
             pre = __shfl_sync(0xFFFFFFFFu, pre, __ffs(peers) - 1);
             rank[i] = pre + lower;
         }
+        GSM_TRACE(tile, 2);  // thread 0's warp ranked (keys arrived)
         __syncthreads();
+        GSM_TRACE(tile, 3);  // all warps ranked
 
         // thread d: exclusive prefix over warps, tile count of digit d
         uint32_t binCount = 0;
@@ -262,11 +303,13 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
             if (groupLeader) st_status32(myGroup, kStatusInclusive | (exclusive + validCount));
         }
         }
+        GSM_TRACE(tile, 4);  // digit 0's prefix known
         uint32_t total;
         uint32_t binExcl = block_exclusive_scan_256(binCount, s_scan, total);
         s_binExcl[tid] = binExcl;
         s_globalBase[tid] = s_histPrefix[tid] + exclusive - binExcl;
         __syncthreads();
+        GSM_TRACE(tile, 5);  // every digit's prefix known
 
         // scatter keys into tile order
 #pragma unroll
@@ -278,6 +321,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) s_vals[rank[i]] = val[i];
         __syncthreads();
+        GSM_TRACE(tile, 6);  // tile ordered in shared memory
         // valid elements occupy tile positions [0, tileValid) except that sentinel padding sits at the end of
         // the sentinel digit's bin; bins after it (none: the sentinel digit is 0xFF) would shift.
 #pragma unroll
@@ -292,6 +336,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
             }
         }
         __syncthreads();
+        GSM_TRACE(tile, 7);  // stores issued
         if (tid == 0) s_tile = atomicAdd(ticket, 1u);
         for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
         __syncthreads();
@@ -305,10 +350,10 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
     KeyT* k0 = (KeyT*)p.k0;
     KeyT* k1 = (KeyT*)p.k1;
     if (!p.histogramReady) switch (p.numPasses) {
-        case 1: radix_histogram_kernel<KeyT, 1, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
-        case 2: radix_histogram_kernel<KeyT, 2, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
-        case 3: radix_histogram_kernel<KeyT, 3, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
-        default: radix_histogram_kernel<KeyT, 4, ITEMS><<<gridHist, 256, 0, s>>>(k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 1: launchChained(radix_histogram_kernel<KeyT, 1, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 2: launchChained(radix_histogram_kernel<KeyT, 2, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        case 3: launchChained(radix_histogram_kernel<KeyT, 3, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+        default: launchChained(radix_histogram_kernel<KeyT, 4, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
     }
     int blocksPerSM = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, onesweep_pass_kernel<KeyT, ITEMS>, kSortThreads, 0);
@@ -316,10 +361,10 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
     const int grid = p.numSMs * blocksPerSM;  // every CTA is resident: the look-back cannot starve
     for (int pass = 0; pass < p.numPasses; ++pass) {
         const bool even = (pass & 1) == 0;
-        onesweep_pass_kernel<KeyT, ITEMS><<<grid, kSortThreads, 0, s>>>(
-            even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
-            p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u,
-            p.gstatus + (size_t)pass * ((p.tilesCap + kLookGroup - 1) / kLookGroup) * 256u, p.tickets + pass, 8 * pass);
+        launchChained(onesweep_pass_kernel<KeyT, ITEMS>, grid, kSortThreads, s,
+                      even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
+                      p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u,
+                      p.gstatus + (size_t)pass * ((p.tilesCap + kLookGroup - 1) / kLookGroup) * 256u, p.tickets + pass, 8 * pass);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -332,8 +377,8 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
 }
 
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p) {
-    if (p.keyBits == 16) return runSort<uint16_t, 16>(s, p);
-    return p.largeTiles ? runSort<uint32_t, 16>(s, p) : runSort<uint32_t, 8>(s, p);
+    if (p.keyBits == 16) return runSort<uint16_t, GSM_SORT_ITEMS_U16>(s, p);
+    return p.largeTiles ? runSort<uint32_t, 16>(s, p) : runSort<uint32_t, GSM_SORT_ITEMS_SMALL>(s, p);
 }
 
 }  // namespace gsm
