@@ -45,6 +45,7 @@ struct Resources {
     void* renderData = nullptr;
     int32_t* bounds = nullptr;
     uint32_t* nTouched = nullptr;
+    uint2* hitMask = nullptr;
     BlendSplat* blendSplats = nullptr;
     // per visible (ping-pong pairs)
     uint32_t* depthKeys[2] = {nullptr, nullptr};
@@ -132,6 +133,7 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t oRender = take((size_t)G * (stereo ? 32 : 16));
     const size_t oBounds = take((size_t)G * 16);
     const size_t oTouched = take((size_t)G * 4);
+    const size_t oHitMask = stereo ? 0 : take((size_t)G * 8);
     const size_t oBlend = stereo ? 0 : take((size_t)G * sizeof(BlendSplat));
     const size_t oKeys0 = take((size_t)G * 4), oKeys1 = take((size_t)G * 4);
     const size_t oIdx0 = take((size_t)G * 4), oIdx1 = take((size_t)G * 4);
@@ -164,6 +166,7 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     res.renderData = a + oRender;
     res.bounds = (int32_t*)(a + oBounds);
     res.nTouched = (uint32_t*)(a + oTouched);
+    res.hitMask = stereo ? nullptr : (uint2*)(a + oHitMask);
     res.blendSplats = stereo ? nullptr : (BlendSplat*)(a + oBlend);
     res.depthKeys[0] = (uint32_t*)(a + oKeys0); res.depthKeys[1] = (uint32_t*)(a + oKeys1);
     res.primIdx[0] = (int32_t*)(a + oIdx0); res.primIdx[1] = (int32_t*)(a + oIdx1);
@@ -238,7 +241,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     const int tilePasses = tileSortPasses(tilesX * tilesY);
     recordStage(r, s, 3);
     // stage 5
-    GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.nTouched, res.offsets, res.scanStatus, &res.fs->ticketScan, res.bounds, res.renderData, res.tileIds[0],
+    GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.nTouched, res.hitMask, res.offsets, res.scanStatus, &res.fs->ticketScan, res.bounds, res.renderData, res.tileIds[0],
                                    res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians, &res.fs->hist[4][0],
                                    (uint32_t)tilePasses, r->numSMs), "create instances");
     recordStage(r, s, 4);
@@ -383,7 +386,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     fillMonoCam(mc, camera, gaussianCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
-    po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
+    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
@@ -445,7 +448,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     sc.tilesX = tilesX; sc.tilesY = tilesY;
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
-    po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
+    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
@@ -543,7 +546,7 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     fillMonoCam(mc, camera, gidCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
-    po.nTouched = res.nTouched; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
+    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
@@ -576,7 +579,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
-    po.nTouched = res.nTouched; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
+    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;

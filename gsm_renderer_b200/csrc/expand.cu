@@ -14,6 +14,7 @@ namespace gsm {
 template <typename TileT, bool STEREO>
 __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __restrict__ sortedIdx,
                                                                const uint32_t* __restrict__ nTouched,
+                                                               const uint2* __restrict__ hitMask,
                                                                uint32_t* __restrict__ offsets, unsigned long long* scanStatus,
                                                                uint32_t* ticket, const int32_t* __restrict__ bounds,
                                                                const void* __restrict__ renderData,
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
                                                                uint32_t maxAssignments, uint32_t* __restrict__ tileHist,
                                                                uint32_t tilePasses) {
     __shared__ WarpTileWork s_work[8];
+    __shared__ WarpMaskWork s_mask[8];
     __shared__ uint32_t s_hist[4][256];  // digit histograms of the emitted tile ids (the tile sort's histogram pass, fused)
     pdlLaunchDependents();
     for (int i = threadIdx.x; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
             writeOffset = s_tileBase + excl;
             if (i < visibleCount) offsets[i] = writeOffset;  // the in-place scan result (debugReadInstanceOffsets)
         }
+        uint2 mask = make_uint2(0u, 0u);  // mono, AABB of at most kMaskTiles tiles: replay stage 1's hit bits
         if (i < visibleCount) {
             if (originalIdx >= 0) {
                 const int4 b = __ldg(reinterpret_cast<const int4*>(bounds) + originalIdx);
@@ -65,16 +68,24 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
                 if (minTX <= maxTX && minTY <= maxTY) {
                     n = (uint32_t)((maxTX - minTX + 1) * (maxTY - minTY + 1));
                     if (!STEREO) {
-                        const uint4 rd = __ldg(reinterpret_cast<const uint4*>(renderData) + originalIdx);
-                        q = makeQuantSplat(__ushort_as_half((unsigned short)(rd.x & 0xFFFFu)),
-                                           __ushort_as_half((unsigned short)(rd.x >> 16)), (uint16_t)(rd.y & 0xFFFFu),
-                                           __ushort_as_half((unsigned short)(rd.y >> 16)),
-                                           __ushort_as_half((unsigned short)(rd.z & 0xFFFFu)), (uint8_t)(rd.w >> 24));
-                        if (!(q.d2Cutoff >= 0.0f)) n = 0;
+                        if (n <= kMaskTiles) {
+                            mask = __ldg(hitMask + originalIdx);
+                            n = 0;
+                        } else {
+                            const uint4 rd = __ldg(reinterpret_cast<const uint4*>(renderData) + originalIdx);
+                            q = makeQuantSplat(__ushort_as_half((unsigned short)(rd.x & 0xFFFFu)),
+                                               __ushort_as_half((unsigned short)(rd.x >> 16)), (uint16_t)(rd.y & 0xFFFFu),
+                                               __ushort_as_half((unsigned short)(rd.y >> 16)),
+                                               __ushort_as_half((unsigned short)(rd.z & 0xFFFFu)), (uint8_t)(rd.w >> 24));
+                            if (!(q.d2Cutoff >= 0.0f)) n = 0;
+                        }
                     }
                 }
             }
         }
+        if (!STEREO)
+            warpEmitMasked<TileT>(s_mask[warp], mask, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
+                                  tileIds, instanceIdx, &s_hist[0][0], tilePasses);
         if (STEREO) {
             // every tile of the union AABB, no ellipse test (DFS.metal:816-825): a splat whose mean is inside every
             // tile makes tileHitP return true for all of them without changing the walk
@@ -92,13 +103,13 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
 }
 
 cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* nTouched,
-                                  uint32_t* offsets, unsigned long long* scanStatus, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
+                                  const uint2* hitMask, uint32_t* offsets, unsigned long long* scanStatus, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
                                   uint32_t* tileHist, uint32_t tilePasses, int numSMs) {
     uint32_t grid = (capVisible + 255u) / 256u;
     if (grid > (uint32_t)numSMs * 6u) grid = (uint32_t)numSMs * 6u;  // persistent: few CTAs flush the fused histograms
     if (grid == 0) grid = 1;
-#define GSM_LAUNCH(T, ST) launchChained(create_instances_kernel<T, ST>, grid, 256, s, sortedIdx, nTouched, offsets, scanStatus, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
+#define GSM_LAUNCH(T, ST) launchChained(create_instances_kernel<T, ST>, grid, 256, s, sortedIdx, nTouched, hitMask, offsets, scanStatus, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
     if (tileId16) { if (stereo) GSM_LAUNCH(uint16_t, true); else GSM_LAUNCH(uint16_t, false); }
     else { if (stereo) GSM_LAUNCH(uint32_t, true); else GSM_LAUNCH(uint32_t, false); }
 #undef GSM_LAUNCH

@@ -10,6 +10,7 @@ struct ProjectOut {
     void* renderData;             // GSMGaussianRenderData[] or GSMStereoTiledRenderData[]
     int32_t* bounds;              // int4 per Gaussian
     uint32_t* nTouched;
+    uint2* hitMask;               // mono only: hit bits of the first 64 AABB tiles per Gaussian (gsm_tiletest.cuh)
     BlendSplat* blendSplats;      // mono only (may be null)
     uint32_t* preDepthKeys;       // per gid, before compaction (the reference aliases the sort scratch for it, DFR.swift:282)
     uint32_t* depthKeys;          // compacted, ascending gid
@@ -61,7 +62,7 @@ struct SortReset {  // look-back words of the tile sort, reset by the header ker
 
 // instance expansion (expand.cu)
 cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* nTouched,
-                                  uint32_t* offsets, unsigned long long* scanStatus, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
+                                  const uint2* hitMask, uint32_t* offsets, unsigned long long* scanStatus, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
                                   uint32_t* tileHist, uint32_t tilePasses, int numSMs);
 

@@ -109,6 +109,7 @@ struct WarpTileWork {
     int minTX[32], minTY[32], w[32];
     uint32_t prefix[32];
     uint32_t counter[32];
+    uint32_t maskLo[32], maskHi[32];  // hit bits of the first 64 AABB tiles (row-major), see warpCountTiles
 };
 
 __device__ __forceinline__ uint32_t warpExclusiveScan(uint32_t v, uint32_t& total) {
@@ -130,6 +131,8 @@ __device__ __forceinline__ void warpPublish(WarpTileWork& s, uint32_t excl, cons
     s.minTX[lane] = minTX; s.minTY[lane] = minTY; s.w[lane] = w;
     s.prefix[lane] = excl;
     s.counter[lane] = 0u;
+    s.maskLo[lane] = 0u;
+    s.maskHi[lane] = 0u;
     __syncwarp();
 }
 
@@ -142,9 +145,15 @@ __device__ __forceinline__ uint32_t warpOwnerOf(const WarpTileWork& s, uint32_t 
 }
 
 // Every lane passes n = number of AABB tiles to test (0 if none). Returns the lane's own hit count
-// (DFS.metal:181-205). Must be called by all 32 lanes.
-__device__ __forceinline__ uint32_t warpCountTiles(WarpTileWork& s, uint32_t n, const QuantSplat& q, int minTX, int minTY, int w) {
+// (DFS.metal:181-205) and, in `mask`, the hit bits of its first 64 AABB tiles in row-major order: for a splat whose
+// AABB has at most kMaskTiles tiles this IS its instance list, and the expansion stage replays it instead of running
+// the ellipse test a second time (the reference tests twice, DFS.metal:181-205 and :692-715; same function, same
+// operands, same result). Must be called by all 32 lanes.
+constexpr uint32_t kMaskTiles = 64;
+__device__ __forceinline__ uint32_t warpCountTiles(WarpTileWork& s, uint32_t n, const QuantSplat& q, int minTX, int minTY, int w,
+                                                   uint2& mask) {
     const unsigned lane = threadIdx.x & 31u;
+    mask = make_uint2(0u, 0u);
     uint32_t total;
     const uint32_t excl = warpExclusiveScan(n, total);
     if (total == 0) return 0u;
@@ -157,13 +166,92 @@ __device__ __forceinline__ uint32_t warpCountTiles(WarpTileWork& s, uint32_t n, 
             const uint32_t ww = (uint32_t)s.w[o];
             const uint32_t row = k / ww;
             const int ty = s.minTY[o] + (int)row, tx = s.minTX[o] + (int)(k - row * ww);
-            if (tileHitP(s.meanX[o], s.meanY[o], s.ca[o], s.cb[o], s.cc[o], s.cutoff[o], tx, ty)) atomicAdd(&s.counter[o], 1u);
+            if (tileHitP(s.meanX[o], s.meanY[o], s.ca[o], s.cb[o], s.cc[o], s.cutoff[o], tx, ty)) {
+                if (k < 32u) atomicOr(&s.maskLo[o], 1u << k);
+                else if (k < kMaskTiles) atomicOr(&s.maskHi[o], 1u << (k - 32u));
+                else atomicAdd(&s.counter[o], 1u);
+            }
         }
     }
     __syncwarp();
-    const uint32_t c = s.counter[lane];
+    mask = make_uint2(s.maskLo[lane], s.maskHi[lane]);
+    const uint32_t c = s.counter[lane] + (uint32_t)__popc(mask.x) + (uint32_t)__popc(mask.y);
     __syncwarp();
     return c;
+}
+
+// ---- replay of the hit masks (instance expansion of splats with <= kMaskTiles AABB tiles) ----------
+struct WarpMaskWork {
+    uint32_t prefix[32];
+    uint32_t maskLo[32], maskHi[32];
+    int minTX[32], minTY[32];
+    uint32_t w[32], recip[32];  // AABB width and ceil(2^16 / width): (b * recip) >> 16 == b / width for b < 64, width <= 64
+    uint32_t base[32];
+    int32_t idx[32];
+};
+
+// Every lane passes its splat's hit mask (0 if it has none or takes the tile-test path), AABB origin and width, the
+// scan offset and the original index. Instance r of a splat is its r-th set bit; lanes take instances, not splats, so
+// the stores are coalesced and the work is balanced. Emission order and the maxAssignments bound are those of
+// DFS.metal:692-715. The tile sort's digit histograms are accumulated for the stored instances.
+template <typename TileT>
+__device__ __forceinline__ void warpEmitMasked(WarpMaskWork& s, uint2 mask, int minTX, int minTY, int w, uint32_t writeBase,
+                                               int32_t originalIdx, uint32_t tilesX, uint32_t maxAssignments,
+                                               TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx, uint32_t* sHist,
+                                               uint32_t histPasses) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = (uint32_t)__popc(mask.x) + (uint32_t)__popc(mask.y);
+    uint32_t total;
+    const uint32_t excl = warpExclusiveScan(n, total);
+    if (total == 0) return;
+    s.prefix[lane] = excl;
+    s.maskLo[lane] = mask.x; s.maskHi[lane] = mask.y;
+    s.minTX[lane] = minTX; s.minTY[lane] = minTY;
+    s.w[lane] = (uint32_t)w;
+    s.recip[lane] = w > 0 ? (65536u + (uint32_t)w - 1u) / (uint32_t)w : 0u;
+    s.base[lane] = writeBase;
+    s.idx[lane] = originalIdx;
+    __syncwarp();
+    for (uint32_t j0 = 0; j0 < total; j0 += 32u) {
+        const uint32_t j = j0 + lane;
+        bool stored = false;
+        uint32_t tileId = 0xFFFFFFFFu;
+        if (j < total) {
+            uint32_t o = 0;  // largest lane with prefix <= j
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (s.prefix[o + step] <= j) o += step;
+            const uint32_t r = j - s.prefix[o];
+            // r-th set bit of the 64-bit mask
+            uint32_t word = s.maskLo[o], bit = 0, rr = r;
+            const uint32_t cLo = (uint32_t)__popc(word);
+            if (rr >= cLo) { rr -= cLo; word = s.maskHi[o]; bit = 32u; }
+            uint32_t pos = 0;
+#pragma unroll
+            for (int wd = 16; wd >= 1; wd >>= 1) {
+                const uint32_t c = (uint32_t)__popc((word >> pos) & ((1u << wd) - 1u));
+                if (rr >= c) { rr -= c; pos += (uint32_t)wd; }
+            }
+            bit += pos;
+            const uint32_t row = (bit * s.recip[o]) >> 16;
+            const int ty = s.minTY[o] + (int)row, tx = s.minTX[o] + (int)(bit - row * s.w[o]);
+            tileId = (uint32_t)(ty * (int)tilesX + tx);
+            const uint32_t dst = s.base[o] + r;
+            if (dst < maxAssignments) {  // DFS.metal:707
+                tileIds[dst] = (TileT)tileId;
+                instanceIdx[dst] = s.idx[o];
+                atomicAdd(&sHist[tileId & 0xFFu], 1u);
+                stored = true;
+            }
+        }
+        if (histPasses > 1) {  // upper digits are shared by most lanes: one shared-memory atomic per distinct value
+            const uint32_t hi = stored ? (tileId >> 8) : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, hi);
+            if (stored && (peers & ((1u << lane) - 1u)) == 0u)
+                for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], (uint32_t)__popc(peers));
+        }
+    }
+    __syncwarp();
 }
 
 // Emits the hit tiles of every lane's splat in row-major order at offsets[lane] + rank (DFS.metal:692-715).

@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const v
         } while (false);
     }
     // exact ellipse-vs-tile count, 32 tiles of the warp's concatenated AABBs per step
-    const uint32_t cnt = warpCountTiles(s_work[threadIdx.x >> 5], nTiles, q, bMinTX, bMinTY, bMaxTX - bMinTX + 1);
+    uint2 hitMask;
+    const uint32_t cnt = warpCountTiles(s_work[threadIdx.x >> 5], nTiles, q, bMinTX, bMinTY, bMaxTX - bMinTX + 1, hitMask);
     if (inRange) {
         if (alive && cnt > 0) {  // cnt == 0 is exit (9), DFS.metal:207-212 (renderData stays written)
             // the pre-expanded blend record (conicFromThetaSigmas on the same quantised values)
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const v
                                 (uint8_t)(sColor >> 24), sDepth);
             reinterpret_cast<int4*>(o.bounds)[gid] = make_int4(bMinTX, bMaxTX, bMinTY, bMaxTY);
             o.nTouched[gid] = cnt;
+            o.hitMask[gid] = hitMask;
             touched = cnt;
             key = float_to_sortable_uint(keyDepth);
         } else {

@@ -68,11 +68,13 @@ __global__ void __launch_bounds__(256) ingest_records_kernel(const SplatRecord* 
                            __ushort_as_half((unsigned short)(rd.z & 0xFFFFu)), (uint8_t)(rd.w >> 24));
         if (q.d2Cutoff >= 0.0f && minTX <= maxTX && minTY <= maxTY) nTiles = (uint32_t)((maxTX - minTX + 1) * (maxTY - minTY + 1));
     }
-    const uint32_t cnt = warpCountTiles(s_work[threadIdx.x >> 5], nTiles, q, minTX, minTY, maxTX - minTX + 1);
+    uint2 hitMask;
+    const uint32_t cnt = warpCountTiles(s_work[threadIdx.x >> 5], nTiles, q, minTX, minTY, maxTX - minTX + 1, hitMask);
     if (inRange && cnt > 0) {
         reinterpret_cast<uint4*>(o.renderData)[gid] = rd;
         reinterpret_cast<int4*>(o.bounds)[gid] = make_int4(minTX, maxTX, minTY, maxTY);
         o.nTouched[gid] = cnt;
+        o.hitMask[gid] = hitMask;
         storeBlendSplat(o.blendSplats + gid, q, __ushort_as_half((unsigned short)(rd.x & 0xFFFFu)),
                         __ushort_as_half((unsigned short)(rd.x >> 16)), (uint8_t)rd.w, (uint8_t)(rd.w >> 8), (uint8_t)(rd.w >> 16),
                         (uint8_t)(rd.w >> 24), __ushort_as_half((unsigned short)(rd.z >> 16)));
