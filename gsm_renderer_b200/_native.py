@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgsm_b200.so")
+# GSM_B200_LIB points at an instrumented build of the same library (tools/: kernel timelines); never at a fallback
+LIB_PATH = os.environ.get("GSM_B200_LIB") or os.path.join(_HERE, "lib", "libgsm_b200.so")
 
 GSM_NUM_STAGES = 8
 

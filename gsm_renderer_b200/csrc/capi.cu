@@ -63,6 +63,8 @@ struct Resources {
     FrameState* fs = nullptr;
     unsigned long long* projStatus = nullptr;
     unsigned long long* scanStatus = nullptr;
+    unsigned long long* scanGroups = nullptr;
+    unsigned long long* projGroups = nullptr;
     size_t zeroBytes = 0;
     // zeroed by the sort's histogram kernel
     uint32_t* depthSortStatus = nullptr;
@@ -146,8 +148,10 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t oHeader = take(sizeof(GSMDepthFirstHeader));
     const size_t oZero = off;
     const size_t oFS = take(sizeof(FrameState));
-    const size_t oProjStatus = take(((size_t)(G + 31) / 32 + 8) * 8);  // one look-back word per 32-gid warp tile
-    const size_t oScanStatus = take(((size_t)(G + 255) / 256 + 8) * 8);  // one look-back word per 256-Gaussian expansion tile
+    const size_t oProjStatus = take(((size_t)(G + 31) / 32 + 8) * 8);  // one prefix word per 32-gid warp tile (strip ingest) / 2048-gid tile (compaction)
+    const size_t oProjGroups = take(((size_t)(G + 31) / 32 / 32 + 8) * 8);  // one word per group of 32 tiles (prefixTwoLevel)
+    const size_t oScanStatus = take(((size_t)(G + 255) / 256 + 8) * 8);  // one prefix word per 256-Gaussian expansion tile
+    const size_t oScanGroups = take(((size_t)(G + 255) / 256 / 32 + 8) * 8);
     const size_t zeroEnd = off;
     const size_t oDepthStatus = take((size_t)4 * res.depthTilesCap * 256 * 4);
     const size_t oTileStatus = take((size_t)4 * res.tileTilesCap * 256 * 4);
@@ -180,6 +184,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     res.fs = (FrameState*)(a + oFS);
     res.projStatus = (unsigned long long*)(a + oProjStatus);
     res.scanStatus = (unsigned long long*)(a + oScanStatus);
+    res.scanGroups = (unsigned long long*)(a + oScanGroups);
+    res.projGroups = (unsigned long long*)(a + oProjGroups);
     res.zeroBytes = zeroEnd - oZero;
     res.depthSortStatus = (uint32_t*)(a + oDepthStatus);
     res.tileSortStatus = (uint32_t*)(a + oTileStatus);
@@ -231,6 +237,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     dp.k0 = res.depthKeys[0]; dp.k1 = res.depthKeys[1];
     dp.v0 = (uint32_t*)res.primIdx[0]; dp.v1 = (uint32_t*)res.primIdx[1];
     dp.countPtr = &res.header->visibleCount; dp.countCap = res.maxGaussians;
+    dp.gatherSrc = res.nTouched; dp.gatherDst = res.offsets;  // stage 3 rides on the last pass: offsets[i] = nTouched[sortedIdx[i]]
     dp.hist = &res.fs->hist[0][0]; dp.status = res.depthSortStatus; dp.gstatus = res.depthSortGStatus; dp.tickets = &res.fs->ticketSort[0];
     dp.largeTiles = largeSort(res.frameGaussians);
     dp.tilesCap = res.depthTilesCap; dp.keyBits = 32; dp.numPasses = key16 ? 2 : 4; dp.numSMs = r->numSMs;
@@ -241,7 +248,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     const int tilePasses = tileSortPasses(tilesX * tilesY);
     recordStage(r, s, 3);
     // stage 5
-    GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.nTouched, res.hitMask, res.offsets, res.scanStatus, &res.fs->ticketScan, res.bounds, res.renderData, res.tileIds[0],
+    GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.offsets, res.hitMask, res.offsets, res.scanStatus, res.scanGroups, &res.fs->ticketScan, res.bounds, res.renderData, res.tileIds[0],
                                    res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians, &res.fs->hist[4][0],
                                    (uint32_t)tilePasses, r->numSMs), "create instances");
     recordStage(r, s, 4);
@@ -385,7 +392,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     MonoCam mc;
     fillMonoCam(mc, camera, gaussianCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
     ProjectOut po;
-    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
@@ -447,7 +454,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     sc.inputIsSRGB = r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB ? 1.0f : 0.0f;
     sc.tilesX = tilesX; sc.tilesY = tilesY;
     ProjectOut po;
-    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
@@ -545,7 +552,7 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     MonoCam mc;
     fillMonoCam(mc, camera, gidCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
     ProjectOut po;
-    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
@@ -578,7 +585,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = false;
     GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
     ProjectOut po;
-    po.fs = res.fs; po.status = res.projStatus; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;

@@ -6,7 +6,8 @@ namespace gsm {
 
 struct ProjectOut {
     FrameState* fs;
-    unsigned long long* status;   // look-back words, one per 256-Gaussian tile
+    unsigned long long* status;   // prefix words, one per tile (32-gid warp tiles in the strip ingest, 2048-gid tiles in the compaction)
+    unsigned long long* statusGroups;  // compaction kernel: one word per group of 32 tiles (prefixTwoLevel)
     void* renderData;             // GSMGaussianRenderData[] or GSMStereoTiledRenderData[]
     int32_t* bounds;              // int4 per Gaussian
     uint32_t* nTouched;
@@ -50,6 +51,8 @@ struct SortPlan {
     int numPasses;
     int numSMs;
     bool largeTiles;     // 32-bit keys only: 4096-key tiles (large inputs) instead of 2048
+    const uint32_t* gatherSrc = nullptr;  // optional: the last pass also writes gatherDst[i] = gatherSrc[sorted payload i]
+    uint32_t* gatherDst = nullptr;
     bool histogramReady; // hist filled and status/gstatus zeroed by earlier kernels of the frame (fused); else a histogram kernel runs
 };
 uint32_t sortTileSize(int keyBits, bool large);
@@ -61,8 +64,8 @@ struct SortReset {  // look-back words of the tile sort, reset by the header ker
 };
 
 // instance expansion (expand.cu)
-cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* nTouched,
-                                  const uint2* hitMask, uint32_t* offsets, unsigned long long* scanStatus, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
+cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* sortedTouched,
+                                  const uint2* hitMask, uint32_t* offsets, unsigned long long* scanStatus, unsigned long long* scanGroups, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
                                   uint32_t* tileHist, uint32_t tilePasses, int numSMs);
 

@@ -294,7 +294,7 @@ __device__ __forceinline__ GaussianIn loadGaussian(const void* base, uint32_t gi
     GaussianIn g;
     if (HALF) {
         const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * (size_t)gid;
-        uint4 a = __ldg(p), b = __ldg(p + 1);
+        uint4 a = __ldcs(p), b = __ldcs(p + 1);
         g.pos = V3{__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)};
         __half2 h0 = *reinterpret_cast<__half2*>(&a.w);  // opacity, sx
         __half2 h1 = *reinterpret_cast<__half2*>(&b.x);  // sy, sz
@@ -305,7 +305,7 @@ __device__ __forceinline__ GaussianIn loadGaussian(const void* base, uint32_t gi
         g.rot = V4{__low2float(h2), __high2float(h2), __low2float(h3), __high2float(h3)};
     } else {
         const uint4* p = reinterpret_cast<const uint4*>(base) + 3 * (size_t)gid;
-        uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        uint4 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
         g.pos = V3{__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z)};
         g.opacity = __uint_as_float(a.w);
         g.scale = V3{__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)};
@@ -329,13 +329,13 @@ __device__ __forceinline__ void loadSH(const void* base, uint32_t gid, float (&o
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             if (VEC == 16) {
-                uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+                uint4 v = __ldcs(reinterpret_cast<const uint4*>(p) + i);
                 w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             } else if (VEC == 8) {
-                uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + i);
+                uint2 v = __ldcs(reinterpret_cast<const uint2*>(p) + i);
                 w[2 * i] = v.x; w[2 * i + 1] = v.y;
             } else {
-                w[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + i);
+                w[i] = __ldcs(reinterpret_cast<const uint32_t*>(p) + i);
             }
         }
 #pragma unroll
@@ -350,7 +350,7 @@ __device__ __forceinline__ void loadSH(const void* base, uint32_t gid, float (&o
     } else {
         const __half* hp = reinterpret_cast<const __half*>(p);
 #pragma unroll
-        for (int i = 0; i < N; ++i) out[i] = __half2float(__ldg(hp + i));
+        for (int i = 0; i < N; ++i) out[i] = __half2float(__ldcs(hp + i));
     }
 }
 
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
             for (int off = 4; off > 0; off >>= 1) bt += __shfl_xor_sync(0xFFFFFFFFu, bt, off);
             bt = __shfl_sync(0xFFFFFFFFu, bt, 0);
             uint32_t ev, et;
-            lookback_exclusive2(o.status, tile, blockVisible, bt, ev, et);
+            prefixTwoLevel(o.status, o.statusGroups, tile, blockVisible, bt, ev, et);
             if (lane == 0) {
                 s_baseVisible = ev;
                 if (tile == numTiles - 1) {

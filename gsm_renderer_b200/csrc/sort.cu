@@ -92,12 +92,17 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
 }
 
 // ---- one digit pass
-template <typename KeyT, int ITEMS>
+// GATHER (the depth sort's last pass): the payload is an index; besides the sorted pairs the pass writes
+// gatherDst[sorted position] = gatherSrc[payload], so the consumer reads that array in order instead of
+// gathering through the sorted indices at the head of its own dependency chain (expansion timeline: the scan
+// waited ~4.5 us per tile for the slowest in-flight predecessor's random gather).
+template <typename KeyT, int ITEMS, bool GATHER>
 __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                                                                      KeyT* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
                                                                      const uint32_t* __restrict__ countPtr, uint32_t countCap,
                                                                      const uint32_t* __restrict__ digitHist, uint32_t* status,
-                                                                     uint32_t* gstatus, uint32_t* ticket, int shift) {
+                                                                     uint32_t* gstatus, uint32_t* ticket, int shift,
+                                                                     const uint32_t* __restrict__ gatherSrc, uint32_t* __restrict__ gatherDst) {
     constexpr int TILE = kSortThreads * ITEMS;
     constexpr KeyT SENTINEL = (KeyT)~(KeyT)0;
 
@@ -324,6 +329,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
         GSM_TRACE(tile, 6);  // tile ordered in shared memory
         // valid elements occupy tile positions [0, tileValid) except that sentinel padding sits at the end of
         // the sentinel digit's bin; bins after it (none: the sentinel digit is 0xFF) would shift.
+        uint32_t gdst[GATHER ? ITEMS : 1], gval[GATHER ? ITEMS : 1];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             uint32_t j = tid + i * kSortThreads;
@@ -331,9 +337,16 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
                 KeyT k = s_keys[j];
                 uint32_t d = ((uint32_t)k >> shift) & 0xFFu;
                 uint32_t dst = s_globalBase[d] + j;
+                const uint32_t v = s_vals[j];
                 keysOut[dst] = k;
-                valsOut[dst] = s_vals[j];
+                valsOut[dst] = v;
+                if (GATHER) { gdst[i] = dst; gval[i] = __ldg(gatherSrc + v); }
             }
+        }
+        if (GATHER) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i)
+                if (tid + i * kSortThreads < tileValid) gatherDst[gdst[i]] = gval[i];
         }
         __syncthreads();
         GSM_TRACE(tile, 7);  // stores issued
@@ -355,16 +368,21 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
         case 3: launchChained(radix_histogram_kernel<KeyT, 3, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
         default: launchChained(radix_histogram_kernel<KeyT, 4, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
     }
-    int blocksPerSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, onesweep_pass_kernel<KeyT, ITEMS>, kSortThreads, 0);
-    if (blocksPerSM < 1) blocksPerSM = 1;
+    static int blocksPerSM = 0;  // per template instance
+    if (blocksPerSM == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, onesweep_pass_kernel<KeyT, ITEMS, false>, kSortThreads, 0);
+        if (blocksPerSM < 1) blocksPerSM = 1;
+    }
     const int grid = p.numSMs * blocksPerSM;  // every CTA is resident: the look-back cannot starve
     for (int pass = 0; pass < p.numPasses; ++pass) {
         const bool even = (pass & 1) == 0;
-        launchChained(onesweep_pass_kernel<KeyT, ITEMS>, grid, kSortThreads, s,
+        const bool gather = p.gatherSrc != nullptr && pass == p.numPasses - 1;
+        auto kernel = gather ? onesweep_pass_kernel<KeyT, ITEMS, true> : onesweep_pass_kernel<KeyT, ITEMS, false>;
+        launchChained(kernel, grid, kSortThreads, s,
                       even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
                       p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u,
-                      p.gstatus + (size_t)pass * ((p.tilesCap + kLookGroup - 1) / kLookGroup) * 256u, p.tickets + pass, 8 * pass);
+                      p.gstatus + (size_t)pass * ((p.tilesCap + kLookGroup - 1) / kLookGroup) * 256u, p.tickets + pass, 8 * pass,
+                      p.gatherSrc, p.gatherDst);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
