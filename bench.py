@@ -401,6 +401,7 @@ def main():
                    "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                    "warmup_extra_steps": extra},
         "mtile_instances_per_s": (I / (sort_blend_ms * 1e-3) / 1e6) if sort_blend_ms > 0 else None,
+        "step_ms": {"min": float(min(step_ms)), "median": float(np.median(step_ms)), "max": float(max(step_ms))},
         "stage_ms": stage_ms,
         "roofline": roofline,
         "stage_roofline": stage_roofline,

@@ -152,11 +152,12 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t oProjGroups = take(((size_t)(G + 31) / 32 / 32 + 8) * 8);  // one word per group of 32 tiles (prefixTwoLevel)
     const size_t oScanStatus = take(((size_t)(G + 255) / 256 + 8) * 8);  // one prefix word per 256-Gaussian expansion tile
     const size_t oScanGroups = take(((size_t)(G + 255) / 256 / 32 + 8) * 8);
-    const size_t zeroEnd = off;
+    // the sorts' per-tile status words are part of the per-frame memset too (a few MB: cheaper than a reset kernel's launch)
     const size_t oDepthStatus = take((size_t)4 * res.depthTilesCap * 256 * 4);
-    const size_t oTileStatus = take((size_t)4 * res.tileTilesCap * 256 * 4);
+    const size_t oTileStatus = take((size_t)(tile16 ? 2 : 4) * res.tileTilesCap * 256 * 4);
     const size_t oDepthGStatus = take((size_t)4 * ((res.depthTilesCap + 15) / 16) * 256 * 4);
-    const size_t oTileGStatus = take((size_t)4 * ((res.tileTilesCap + 15) / 16) * 256 * 4);
+    const size_t oTileGStatus = take((size_t)(tile16 ? 2 : 4) * ((res.tileTilesCap + 15) / 16) * 256 * 4);
+    const size_t zeroEnd = off;
     res.bytes = off;
 
     cudaError_t e = cudaMalloc((void**)&res.arena, res.bytes);
@@ -394,14 +395,13 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
-    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances, tileSortReset(r, res, tilesX, tilesY), r->numSMs), "finalize header");
     recordStage(r, s, 1);
     st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);
     if (st != GSM_OK) return st;
@@ -456,14 +456,13 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
-    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances, tileSortReset(r, res, tilesX, tilesY), r->numSMs), "finalize header");
     recordStage(r, s, 1);
     st = encodeSortExpandRange(r, res, s, true, tilesX, tilesY);
     if (st != GSM_OK) return st;
@@ -554,7 +553,7 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
@@ -587,7 +586,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     ProjectOut po;
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.preDepthKeys = res.depthKeys[1];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u; po.depthKey16 = 0; po.gidFirst = 0;

@@ -148,71 +148,6 @@ __device__ __forceinline__ uint32_t lookback_exclusive(unsigned long long* statu
     return exclusive;
 }
 
-// Two-level direct prefix over per-tile 64-bit words ([63:62] flag, [61:32] "hi" sum of 30 bits, [31:0] "lo" sum,
-// wrapping), run by one full warp; returns the exclusive sums of tiles < tile. The persistent kernels that use it keep
-// hundreds of tiles in flight at once, so in a chained look-back nothing is "inclusive" yet and a tile walks its
-// predecessors window by window, one dependent L2 round trip each (ncu r1_v9: 28 % of the expansion kernel's samples
-// sat at the barrier behind that walk). Here a tile publishes its aggregate once and sums directly: the earlier tiles of
-// its own group of 32 (one word per lane) and one word per earlier GROUP, published by each group's last tile as
-// soon as its own level-1 sum is known. Both levels are requested together; the dependency chain is two round trips.
-// Forward progress: tiles are handed out by an atomic ticket, so every predecessor is running or done.
-__device__ __forceinline__ unsigned long long packPrefixWord(uint32_t hi, uint32_t lo) {
-    return (1ull << 62) | ((unsigned long long)(hi & 0x3FFFFFFFu) << 32) | lo;
-}
-__device__ __forceinline__ void prefixTwoLevel(unsigned long long* tileWords, unsigned long long* groupWords, uint32_t tile,
-                                               uint32_t aggHi, uint32_t aggLo, uint32_t& exclHi, uint32_t& exclLo) {
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t g = tile >> 5, nT = tile & 31u;
-    if (lane == 0) st_u64_relaxed(tileWords + tile, packPrefixWord(aggHi, aggLo));
-    const unsigned long long ready = packPrefixWord(0u, 0u);
-    uint32_t hi = 0, lo = 0;
-    bool done1 = false, done2 = false;
-    do {  // level 1 and the first 128 groups of level 2 in flight together
-        unsigned long long w1 = ready, w2[4] = {ready, ready, ready, ready};
-        if (!done1 && lane < nT) w1 = ld_status64(tileWords + (g << 5) + lane);
-        if (!done2) {
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k)
-                if (k * 32u + lane < g) w2[k] = ld_status64(groupWords + k * 32u + lane);
-        }
-        if (!done1 && __all_sync(0xFFFFFFFFu, (w1 >> 62) != 0ull)) {
-            uint32_t h = (uint32_t)(w1 >> 32) & 0x3FFFFFFFu, l = (uint32_t)w1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xFFFFFFFFu, h, o); l += __shfl_xor_sync(0xFFFFFFFFu, l, o); }
-            if (nT == 31u && lane == 0) st_u64_relaxed(groupWords + g, packPrefixWord(h + aggHi, l + aggLo));  // the group's last tile
-            hi += h; lo += l;
-            done1 = true;
-        }
-        if (!done2 && __all_sync(0xFFFFFFFFu, ((w2[0] & w2[1] & w2[2] & w2[3]) >> 62) != 0ull)) {
-            uint32_t h = 0, l = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) { h += (uint32_t)(w2[k] >> 32) & 0x3FFFFFFFu; l += (uint32_t)w2[k]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xFFFFFFFFu, h, o); l += __shfl_xor_sync(0xFFFFFFFFu, l, o); }
-            hi += h; lo += l;
-            done2 = true;
-        }
-    } while (!(done1 && done2));
-    for (uint32_t base = 128u; base < g; base += 128u) {  // very many tiles: the remaining groups, 128 at a time
-        while (true) {
-            unsigned long long w2[4] = {ready, ready, ready, ready};
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k)
-                if (base + k * 32u + lane < g) w2[k] = ld_status64(groupWords + base + k * 32u + lane);
-            if (!__all_sync(0xFFFFFFFFu, ((w2[0] & w2[1] & w2[2] & w2[3]) >> 62) != 0ull)) continue;
-            uint32_t h = 0, l = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) { h += (uint32_t)(w2[k] >> 32) & 0x3FFFFFFFu; l += (uint32_t)w2[k]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xFFFFFFFFu, h, o); l += __shfl_xor_sync(0xFFFFFFFFu, l, o); }
-            hi += h; lo += l;
-            break;
-        }
-    }
-    exclHi = hi & 0x3FFFFFFFu;
-    exclLo = lo;
-}
-
 // Eager variant for software-pipelined consumers: a tile PUBLISHES as soon as its aggregate is known (a word per tile
 // and a RED into its group's accumulator, whose top bits count arrivals), goes on with other work, and RESOLVES its
 // exclusive prefix later -- by then every predecessor has long published, so the resolve is one round trip and no tile
@@ -250,6 +185,48 @@ __device__ __forceinline__ uint32_t prefixResolve(const unsigned long long* tile
         }
     }
     return sum;
+}
+
+// Dual-sum flavour of the eager prefix (visibility compaction): every word carries a visible count (18 bits) and a
+// touched-tile sum (40 bits). Tile word: [63] published. Group word: [63:58] arrivals (32 tiles per group).
+// Same-address REDs cost ~0.7 ns each on B200 (tools/micro/atomic_rate.cu): 32 arrivals per word are free.
+__device__ __forceinline__ void prefixPublish2(unsigned long long* tileWords, unsigned long long* groupWords, uint32_t tile,
+                                               uint32_t visible, uint32_t touched) {  // one thread
+    const unsigned long long v = ((unsigned long long)visible << 40) | (unsigned long long)touched;
+    st_u64_relaxed(tileWords + tile, (1ull << 63) | v);
+    atomicAdd(groupWords + (tile >> 5), (1ull << 58) | v);
+}
+__device__ __forceinline__ void prefixResolve2(const unsigned long long* tileWords, const unsigned long long* groupWords,
+                                               uint32_t tile, uint32_t& exclVisible, unsigned long long& exclTouched) {  // one full warp
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t g = tile >> 5, nT = tile & 31u;
+    const unsigned long long fullGroup = 32ull << 58, touchedMask = (1ull << 40) - 1ull;
+    uint32_t vis = 0;
+    unsigned long long tch = 0;
+    for (uint32_t base = 0; base == 0 || base < g; base += 128u) {
+        while (true) {
+            unsigned long long w1 = 1ull << 63, w2[4] = {fullGroup, fullGroup, fullGroup, fullGroup};
+            if (base == 0 && lane < nT) w1 = ld_status64(tileWords + (g << 5) + lane);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                if (base + k * 32u + lane < g) w2[k] = ld_status64(groupWords + base + k * 32u + lane);
+            bool ok = (w1 >> 63) != 0ull;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) ok = ok && (w2[k] >> 58) == 32ull;
+            if (!__all_sync(0xFFFFFFFFu, ok)) continue;
+            uint32_t v = (uint32_t)(w1 >> 40) & 0x3FFFFu;
+            unsigned long long t = w1 & touchedMask;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) { v += (uint32_t)(w2[k] >> 40) & 0x3FFFFu; t += w2[k] & touchedMask; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xFFFFFFFFu, v, o); t += __shfl_xor_sync(0xFFFFFFFFu, t, o); }
+            vis += v;
+            tch += t;
+            break;
+        }
+    }
+    exclVisible = vis;
+    exclTouched = tch;
 }
 
 // exclusive scan of one value per thread over a 256-thread block; returns the exclusive prefix and

@@ -7,7 +7,7 @@ namespace gsm {
 struct ProjectOut {
     FrameState* fs;
     unsigned long long* status;   // prefix words, one per tile (32-gid warp tiles in the strip ingest, 2048-gid tiles in the compaction)
-    unsigned long long* statusGroups;  // compaction kernel: one word per group of 32 tiles (prefixTwoLevel)
+    unsigned long long* statusGroups;  // one word per group of 32 tiles
     void* renderData;             // GSMGaussianRenderData[] or GSMStereoTiledRenderData[]
     int32_t* bounds;              // int4 per Gaussian
     uint32_t* nTouched;
@@ -16,7 +16,9 @@ struct ProjectOut {
     uint32_t* preDepthKeys;       // per gid, before compaction (the reference aliases the sort scratch for it, DFR.swift:282)
     uint32_t* depthKeys;          // compacted, ascending gid
     int32_t* primitiveIndices;
-    uint32_t maxOut;
+    uint32_t maxOut;              // capacity of the compacted arrays (maxGaussians)
+    GSMDepthFirstHeader* header;  // if set, the projection's last block also writes the frame header (no finalize kernel)
+    uint32_t maxInstances;
     uint32_t depthKey16;
     uint32_t gidFirst;
     // fused into the compaction kernel: digit histograms of the compacted depth keys and the reset of the depth

@@ -684,6 +684,20 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_stereo_kernel(const
 // DFS.metal:218). It is a separate kernel on purpose: fused into the projection kernel, every warp had to wait
 // for all earlier warps' tile walks before it could retire (ncu r1_v3: 36 % of that kernel's instructions were
 // look-back spins). Here the work per element is uniform, so the chain never stalls.
+// DFS.metal:2184-2203: clamp the raw totals to the buffer capacities, radix-aligned padded counts, overflow flag
+__device__ __forceinline__ void writeFrameHeader(GSMDepthFirstHeader* header, uint32_t v, uint32_t i, uint32_t maxGaussians,
+                                                 uint32_t maxInstances) {
+    uint32_t overflow = 0;
+    if (v > maxGaussians) { v = maxGaussians; overflow = 1u; }
+    if (i > maxInstances) { i = maxInstances; overflow = 1u; }
+    header->visibleCount = v;
+    header->totalInstances = i;
+    header->paddedVisibleCount = ((v + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
+    header->paddedInstanceCount = ((i + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
+    header->overflow = overflow;
+    header->padding0 = 0; header->padding1 = 0; header->padding2 = 0;
+}
+
 constexpr int kCompactItems = 8;
 __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, ProjectOut o) {
     __shared__ uint32_t s_scan[9];
@@ -695,13 +709,6 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
     pdlLaunchDependents();
     for (int i = tid; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
     pdlWait();
-    {   // reset the depth sort's look-back words for this frame: ceil(N / sortTile) tiles per pass bound V <= N
-        const uint32_t words = ((N + o.depthTileSize - 1u) / o.depthTileSize) * 256u, gwords = ((words / 256u + 15u) / 16u) * 256u;
-        for (uint32_t p = 0; p < o.depthPasses; ++p) {
-            for (uint32_t i = blockIdx.x * 256u + tid; i < words; i += gridDim.x * 256u) o.depthStatus[(size_t)p * o.depthStatusStride + i] = 0u;
-            for (uint32_t i = blockIdx.x * 256u + tid; i < gwords; i += gridDim.x * 256u) o.depthGStatus[(size_t)p * o.depthGStatusStride + i] = 0u;
-        }
-    }
     __syncthreads();
     while (true) {
         if (tid == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);
@@ -727,13 +734,18 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
             uint32_t bt = (lane < 8) ? s_touched[lane] : 0u;
             for (int off = 4; off > 0; off >>= 1) bt += __shfl_xor_sync(0xFFFFFFFFu, bt, off);
             bt = __shfl_sync(0xFFFFFFFFu, bt, 0);
-            uint32_t ev, et;
-            prefixTwoLevel(o.status, o.statusGroups, tile, blockVisible, bt, ev, et);
+            // publish, then sum the predecessors directly: no tile depends on another tile's resolve
+            if (lane == 0) prefixPublish2(o.status, o.statusGroups, tile, blockVisible, bt);
+            uint32_t ev;
+            unsigned long long et;
+            prefixResolve2(o.status, o.statusGroups, tile, ev, et);
             if (lane == 0) {
                 s_baseVisible = ev;
                 if (tile == numTiles - 1) {
-                    o.fs->visibleCountRaw = ev + blockVisible;  // DFS.metal:618-620
-                    o.fs->totalInstancesRaw = et + bt;          // DFS.metal:218
+                    o.fs->visibleCountRaw = ev + blockVisible;            // DFS.metal:618-620
+                    o.fs->totalInstancesRaw = (uint32_t)(et + bt);        // DFS.metal:218 (u32, wraps)
+                    // the frame header (prepareIndirectDispatchKernel's role, DFS.metal:2184-2203) rides on the same thread
+                    if (o.header) writeFrameHeader(o.header, ev + blockVisible, (uint32_t)(et + bt), o.maxOut, o.maxInstances);
                 }
             }
         }
@@ -777,17 +789,9 @@ __global__ void __launch_bounds__(256) finalize_header_kernel(const FrameState* 
                                                               uint32_t maxInstances, SortReset reset) {
     pdlLaunchDependents();
     pdlWait();
-    uint32_t v = fs->visibleCountRaw, i = fs->totalInstancesRaw, overflow = 0;
-    if (v > maxGaussians) { v = maxGaussians; overflow = 1u; }
-    if (i > maxInstances) { i = maxInstances; overflow = 1u; }
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        header->visibleCount = v;
-        header->totalInstances = i;
-        header->paddedVisibleCount = ((v + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
-        header->paddedInstanceCount = ((i + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
-        header->overflow = overflow;
-        header->padding0 = 0; header->padding1 = 0; header->padding2 = 0;
-    }
+    uint32_t i = fs->totalInstancesRaw;
+    if (i > maxInstances) i = maxInstances;
+    if (threadIdx.x == 0 && blockIdx.x == 0) writeFrameHeader(header, fs->visibleCountRaw, fs->totalInstancesRaw, maxGaussians, maxInstances);
     // reset the tile sort's look-back words for exactly the tiles this frame's totalInstances needs
     const uint32_t words = ((i + reset.tileSize - 1u) / reset.tileSize) * 256u;
     const uint32_t gwords = ((words / 256u + 15u) / 16u) * 256u;
