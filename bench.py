@@ -38,7 +38,7 @@ WORKLOADS = {
     "C5v": (3_000_000, 3, "float16", 1280, 720, 0.012, "C5 (one view): 3M Gaussians SH3 float16, 1280x720"),
 }
 NEAR, FAR = 0.1, 100.0  # PLYBenchmarkTests.swift:60-62
-KERNELS_PER_FRAME = 12  # project, compaction, header, 4+2 onesweep passes, scan+expand, ranges, blend
+KERNELS_PER_FRAME = 11  # project, compaction (+header), 4 depth + 2 tile onesweep passes, scan+expand, ranges, blend
 
 
 def measured_peaks():

@@ -112,6 +112,22 @@ public:
                                 (uint32_t)input.gaussianCount, (uint32_t)input.shComponents, &l, &r, (uint32_t)width,
                                 (uint32_t)height));
     }
+    // Host buffers (no device allocator on the caller's side): upload + frame + download. renderHostAsync only encodes,
+    // like the reference's render() into a command buffer; waitHost() is the waitUntilCompleted. One frame in flight per
+    // renderer -- use two renderers to overlap a frame's upload with the previous frame's render + download.
+    void renderHost(const void* hostGaussians, const void* hostHarmonics, int gaussianCount, int shComponents,
+                    const CameraParams& camera, int width, int height, void* hostColor, void* hostDepth = nullptr) {
+        gsm_camera c = camera.native();
+        check(gsm_render_host(h_, hostGaussians, hostHarmonics, (uint32_t)gaussianCount, (uint32_t)shComponents, &c,
+                              (uint32_t)width, (uint32_t)height, hostColor, hostDepth));
+    }
+    void renderHostAsync(const void* hostGaussians, const void* hostHarmonics, int gaussianCount, int shComponents,
+                         const CameraParams& camera, int width, int height, void* hostColor, void* hostDepth = nullptr) {
+        gsm_camera c = camera.native();
+        check(gsm_render_host_async(h_, hostGaussians, hostHarmonics, (uint32_t)gaussianCount, (uint32_t)shComponents, &c,
+                                    (uint32_t)width, (uint32_t)height, hostColor, hostDepth));
+    }
+    void waitHost() { check(gsm_render_host_wait(h_)); }
     double lastGPUTime() const { return gsm_last_gpu_time_ms(h_) * 1e-3; }
 
     // white-box reads

@@ -195,6 +195,17 @@ public final class DepthFirstRenderer: GaussianRenderer, @unchecked Sendable {
                        UInt32(width), UInt32(height))
     }
 
+    /// Host buffers: upload + frame + download on the renderer's own stream. `renderHostAsync` only encodes (the shape of
+    /// render() + commit()); `waitHost()` is waitUntilCompleted. The buffers must stay valid until the wait.
+    public func renderHostAsync(gaussians: UnsafeRawPointer, harmonics: UnsafeRawPointer, gaussianCount: Int, shComponents: Int,
+                                camera: CameraParams, width: Int, height: Int, color: UnsafeMutableRawPointer,
+                                depth: UnsafeMutableRawPointer?) {
+        var cam = camera.native()
+        _ = gsm_render_host_async(handle, gaussians, harmonics, UInt32(gaussianCount), UInt32(shComponents), &cam,
+                                  UInt32(width), UInt32(height), color, depth)
+    }
+    public func waitHost() { _ = gsm_render_host_wait(handle) }
+
     public func renderStereo(commandBuffer: CommandBuffer, target: StereoRenderTarget, input: GaussianInput,
                              camera: StereoCameraParams, width: Int, height: Int) {
         guard case let .sideBySide(colorTexture, _) = target else { return }
