@@ -27,6 +27,17 @@ class gsm_camera(C.Structure):
                 ("nearPlane", C.c_float), ("farPlane", C.c_float)]
 
 
+class gsm_ply_info(C.Structure):  # include/gsm/gsm_scene.h
+    _fields_ = [("vertexCount", C.c_uint32), ("format", C.c_uint32), ("compressed", C.c_uint32),
+                ("shProperties", C.c_uint32), ("bodyOffset", C.c_uint64)]
+
+
+class gsm_scene_info(C.Structure):  # include/gsm/gsm_scene.h
+    _fields_ = [("count", C.c_uint32), ("shComponents", C.c_uint32), ("harmonicsStride", C.c_uint32),
+                ("compressed", C.c_uint32), ("scaleIsLogSpace", C.c_uint32), ("opacityIsLogit", C.c_uint32),
+                ("center", C.c_float * 3), ("boundsCenter", C.c_float * 3), ("boundsRadius", C.c_float)]
+
+
 class DepthFirstHeader(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("visibleCount", "totalInstances", "paddedVisibleCount",
                                           "paddedInstanceCount", "overflow", "padding0", "padding1",
@@ -51,6 +62,10 @@ EXPORTS = {
     "gsm_render_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                         C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_render_host_wait": (C.c_int, [C.c_void_p]),
+    "gsm_ply_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(gsm_ply_info)]),
+    "gsm_ply_load": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32,
+                               C.c_size_t, C.POINTER(gsm_scene_info)]),
+    "gsm_scene_morton_sort": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     "gsm_last_gpu_time_ms": (C.c_double, [C.c_void_p]),
     "gsm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gsm_get_stage_times_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

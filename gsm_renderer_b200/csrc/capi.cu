@@ -24,6 +24,48 @@ gsm_status fail(gsm_status s, const char* what, cudaError_t e = cudaSuccess) {
     return s;
 }
 
+}  // namespace
+
+namespace gsm {
+gsm_status reportFailure(gsm_status s, const char* what, cudaError_t e) { return fail(s, what, e); }  // scene.cu
+
+// Standalone stable pair sort on the current device (gsm_sort_pairs, the Morton pre-sort of scene.cu): scratch is
+// allocated per call and the stream is synchronised before it is freed.
+gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* payload, uint32_t count, int keyBits, int numPasses) {
+    if (count == 0) return GSM_OK;
+    const bool large = keyBits == 32 && count >= 3000000u;
+    const uint32_t tile = sortTileSize(keyBits, large);
+    const uint32_t tiles = (count + tile - 1) / tile;
+    const size_t keyBytes = (size_t)count * (keyBits / 8);
+    auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    // scratch: [count u32][hist 4*256][tickets 4][status passes*tiles*256][k1][v1]
+    const size_t oHist = 256, oTickets = oHist + 4 * 256 * 4, oStatus = up(oTickets + 16, 256);
+    const size_t oGStatus = up(oStatus + (size_t)numPasses * tiles * 256 * 4, 256);
+    const size_t oK1 = up(oGStatus + (size_t)numPasses * ((tiles + 15) / 16) * 256 * 4, 256), oV1 = up(oK1 + keyBytes, 256);
+    const size_t total = oV1 + (size_t)count * 4;
+    char* scratch = nullptr;
+    cudaError_t e = cudaMalloc((void**)&scratch, total);
+    if (e != cudaSuccess) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "sort scratch", e);
+    gsm_status st = GSM_OK;
+    do {
+        if ((e = cudaMemsetAsync(scratch, 0, oK1, s)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(scratch, &count, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
+        SortPlan p;
+        p.k0 = keys; p.k1 = scratch + oK1; p.v0 = (uint32_t*)payload; p.v1 = (uint32_t*)(scratch + oV1);
+        p.countPtr = (const uint32_t*)scratch; p.countCap = count;
+        p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.gstatus = (uint32_t*)(scratch + oGStatus); p.tickets = (uint32_t*)(scratch + oTickets);
+        p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = numSMs; p.histogramReady = false; p.largeTiles = large;
+        if ((e = launchSort(s, p)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(s);
+    } while (false);
+    if (e != cudaSuccess) st = fail(GSM_ERR_RENDER_FAILED, "sort pairs", e);
+    cudaFree(scratch);
+    return st;
+}
+}
+
+namespace {
+
 #define GSM_CUDA(call, what)                                            \
     do {                                                                \
         cudaError_t e__ = (call);                                       \
@@ -732,34 +774,7 @@ gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* paylo
     if ((keyBits != 16 && keyBits != 32) || numPasses < 1 || numPasses > keyBits / 8) return fail(GSM_ERR_INVALID_ARGUMENT, "bad key width / pass count");
     if (count == 0) return GSM_OK;
     DeviceGuard guard(r->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    const bool large = keyBits == 32 && count >= 3000000u;
-    const uint32_t tile = sortTileSize(keyBits, large);
-    const uint32_t tiles = (count + tile - 1) / tile;
-    const size_t keyBytes = (size_t)count * (keyBits / 8);
-    // scratch: [count u32][hist 4*256][tickets 4][status passes*tiles*256][k1][v1]
-    const size_t oHist = 256, oTickets = oHist + 4 * 256 * 4, oStatus = alignUp(oTickets + 16, 256);
-    const size_t oGStatus = alignUp(oStatus + (size_t)numPasses * tiles * 256 * 4, 256);
-    const size_t oK1 = alignUp(oGStatus + (size_t)numPasses * ((tiles + 15) / 16) * 256 * 4, 256), oV1 = alignUp(oK1 + keyBytes, 256);
-    const size_t total = oV1 + (size_t)count * 4;
-    char* scratch = nullptr;
-    cudaError_t e = cudaMalloc((void**)&scratch, total);
-    if (e != cudaSuccess) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "sort scratch", e);
-    gsm_status st = GSM_OK;
-    do {
-        if ((e = cudaMemsetAsync(scratch, 0, oK1, s)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(scratch, &count, 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
-        SortPlan p;
-        p.k0 = keys; p.k1 = scratch + oK1; p.v0 = (uint32_t*)payload; p.v1 = (uint32_t*)(scratch + oV1);
-        p.countPtr = (const uint32_t*)scratch; p.countCap = count;
-        p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.gstatus = (uint32_t*)(scratch + oGStatus); p.tickets = (uint32_t*)(scratch + oTickets);
-        p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = r->numSMs; p.histogramReady = false; p.largeTiles = large;
-        if ((e = launchSort(s, p)) != cudaSuccess) break;
-        e = cudaStreamSynchronize(s);
-    } while (false);
-    if (e != cudaSuccess) st = fail(GSM_ERR_RENDER_FAILED, "gsm_sort_pairs", e);
-    cudaFree(scratch);
-    return st;
+    return gsm::sortPairsStandalone((cudaStream_t)stream, r->numSMs, keys, payload, count, keyBits, numPasses);
 }
 
 gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void* out, uint32_t n) {

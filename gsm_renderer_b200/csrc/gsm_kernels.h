@@ -84,6 +84,10 @@ cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
                               __half* dstSideBySide, int eyeMask, int flipY, TileOut tout);
 
+// error reporting shared with scene.cu (thread-local message behind gsm_last_error_string)
+gsm_status reportFailure(gsm_status s, const char* what, cudaError_t e = cudaSuccess);
+gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* payload, uint32_t count, int keyBits, int numPasses);
+
 // strip-sharded frame (strip.cu)
 cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,
                               const int32_t* bounds, const uint32_t* nTouched, void* out, uint32_t cap, int numSMs);

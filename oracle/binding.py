@@ -77,7 +77,7 @@ STAGE_NAMES = ("project", "compact", "depthSort", "applyScan", "expand", "tileSo
 
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (gcc). Building the checker is not using it."""
-    src = [os.path.join(_HERE, f) for f in ("gsm_oracle.c", "gsm_oracle.h", "gsmo_math.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("gsm_oracle.c", "gsm_oracle_ply.c", "gsm_oracle.h", "gsmo_math.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -273,3 +273,71 @@ class OracleFrame:
                                  C.byref(cam), C.c_uint32(width), C.c_uint32(height), C.c_int(int(flip_y)),
                                  _p(scratch), _p(dst))
         return dst, scratch
+
+
+# ---------------------------------------------------------------- scene ingest (gsm_oracle_ply.c)
+class PlyResult(C.Structure):
+    _fields_ = [("count", C.c_uint32), ("shComponents", C.c_uint32), ("harmonicsStride", C.c_uint32),
+                ("compressed", C.c_uint32), ("scaleIsLogSpace", C.c_uint32), ("opacityIsLogit", C.c_uint32),
+                ("center", C.c_float * 3), ("boundsCenter", C.c_float * 3), ("boundsRadius", C.c_float)]
+
+
+PLY_ERRORS = {1: "invalidHeader", 2: "unsupportedFormat", 3: "missingVertexElement", 4: "missingRequiredProperties",
+              5: "listPropertiesNotSupported", 6: "insufficientData", 7: "missingChunkElement", 8: "invalidHeader"}
+
+
+def ply_load(data: bytes):
+    """PLYLoader.load restated (oracle). Returns dict(pos, scale, rot, opacity, harmonics, result) or raises ValueError(case)."""
+    l = lib()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    n = C.c_uint32(0)
+    shp = C.c_uint32(0)
+    l.gsmo_ply_probe.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    rc = l.gsmo_ply_probe(buf.ctypes.data, buf.size, C.byref(n), C.byref(shp))
+    if rc:
+        raise ValueError(PLY_ERRORS.get(rc, str(rc)))
+    cnt = max(int(n.value), 1)
+    pos = np.zeros((cnt, 3), np.float32); scale = np.zeros((cnt, 3), np.float32)
+    rot = np.zeros((cnt, 4), np.float32); op = np.zeros(cnt, np.float32)
+    har = np.zeros(cnt * max(int(shp.value), 3), np.float32)
+    res = PlyResult()
+    l.gsmo_ply_load.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 5 + [C.c_size_t, C.POINTER(PlyResult)]
+    rc = l.gsmo_ply_load(buf.ctypes.data, buf.size, _p(pos), _p(scale), _p(rot), _p(op), _p(har), har.size, C.byref(res))
+    if rc:
+        raise ValueError(PLY_ERRORS.get(rc, str(rc)))
+    m, hs = int(res.count), int(res.harmonicsStride)
+    return {"pos": pos[:m], "scale": scale[:m], "rot": rot[:m], "opacity": op[:m],
+            "harmonics": har[:m * hs].reshape(m, hs) if hs else np.zeros((m, 0), np.float32), "result": res}
+
+
+def pack_gaussians(rec, half: bool, order=None) -> np.ndarray:
+    l = lib()
+    m = len(rec["pos"])
+    out = np.zeros((m, 32 if half else 48), np.uint8)
+    l.gsmo_pack_gaussians.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]
+    o = None if order is None else np.ascontiguousarray(order, np.uint32)
+    l.gsmo_pack_gaussians(_p(np.ascontiguousarray(rec["pos"])), _p(np.ascontiguousarray(rec["scale"])),
+                          _p(np.ascontiguousarray(rec["rot"])), _p(np.ascontiguousarray(rec["opacity"])), m, _p(o), int(half), _p(out))
+    return out
+
+
+def pack_harmonics(har: np.ndarray, half: bool, order=None) -> np.ndarray:
+    l = lib()
+    m, hs = har.shape
+    out = np.zeros((m, hs), np.float16 if half else np.float32)
+    if m * hs == 0:
+        return out
+    l.gsmo_pack_harmonics.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]
+    o = None if order is None else np.ascontiguousarray(order, np.uint32)
+    l.gsmo_pack_harmonics(_p(np.ascontiguousarray(har)), m, hs, _p(o), int(half), _p(out))
+    return out
+
+
+def morton_order(pos: np.ndarray):
+    l = lib()
+    n = len(pos)
+    codes = np.zeros(n, np.uint64)
+    order = np.zeros(n, np.uint32)
+    l.gsmo_morton_order.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    l.gsmo_morton_order(_p(np.ascontiguousarray(pos, np.float32)), n, _p(codes), _p(order))
+    return codes, order

@@ -20,9 +20,12 @@ def native():
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "gsm", "gsm.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(gsm_[a-z0-9_]+)\s*\(", src)))
+    syms = set()
+    for h in ("gsm.h", "gsm_scene.h"):  # every header of the boundary that declares entry points
+        src = open(os.path.join(ROOT, "include", "gsm", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms |= set(re.findall(r"\b(gsm_[a-z0-9_]+)\s*\(", src))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol(native):
@@ -39,6 +42,7 @@ def test_header_compiles_as_c_and_layouts_match():
     # the RendererTypes restatement must be plain C (SwiftPM C target) with the reference's sizes
     code = r'''
 #include "gsm/gsm.h"
+#include "gsm/gsm_scene.h"
 #include "gsm/gsm_types.h"
 #include <stdio.h>
 #include <stddef.h>
@@ -46,7 +50,7 @@ int main(void){
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(GSMPackedWorldGaussian), sizeof(GSMPackedWorldGaussianHalf),
     sizeof(GSMGaussianRenderData), sizeof(GSMStereoTiledRenderData), sizeof(GSMDepthFirstHeader),
     sizeof(GSMStereoCameraUniforms), offsetof(GSMStereoCameraUniforms, rightViewMatrix), offsetof(GSMStereoCameraUniforms, sceneTransform));
-  printf("%zu %zu\n", sizeof(gsm_config), sizeof(gsm_camera));
+  printf("%zu %zu %zu %zu\n", sizeof(gsm_config), sizeof(gsm_camera), sizeof(gsm_ply_info), sizeof(gsm_scene_info));
   return 0; }
 '''
     import tempfile
@@ -60,6 +64,7 @@ int main(void){
     assert out[:8] == ["48", "32", "16", "32", "32", "416", "160", "352"]
     from gsm_renderer_b200 import _native
     assert int(out[8]) == C.sizeof(_native.gsm_config) and int(out[9]) == C.sizeof(_native.gsm_camera)
+    assert int(out[10]) == C.sizeof(_native.gsm_ply_info) and int(out[11]) == C.sizeof(_native.gsm_scene_info)
 
 
 def test_config_defaults_match_reference(native):
