@@ -31,21 +31,37 @@ gsm_status reportFailure(gsm_status s, const char* what, cudaError_t e) { return
 
 // Standalone stable pair sort on the current device (gsm_sort_pairs, the Morton pre-sort of scene.cu): scratch is
 // allocated per call and the stream is synchronised before it is freed.
-gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* payload, uint32_t count, int keyBits, int numPasses) {
-    if (count == 0) return GSM_OK;
-    const bool large = keyBits == 32 && count >= 3000000u;
-    const uint32_t tile = sortTileSize(keyBits, large);
-    const uint32_t tiles = (count + tile - 1) / tile;
+struct SortScratchLayout { size_t oHist, oTickets, oStatus, oGStatus, oK1, oV1, total; uint32_t tiles; bool large; };
+static SortScratchLayout sortScratchLayout(uint32_t count, int keyBits, int numPasses) {
+    SortScratchLayout L;
+    L.large = keyBits == 32 && count >= 3000000u;
+    const uint32_t tile = sortTileSize(keyBits, L.large);
+    L.tiles = (count + tile - 1) / tile;
     const size_t keyBytes = (size_t)count * (keyBits / 8);
     auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     // scratch: [count u32][hist 4*256][tickets 4][status passes*tiles*256][k1][v1]
-    const size_t oHist = 256, oTickets = oHist + 4 * 256 * 4, oStatus = up(oTickets + 16, 256);
-    const size_t oGStatus = up(oStatus + (size_t)numPasses * tiles * 256 * 4, 256);
-    const size_t oK1 = up(oGStatus + (size_t)numPasses * ((tiles + 15) / 16) * 256 * 4, 256), oV1 = up(oK1 + keyBytes, 256);
-    const size_t total = oV1 + (size_t)count * 4;
-    char* scratch = nullptr;
-    cudaError_t e = cudaMalloc((void**)&scratch, total);
-    if (e != cudaSuccess) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "sort scratch", e);
+    L.oHist = 256; L.oTickets = L.oHist + 4 * 256 * 4; L.oStatus = up(L.oTickets + 16, 256);
+    L.oGStatus = up(L.oStatus + (size_t)numPasses * L.tiles * 256 * 4, 256);
+    L.oK1 = up(L.oGStatus + (size_t)numPasses * ((L.tiles + 15) / 16) * 256 * 4, 256);
+    L.oV1 = up(L.oK1 + keyBytes, 256);
+    L.total = up(L.oV1 + (size_t)count * 4, 256);
+    return L;
+}
+size_t sortScratchBytes(uint32_t count, int keyBits, int numPasses) { return sortScratchLayout(count, keyBits, numPasses).total; }
+
+gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* payload, uint32_t count, int keyBits, int numPasses,
+                               void* callerScratch) {
+    if (count == 0) return GSM_OK;
+    const SortScratchLayout L = sortScratchLayout(count, keyBits, numPasses);
+    const bool large = L.large;
+    const uint32_t tiles = L.tiles;
+    const size_t oHist = L.oHist, oTickets = L.oTickets, oStatus = L.oStatus, oGStatus = L.oGStatus, oK1 = L.oK1, oV1 = L.oV1;
+    char* scratch = (char*)callerScratch;
+    cudaError_t e = cudaSuccess;
+    if (!scratch) {
+        e = cudaMalloc((void**)&scratch, L.total);
+        if (e != cudaSuccess) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "sort scratch", e);
+    }
     gsm_status st = GSM_OK;
     do {
         if ((e = cudaMemsetAsync(scratch, 0, oK1, s)) != cudaSuccess) break;
@@ -56,10 +72,10 @@ gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* pay
         p.hist = (uint32_t*)(scratch + oHist); p.status = (uint32_t*)(scratch + oStatus); p.gstatus = (uint32_t*)(scratch + oGStatus); p.tickets = (uint32_t*)(scratch + oTickets);
         p.tilesCap = tiles; p.keyBits = keyBits; p.numPasses = numPasses; p.numSMs = numSMs; p.histogramReady = false; p.largeTiles = large;
         if ((e = launchSort(s, p)) != cudaSuccess) break;
-        e = cudaStreamSynchronize(s);
+        if (!callerScratch) e = cudaStreamSynchronize(s);  // the scratch is freed below; a caller's scratch outlives the call
     } while (false);
     if (e != cudaSuccess) st = fail(GSM_ERR_RENDER_FAILED, "sort pairs", e);
-    cudaFree(scratch);
+    if (!callerScratch) cudaFree(scratch);
     return st;
 }
 }

@@ -86,7 +86,10 @@ cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const
 
 // error reporting shared with scene.cu (thread-local message behind gsm_last_error_string)
 gsm_status reportFailure(gsm_status s, const char* what, cudaError_t e = cudaSuccess);
-gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* payload, uint32_t count, int keyBits, int numPasses);
+// callerScratch: optional device buffer of sortScratchBytes(...) bytes (then nothing is allocated and the stream is not synchronised)
+size_t sortScratchBytes(uint32_t count, int keyBits, int numPasses);
+gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* payload, uint32_t count, int keyBits, int numPasses,
+                               void* callerScratch = nullptr);
 
 // strip-sharded frame (strip.cu)
 cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,

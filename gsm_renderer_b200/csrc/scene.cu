@@ -3,10 +3,12 @@
 // (:692-719), recentering (:496-503, :722-730), GaussianSceneBuilder.bounds (Scene.swift:159-190), the packing into
 // PackedWorldGaussian(+Half) (PLYBenchmarkTests.swift:139-149) and the Morton pre-sort (Scene.swift:47-138).
 //
-// The header is parsed on the host (text, a few hundred bytes); the body is copied to the device once and decoded there:
-// kernel 1 decodes every vertex into float records + planar SH and reduces the position bounds, kernel 2 recenters, packs
-// and reduces the scene radius. Placeholder vertices (PLYLoader.swift:658-660) are rare, so their order-preserving
-// compaction is a third kernel that only runs when kernel 1 found any. Arithmetic is the canonical set of gsm_dmath.cuh
+// The header is parsed on the host (text, a few hundred bytes); the body is copied to the device once and decoded there.
+// Standard layout: pass A reads the seven properties that decide the placeholder flags and the position bounds; pass B
+// decodes, recenters, packs and writes the renderer's buffers directly (records and SH rows staged through shared memory
+// so that both the file and the outputs move in coalesced 16-byte accesses) and reduces the scene radius. The compressed
+// layout (16 B per vertex) decodes into float records first. Placeholder vertices (PLYLoader.swift:658-660) are rare, so
+// their order-preserving compaction index is a kernel that only runs when pass A found any. Arithmetic is the canonical set of gsm_dmath.cuh
 // (IEEE + - * / sqrt, Cephes exp), the same definitions the CPU oracle uses, so the outputs are compared bit for bit.
 #include <cctype>
 #include <cstdlib>
@@ -205,17 +207,18 @@ __device__ __forceinline__ void reduceBounds(SceneScratch* sc, bool valid, float
             hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
         }
         if ((threadIdx.x & 31u) == 0u) {
-            if (lo != 0xFFFFFFFFu) atomicMin(&sc->minKey[k], lo);
-            if (hi != 0u) atomicMax(&sc->maxKey[k], hi);
+            // same-address atomics cost ~0.7 ns each (tools/micro/atomic_rate.cu): 6 per warp would dominate the kernel, and
+            // after the first few warps almost none of them changes the bounds -- look before updating
+            if (lo < *(volatile uint32_t*)&sc->minKey[k]) atomicMin(&sc->minKey[k], lo);
+            if (hi > *(volatile uint32_t*)&sc->maxKey[k]) atomicMax(&sc->maxKey[k], hi);
         }
     }
 }
 
-// one thread per vertex: float records (SoA, slot = vertex index) + planar SH + keep flag + bounds
-__global__ void __launch_bounds__(256) ply_decode_standard_kernel(const unsigned char* __restrict__ body, const __grid_constant__ StandardLayout L,
-                                                                  float* __restrict__ pos, float* __restrict__ scale,
-                                                                  float* __restrict__ rot, float* __restrict__ opacity,
-                                                                  float* __restrict__ sh, uint8_t* __restrict__ keep, SceneScratch* sc) {
+// Standard layout, pass A: keep flags (placeholders, PLYLoader.swift:658-660) and the position bounds. Reads only the
+// seven properties it needs -- a fraction of each record's sectors.
+__global__ void __launch_bounds__(256) ply_scan_standard_kernel(const unsigned char* __restrict__ body, const __grid_constant__ StandardLayout L,
+                                                                uint8_t* __restrict__ keep, SceneScratch* sc) {
     const uint32_t v = blockIdx.x * 256u + threadIdx.x;
     bool kept = false;
     float px = 0, py = 0, pz = 0;
@@ -223,34 +226,132 @@ __global__ void __launch_bounds__(256) ply_decode_standard_kernel(const unsigned
         const unsigned char* rec = body + (size_t)v * L.stride;
         auto get = [&](int i) { return L.off[i] >= 0 ? readPlyProp(rec + L.off[i], L.type[i]) : 0.0f; };
         const float s0 = get(3), s1 = get(4), s2 = get(5), opRaw = get(10);
-        kept = !(s0 == 2.0f && s1 == 2.0f && s2 == 2.0f && fabsf(opRaw - 4.8402f) < 0.001f);  // PLYLoader.swift:658-660
+        kept = !(s0 == 2.0f && s1 == 2.0f && s2 == 2.0f && fabsf(opRaw - 4.8402f) < 0.001f);
         keep[v] = kept ? 1 : 0;
-        if (kept) {
-            px = get(0); py = get(1); pz = get(2);
-            pos[3 * (size_t)v] = px; pos[3 * (size_t)v + 1] = py; pos[3 * (size_t)v + 2] = pz;
-            if (L.scaleIsLogSpace) { scale[3 * (size_t)v] = dexp(s0); scale[3 * (size_t)v + 1] = dexp(s1); scale[3 * (size_t)v + 2] = dexp(s2); }
-            else { scale[3 * (size_t)v] = s0; scale[3 * (size_t)v + 1] = s1; scale[3 * (size_t)v + 2] = s2; }
-            const float qx = get(7), qy = get(8), qz = get(9), qw = get(6);  // simd_quatf(ix: rot_1, iy: rot_2, iz: rot_3, r: rot_0)
-            const float inv = 1.0f / sqrtf(((qx * qx + qy * qy) + qz * qz) + qw * qw);
-            rot[4 * (size_t)v] = qx * inv; rot[4 * (size_t)v + 1] = qy * inv; rot[4 * (size_t)v + 2] = qz * inv; rot[4 * (size_t)v + 3] = qw * inv;
-            opacity[v] = L.opacityIsLogit ? 1.0f / (1.0f + dexp(-opRaw)) : opRaw;
-            if (L.shComponents > 0) {  // PLY [DC_R, DC_G, DC_B, R1.., G1.., B1..] -> shader [R0.., G0.., B0..] (PLYLoader.swift:700-719)
-                float* dst = sh + (size_t)v * L.shProps;
-                const uint32_t K = L.shComponents, hoc = K - 1u;
-                for (uint32_t k = 3u * K; k < L.shProps; ++k) dst[k] = 0.0f;  // property counts that are not a multiple of 3
-                for (uint32_t k = 0; k < 3u + 3u * hoc; ++k) {
-                    const float val = readPlyProp(rec + L.shOff[k], L.shType[k]);
-                    uint32_t d;
-                    if (k < 3u) d = k * K;
-                    else { const uint32_t r = k - 3u, ch = r / hoc, c = r - ch * hoc; d = ch * K + 1u + c; }
-                    dst[d] = val;
-                }
-            }
+        if (kept) { px = get(0); py = get(1); pz = get(2); }
+    }
+    const unsigned lost = __ballot_sync(0xFFFFFFFFu, v < L.count && !kept);
+    if ((threadIdx.x & 31u) == 0u && lost) atomicAdd(&sc->placeholders, (uint32_t)__popc(lost));
+    reduceBounds(sc, kept, px, py, pz);
+}
+
+// the recentering shift and the center of the recentered bounds, from the reduced keys; every thread (and the host)
+// derives them with the same float arithmetic
+struct SceneCenters { float c[3], c2[3]; bool shift; };
+__host__ __device__ inline float sceneKeyToFloat(uint32_t k) {
+    const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+__host__ __device__ inline SceneCenters sceneCenters(const uint32_t minKey[3], const uint32_t maxKey[3]) {
+    SceneCenters r;
+    float mn[3], mx[3];
+    const bool any = minKey[0] != 0xFFFFFFFFu;
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = any ? sceneKeyToFloat(minKey[k]) : 0.0f;
+        mx[k] = any ? sceneKeyToFloat(maxKey[k]) : 0.0f;
+        r.c[k] = (mn[k] + mx[k]) * 0.5f;
+    }
+    r.shift = sqrtf((r.c[0] * r.c[0] + r.c[1] * r.c[1]) + r.c[2] * r.c[2]) > 1e-6f;  // PLYLoader.swift:725
+    for (int k = 0; k < 3; ++k) {
+        if (!r.shift) r.c[k] = 0.0f;
+        // bounds of the recentered records: subtracting the same c is monotonic, so min' = min - c and max' = max - c exactly
+        const float mn2 = r.shift ? mn[k] - r.c[k] : mn[k], mx2 = r.shift ? mx[k] - r.c[k] : mx[k];
+        r.c2[k] = (mn2 + mx2) * 0.5f;
+    }
+    return r;
+}
+
+// Standard layout, pass B: decode, recenter, pack and write -- no intermediate arrays. A CTA stages its 128 consecutive
+// records in shared memory with coalesced 16-byte loads (a thread-per-record read of 248-byte records touches 32 lines
+// per instruction and re-fetched the file twice from DRAM, ncu r1_scene) and stages its planar SH rows the same way on the
+// way out. Also reduces the scene radius (Scene.swift:179-188).
+constexpr uint32_t kPlyBlock = 128;
+template <bool HALF>
+__global__ void __launch_bounds__(kPlyBlock) ply_decode_pack_standard_kernel(const unsigned char* __restrict__ body, const __grid_constant__ StandardLayout L,
+                                                                             const uint8_t* __restrict__ keep, const uint32_t* __restrict__ dstIndex,
+                                                                             void* __restrict__ gaussiansOut, void* __restrict__ harmonicsOut,
+                                                                             SceneScratch* sc, uint32_t stageRecords) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const uint32_t first = blockIdx.x * kPlyBlock, v = first + threadIdx.x;
+    const uint32_t nHere = min(kPlyBlock, L.count - first);
+    const unsigned char* rec = body + (size_t)v * L.stride;
+    if (stageRecords) {  // the body buffer is 16-byte aligned and a block starts at 128 * stride bytes: always a multiple of 16
+        const size_t startByte = (size_t)first * L.stride, bytes = (size_t)nHere * L.stride;
+        const size_t vecs = bytes / 16u;
+        const uint4* src = reinterpret_cast<const uint4*>(body + startByte);
+        for (size_t i = threadIdx.x; i < vecs; i += kPlyBlock) reinterpret_cast<uint4*>(s_dyn)[i] = __ldcs(src + i);
+        for (size_t i = vecs * 16u + threadIdx.x; i < bytes; i += kPlyBlock) s_dyn[i] = body[startByte + i];
+        __syncthreads();
+        rec = s_dyn + (size_t)threadIdx.x * L.stride;
+    }
+    const SceneCenters cen = sceneCenters(sc->minKey, sc->maxKey);
+    float r = 0.0f;
+    const bool kept = v < L.count && keep[v];
+    const uint32_t shStride = L.shComponents > 0 ? L.shProps : 0u;
+    float* shStage = reinterpret_cast<float*>(s_dyn + (((size_t)(stageRecords ? kPlyBlock : 0) * L.stride + 15u) & ~(size_t)15u));
+    const bool stageSh = dstIndex == nullptr && shStride > 0;  // contiguous destination rows: stage and write coalesced
+    if (kept) {
+        auto get = [&](int i) { return L.off[i] >= 0 ? readPlyProp(rec + L.off[i], L.type[i]) : 0.0f; };
+        const uint32_t d = dstIndex ? dstIndex[v] : v;
+        float p[3] = {get(0), get(1), get(2)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = cen.shift ? p[k] - cen.c[k] : p[k];
+        const float s0 = get(3), s1 = get(4), s2 = get(5), opRaw = get(10);
+        const float sx = L.scaleIsLogSpace ? dexp(s0) : s0, sy = L.scaleIsLogSpace ? dexp(s1) : s1, sz = L.scaleIsLogSpace ? dexp(s2) : s2;
+        float qx = get(7), qy = get(8), qz = get(9), qw = get(6);  // simd_quatf(ix: rot_1, iy: rot_2, iz: rot_3, r: rot_0)
+        const float inv = 1.0f / sqrtf(((qx * qx + qy * qy) + qz * qz) + qw * qw);
+        qx *= inv; qy *= inv; qz *= inv; qw *= inv;
+        const float op = L.opacityIsLogit ? 1.0f / (1.0f + dexp(-opRaw)) : opRaw;
+        if (HALF) {
+            GSMPackedWorldGaussianHalf g;
+            g.px = p[0]; g.py = p[1]; g.pz = p[2];
+            g.opacity = __half_as_ushort(__float2half_rn(op));
+            g.sx = __half_as_ushort(__float2half_rn(sx)); g.sy = __half_as_ushort(__float2half_rn(sy)); g.sz = __half_as_ushort(__float2half_rn(sz));
+            g.rx = __half_as_ushort(__float2half_rn(qx)); g.ry = __half_as_ushort(__float2half_rn(qy));
+            g.rz = __half_as_ushort(__float2half_rn(qz)); g.rw = __half_as_ushort(__float2half_rn(qw));
+            g._pad0 = 0; g._pad1 = 0;
+            uint4* o = reinterpret_cast<uint4*>(gaussiansOut) + 2 * (size_t)d;
+            o[0] = reinterpret_cast<const uint4*>(&g)[0];
+            o[1] = reinterpret_cast<const uint4*>(&g)[1];
         } else {
-            atomicAdd(&sc->placeholders, 1u);
+            float4* o = reinterpret_cast<float4*>(gaussiansOut) + 3 * (size_t)d;
+            o[0] = make_float4(p[0], p[1], p[2], op);
+            o[1] = make_float4(sx, sy, sz, 0.0f);
+            o[2] = make_float4(qx, qy, qz, qw);
+        }
+        if (shStride > 0) {  // PLY [DC_R, DC_G, DC_B, R1.., G1.., B1..] -> shader [R0.., G0.., B0..] (PLYLoader.swift:700-719)
+            const uint32_t K = L.shComponents, hoc = K - 1u;
+            for (uint32_t k = 0; k < shStride; ++k) {
+                // destination slot k <- source property: channel ch = k / K, coefficient c = k % K
+                float val = 0.0f;
+                if (k < 3u * K) {
+                    const uint32_t ch = k / K, c = k - ch * K;
+                    const uint32_t src = c == 0u ? ch : 3u + ch * hoc + (c - 1u);
+                    val = readPlyProp(rec + L.shOff[src], L.shType[src]);
+                }
+                if (stageSh) shStage[(size_t)threadIdx.x * shStride + k] = val;
+                else if (HALF) reinterpret_cast<__half*>(harmonicsOut)[(size_t)d * shStride + k] = __float2half_rn(val);
+                else reinterpret_cast<float*>(harmonicsOut)[(size_t)d * shStride + k] = val;
+            }
+        }
+        const float ox = p[0] - cen.c2[0], oy = p[1] - cen.c2[1], oz = p[2] - cen.c2[2];
+        r = sqrtf((ox * ox + oy * oy) + oz * oz) + dmax(sx, dmax(sy, sz));
+        if (!(r == r)) r = 0.0f;  // a NaN candidate loses (max semantics of gsm_dmath.cuh)
+    }
+    if (stageSh) {
+        __syncthreads();
+        const size_t total = (size_t)nHere * shStride, base = (size_t)first * shStride;
+        for (size_t i = threadIdx.x; i < total; i += kPlyBlock) {
+            if (HALF) reinterpret_cast<__half*>(harmonicsOut)[base + i] = __float2half_rn(shStage[i]);
+            else reinterpret_cast<float*>(harmonicsOut)[base + i] = shStage[i];
         }
     }
-    reduceBounds(sc, kept, px, py, pz);
+    uint32_t rk = __float_as_uint(dmax(r, 0.0f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rk = max(rk, __shfl_xor_sync(0xFFFFFFFFu, rk, o));
+    if ((threadIdx.x & 31u) == 0u && rk > *(volatile uint32_t*)&sc->radiusKey) atomicMax(&sc->radiusKey, rk);
 }
 
 struct CompressedLayout {
@@ -344,22 +445,10 @@ __global__ void __launch_bounds__(256) scene_pack_kernel(const float* __restrict
                                                          void* __restrict__ gaussiansOut, void* __restrict__ harmonicsOut, SceneScratch* sc) {
     const uint32_t v = blockIdx.x * 256u + threadIdx.x;
     // the bounds are complete (previous kernel); every thread derives the same center with the same arithmetic
-    float mn[3], mx[3], c[3], c2[3];
-    bool any = sc->minKey[0] != 0xFFFFFFFFu;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        mn[k] = any ? floatFromOrderKey(sc->minKey[k]) : 0.0f;
-        mx[k] = any ? floatFromOrderKey(sc->maxKey[k]) : 0.0f;
-        c[k] = (mn[k] + mx[k]) * 0.5f;
-    }
-    const bool shift = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]) > 1e-6f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (!shift) c[k] = 0.0f;
-        // bounds of the recentered records: subtracting the same c is monotonic, so min' = min - c and max' = max - c exactly
-        const float mn2 = shift ? mn[k] - c[k] : mn[k], mx2 = shift ? mx[k] - c[k] : mx[k];
-        c2[k] = (mn2 + mx2) * 0.5f;
-    }
+    const SceneCenters cen = sceneCenters(sc->minKey, sc->maxKey);
+    const bool shift = cen.shift;
+    const float* c = cen.c;
+    const float* c2 = cen.c2;
     float r = 0.0f;
     if (v < n && keep[v]) {
         const uint32_t d = dstIndex ? dstIndex[v] : v;
@@ -397,7 +486,7 @@ __global__ void __launch_bounds__(256) scene_pack_kernel(const float* __restrict
     uint32_t rk = __float_as_uint(dmax(r, 0.0f));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rk = max(rk, __shfl_xor_sync(0xFFFFFFFFu, rk, o));
-    if ((threadIdx.x & 31u) == 0u && rk) atomicMax(&sc->radiusKey, rk);
+    if ((threadIdx.x & 31u) == 0u && rk > *(volatile uint32_t*)&sc->radiusKey) atomicMax(&sc->radiusKey, rk);
 }
 
 // ---------------------------------------------------------------- device: Morton pre-sort
@@ -640,11 +729,13 @@ gsm_status gsm_ply_load(int device, void* stream, const void* fileBytes, size_t 
     {
         // the body lands 16-byte aligned on the device whatever the header length was
         SCENE_CUDA(cudaMalloc((void**)&dBody, bodyBytes + 16), "scene: body buffer");
-        SCENE_CUDA(cudaMalloc((void**)&dPos, nn * 12), "scene: records");
-        SCENE_CUDA(cudaMalloc((void**)&dScale, nn * 12), "scene: records");
-        SCENE_CUDA(cudaMalloc((void**)&dRot, nn * 16), "scene: records");
-        SCENE_CUDA(cudaMalloc((void**)&dOp, nn * 4), "scene: records");
-        SCENE_CUDA(cudaMalloc((void**)&dSh, nn * (shStride ? shStride : 1) * 4), "scene: harmonics");
+        if (compressed) {  // the compressed layout decodes into float records first (16 B in, 60 B out per vertex)
+            SCENE_CUDA(cudaMalloc((void**)&dPos, nn * 12), "scene: records");
+            SCENE_CUDA(cudaMalloc((void**)&dScale, nn * 12), "scene: records");
+            SCENE_CUDA(cudaMalloc((void**)&dRot, nn * 16), "scene: records");
+            SCENE_CUDA(cudaMalloc((void**)&dOp, nn * 4), "scene: records");
+            SCENE_CUDA(cudaMalloc((void**)&dSh, nn * (shStride ? shStride : 1) * 4), "scene: harmonics");
+        }
         SCENE_CUDA(cudaMalloc((void**)&dKeep, nn), "scene: flags");
         SCENE_CUDA(cudaMalloc((void**)&dScratch, sizeof(SceneScratch)), "scene: scratch");
         initScratch(hs);
@@ -652,7 +743,7 @@ gsm_status gsm_ply_load(int device, void* stream, const void* fileBytes, size_t 
         if (bodyBytes) SCENE_CUDA(cudaMemcpyAsync(dBody, data + h.bodyStart, bodyBytes, cudaMemcpyHostToDevice, s), "scene: body upload");
         if (n > 0) {
             if (compressed) ply_decode_compressed_kernel<<<blocks, 256, 0, s>>>(dBody, CL, dPos, dScale, dRot, dOp, dSh, dKeep, dScratch);
-            else ply_decode_standard_kernel<<<blocks, 256, 0, s>>>(dBody, SL, dPos, dScale, dRot, dOp, dSh, dKeep, dScratch);
+            else ply_scan_standard_kernel<<<blocks, 256, 0, s>>>(dBody, SL, dKeep, dScratch);
             SCENE_CUDA(cudaGetLastError(), "scene: decode kernel");
         }
         SCENE_CUDA(cudaMemcpyAsync(&hs, dScratch, sizeof(hs), cudaMemcpyDeviceToHost, s), "scene: scratch readback");
@@ -670,29 +761,40 @@ gsm_status gsm_ply_load(int device, void* stream, const void* fileBytes, size_t 
             SCENE_CUDA(cudaGetLastError(), "scene: compaction kernel");
             kept = n - hs.placeholders;
         }
-        if (n > 0) {
+        if (n > 0 && compressed) {
             if (half) scene_pack_kernel<true><<<blocks, 256, 0, s>>>(dPos, dScale, dRot, dOp, dSh, dKeep, dIndex, n, shStride, gaussiansOut, harmonicsOut, dScratch);
             else scene_pack_kernel<false><<<blocks, 256, 0, s>>>(dPos, dScale, dRot, dOp, dSh, dKeep, dIndex, n, shStride, gaussiansOut, harmonicsOut, dScratch);
             SCENE_CUDA(cudaGetLastError(), "scene: pack kernel");
+        } else if (n > 0) {
+            // shared memory: the block's records (if they fit) + its planar SH rows (when the destination rows are contiguous)
+            const size_t recBytes = ((size_t)kPlyBlock * SL.stride + 15u) & ~(size_t)15u;
+            const size_t shBytes = (dIndex == nullptr) ? (size_t)kPlyBlock * shStride * 4u : 0u;
+            const uint32_t stage = (recBytes + shBytes <= 160u * 1024u) ? 1u : 0u;
+            const size_t smem = (stage ? recBytes : 0u) + shBytes;
+            const uint32_t pblocks = (n + kPlyBlock - 1u) / kPlyBlock;
+            if (half) {
+                SCENE_CUDA(cudaFuncSetAttribute(ply_decode_pack_standard_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "scene: shared memory opt-in");
+                ply_decode_pack_standard_kernel<true><<<pblocks, kPlyBlock, smem, s>>>(dBody, SL, dKeep, dIndex, gaussiansOut, harmonicsOut, dScratch, stage);
+            } else {
+                SCENE_CUDA(cudaFuncSetAttribute(ply_decode_pack_standard_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "scene: shared memory opt-in");
+                ply_decode_pack_standard_kernel<false><<<pblocks, kPlyBlock, smem, s>>>(dBody, SL, dKeep, dIndex, gaussiansOut, harmonicsOut, dScratch, stage);
+            }
+            SCENE_CUDA(cudaGetLastError(), "scene: decode+pack kernel");
         }
         SCENE_CUDA(cudaMemcpyAsync(&hs, dScratch, sizeof(hs), cudaMemcpyDeviceToHost, s), "scene: scratch readback");
         SCENE_CUDA(cudaStreamSynchronize(s), "scene: pack sync");
         info->count = kept;
         // center / bounds on the host from the reduced keys, with the same float arithmetic as the kernels
-        auto fromKey = [](uint32_t k) { uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; float f; std::memcpy(&f, &b, 4); return f; };
         if (kept > 0 && hs.minKey[0] != 0xFFFFFFFFu) {
-            float mn[3], mx[3], c[3];
-            for (int k = 0; k < 3; ++k) { mn[k] = fromKey(hs.minKey[k]); mx[k] = fromKey(hs.maxKey[k]); c[k] = (mn[k] + mx[k]) * 0.5f; }
-            const bool shift = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]) > 1e-6f;
-            float far2 = 0.0f, d[3];
+            const SceneCenters cen = sceneCenters(hs.minKey, hs.maxKey);
+            float d[3];
             for (int k = 0; k < 3; ++k) {
-                if (!shift) c[k] = 0.0f;
-                info->center[k] = c[k];
-                const float mn2 = shift ? mn[k] - c[k] : mn[k], mx2 = shift ? mx[k] - c[k] : mx[k];
-                info->boundsCenter[k] = (mn2 + mx2) * 0.5f;
-                d[k] = mx2 - info->boundsCenter[k];
+                info->center[k] = cen.c[k];
+                info->boundsCenter[k] = cen.c2[k];
+                const float mx = sceneKeyToFloat(hs.maxKey[k]);
+                d[k] = (cen.shift ? mx - cen.c[k] : mx) - cen.c2[k];
             }
-            far2 = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);  // Scene.swift:187
+            const float far2 = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);  // Scene.swift:187
             float r;
             std::memcpy(&r, &hs.radiusKey, 4);
             r = r > far2 ? r : far2;
@@ -720,51 +822,60 @@ gsm_status gsm_scene_morton_sort(int device, void* stream, void* gaussians, void
     const bool half = precision == GSM_PRECISION_FLOAT16;
     const uint32_t recBytes = half ? 32u : 48u, elemBytes = half ? 2u : 4u;
     const uint32_t blocks = (count + 255u) / 256u;
-    uint32_t *dLo = nullptr, *dHi = nullptr, *dIdx = nullptr, *dKey = nullptr;
-    unsigned char *dRec = nullptr, *dSh = nullptr;
-    SceneScratch* dScratch = nullptr;
+    uint32_t *dLo, *dHi, *dIdx, *dKey;
+    unsigned char *dRec, *dSh, *arena = nullptr;
+    void* dSortScratch;
+    SceneScratch* dScratch;
     SceneScratch hs;
     gsm_status st = GSM_OK;
     int numSMs = 1;
     cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, device);
     {
+        // one allocation for every temporary (allocation and free calls would otherwise cost more than the kernels)
         const size_t shBytes = (size_t)count * harmonicsStride * elemBytes;
-        SCENE_CUDA(cudaMalloc((void**)&dLo, (size_t)count * 4), "morton: keys");
-        SCENE_CUDA(cudaMalloc((void**)&dHi, (size_t)count * 4), "morton: keys");
-        SCENE_CUDA(cudaMalloc((void**)&dKey, (size_t)count * 4), "morton: keys");
-        SCENE_CUDA(cudaMalloc((void**)&dIdx, (size_t)count * 4), "morton: index");
-        SCENE_CUDA(cudaMalloc((void**)&dRec, (size_t)count * recBytes), "morton: records");
-        if (shBytes) SCENE_CUDA(cudaMalloc((void**)&dSh, shBytes), "morton: harmonics");
-        SCENE_CUDA(cudaMalloc((void**)&dScratch, sizeof(SceneScratch)), "morton: scratch");
+        auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+        const size_t keyB = up((size_t)count * 4), oHi = keyB, oKey = 2 * keyB, oIdx = 3 * keyB, oRec = 4 * keyB;
+        const size_t oSh = oRec + up((size_t)count * recBytes), oScr = oSh + up(shBytes), oSort = oScr + 256;
+        const size_t total = oSort + sortScratchBytes(count, 32, 4);
+        SCENE_CUDA(cudaMalloc((void**)&arena, total), "morton: temporaries");
+        dLo = (uint32_t*)arena; dHi = (uint32_t*)(arena + oHi); dKey = (uint32_t*)(arena + oKey); dIdx = (uint32_t*)(arena + oIdx);
+        dRec = arena + oRec; dSh = arena + oSh; dScratch = (SceneScratch*)(arena + oScr); dSortScratch = arena + oSort;
         initScratch(hs);
         SCENE_CUDA(cudaMemcpyAsync(dScratch, &hs, sizeof(hs), cudaMemcpyHostToDevice, s), "morton: scratch init");
         scene_position_bounds_kernel<<<blocks, 256, 0, s>>>((const unsigned char*)gaussians, recBytes, count, dScratch);
         scene_morton_codes_kernel<<<blocks, 256, 0, s>>>((const unsigned char*)gaussians, recBytes, count, dScratch, dLo, dHi, dIdx);
         SCENE_CUDA(cudaGetLastError(), "morton: code kernels");
         // stable LSD over the 64-bit code: sort (lo, index), then (hi[index], index)
-        st = sortPairsStandalone(s, numSMs, dLo, dIdx, count, 32, 4);
+        st = sortPairsStandalone(s, numSMs, dLo, dIdx, count, 32, 4, dSortScratch);
         if (st != GSM_OK) goto done;
         gather_u32_kernel<<<blocks, 256, 0, s>>>(dHi, dIdx, count, dKey);
         SCENE_CUDA(cudaGetLastError(), "morton: gather");
-        st = sortPairsStandalone(s, numSMs, dKey, dIdx, count, 32, 4);
+        st = sortPairsStandalone(s, numSMs, dKey, dIdx, count, 32, 4, dSortScratch);
         if (st != GSM_OK) goto done;
         {
             const uint32_t words = recBytes / 4u;
-            const size_t total = (size_t)count * words;
-            permute_records_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint32_t*)gaussians, dIdx, count, words, (uint32_t*)dRec);
+            const size_t totalWords = (size_t)count * words;
+            permute_records_kernel<<<(unsigned)((totalWords + 255) / 256), 256, 0, s>>>((const uint32_t*)gaussians, dIdx, count, words, (uint32_t*)dRec);
             SCENE_CUDA(cudaMemcpyAsync(gaussians, dRec, (size_t)count * recBytes, cudaMemcpyDeviceToDevice, s), "morton: records back");
         }
         if (shBytes) {
-            const size_t total = (size_t)count * harmonicsStride;
-            if (half) permute_halfs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint16_t*)harmonics, dIdx, count, harmonicsStride, (uint16_t*)dSh);
-            else permute_records_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint32_t*)harmonics, dIdx, count, harmonicsStride, (uint32_t*)dSh);
+            const size_t totalElems = (size_t)count * harmonicsStride;
+            const uint32_t rowBytes = harmonicsStride * elemBytes;
+            if (rowBytes % 4u == 0u) {  // whole 32-bit words per row (always for float, and for half rows of even length)
+                const uint32_t words = rowBytes / 4u;
+                const size_t totalWords = (size_t)count * words;
+                permute_records_kernel<<<(unsigned)((totalWords + 255) / 256), 256, 0, s>>>((const uint32_t*)harmonics, dIdx, count, words, (uint32_t*)dSh);
+            } else {
+                permute_halfs_kernel<<<(unsigned)((totalElems + 255) / 256), 256, 0, s>>>((const uint16_t*)harmonics, dIdx, count, harmonicsStride, (uint16_t*)dSh);
+            }
             SCENE_CUDA(cudaMemcpyAsync(harmonics, dSh, shBytes, cudaMemcpyDeviceToDevice, s), "morton: harmonics back");
         }
         SCENE_CUDA(cudaGetLastError(), "morton: permute kernels");
         SCENE_CUDA(cudaStreamSynchronize(s), "morton: sync");
     }
 done:
-    cudaFree(dLo); cudaFree(dHi); cudaFree(dKey); cudaFree(dIdx); cudaFree(dRec); cudaFree(dSh); cudaFree(dScratch);
+    if (st != GSM_OK) cudaStreamSynchronize(s);
+    cudaFree(arena);
     if (prevDevice != device && prevDevice >= 0) cudaSetDevice(prevDevice);
     return st;
 }

@@ -62,6 +62,9 @@ class GaussianDataset:
 
 def _file_bytes(path_or_bytes):
     """(keepalive, address, size) of the whole file in host memory; paths are memory-mapped like Data(.mappedIfSafe)."""
+    if isinstance(path_or_bytes, np.ndarray):  # the file already in host memory (e.g. a pinned buffer)
+        a = np.ascontiguousarray(path_or_bytes).view(np.uint8).reshape(-1)
+        return a, a.ctypes.data, a.size
     if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
         a = np.frombuffer(path_or_bytes, dtype=np.uint8)
         return a, a.ctypes.data, a.size
