@@ -323,7 +323,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     GSM_CUDA(launchSort(s, tp), "tile sort");
     recordStage(r, s, 5);
     // stage 7
-    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, r->numSMs), "tile ranges");
+    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.maxInstances), "tile ranges");
     recordStage(r, s, 6);
     return GSM_OK;
 }
@@ -446,7 +446,8 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
 
     recordStage(r, s, 0);
     // step 0: reset state + counters (DFR.swift:259-272)
-    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    const bool zeroInKernel = gaussianCount >= 65536u;  // enough CTAs to clear the region in a few stores per thread
+    if (!zeroInKernel) GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
     // step 1 + 1.25 + 1.5
     MonoCam mc;
     fillMonoCam(mc, camera, gaussianCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
@@ -458,6 +459,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
+    if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
     recordStage(r, s, 1);
@@ -497,7 +499,8 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = true;
 
     recordStage(r, s, 0);
-    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    const bool zeroInKernel = gaussianCount >= 65536u;  // enough CTAs to clear the region in a few stores per thread
+    if (!zeroInKernel) GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
     // makeStereoCameraUniforms (DFR.swift:554-591): near/far from the left eye, sceneTransform = identity for sideBySide
     StereoCam sc;
     memcpy(sc.leftView, leftEye->viewMatrix, 64); memcpy(sc.leftProj, leftEye->projectionMatrix, 64);
@@ -519,6 +522,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
     po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
+    if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
     recordStage(r, s, 1);

@@ -16,6 +16,8 @@ struct ProjectOut {
     uint32_t* preDepthKeys;       // per gid, before compaction (the reference aliases the sort scratch for it, DFR.swift:282)
     uint32_t* depthKeys;          // compacted, ascending gid
     int32_t* primitiveIndices;
+    uint4* zeroBase = nullptr;    // if set, the projection kernel clears the frame's zero region (zeroVecs 16-byte words) itself
+    size_t zeroVecs = 0;
     uint32_t maxOut;              // capacity of the compacted arrays (maxGaussians)
     GSMDepthFirstHeader* header;  // if set, the projection's last block also writes the frame header (no finalize kernel)
     uint32_t maxInstances;
@@ -73,7 +75,7 @@ cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, co
 
 // tile ranges (ranges.cu)
 cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,
-                             uint32_t tileCount, uint32_t* lowerBounds, int numSMs);
+                             uint32_t tileCount, uint32_t* lowerBounds, uint32_t capInstances);
 
 // blend (blend.cu). Each tile's CTA also writes its GaussianHeader and appends itself to the active list.
 struct TileOut { GSMGaussianHeader* tileHeaders; uint32_t* activeTiles; uint32_t* activeTileCount; };

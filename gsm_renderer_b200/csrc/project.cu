@@ -402,6 +402,15 @@ __device__ __forceinline__ V3 computeSHColor(const void* harmonics, uint32_t gid
     return color;
 }
 
+// The per-frame zero region (frame state, prefix and status words) is cleared by the frame's first kernel when its grid is
+// large enough to do it in a few stores per thread: one operation less on the stream, and nothing between the previous
+// frame's blend and this kernel, so the two chain with programmatic dependent launch. Consumers are later kernels.
+__device__ __forceinline__ void zeroFrameState(const ProjectOut& o) {
+    if (!o.zeroBase) return;
+    for (size_t i = (size_t)blockIdx.x * kProjThreads + threadIdx.x; i < o.zeroVecs; i += (size_t)gridDim.x * kProjThreads)
+        o.zeroBase[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ---------------------------------------------------------------- mono kernel
 template <bool HALF, int DEG>
 __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const void* __restrict__ gaussians,
@@ -409,6 +418,7 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const v
                                                                 const __grid_constant__ MonoCam cam, ProjectOut o) {
     pdlLaunchDependents();
     pdlWait();
+    zeroFrameState(o);
     const uint32_t tile = blockIdx.x;
     const uint32_t N = cam.gaussianCount;
     const uint32_t numWarpTiles = (N + 31u) / 32u;
@@ -585,6 +595,7 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_stereo_kernel(const
                                                                   const __grid_constant__ StereoCam cam, ProjectOut o) {
     pdlLaunchDependents();
     pdlWait();
+    zeroFrameState(o);
     const uint32_t tile = blockIdx.x;
     const uint32_t N = cam.gaussianCount;
     const uint32_t numWarpTiles = (N + 31u) / 32u;
