@@ -42,7 +42,7 @@ static SortScratchLayout sortScratchLayout(uint32_t count, int keyBits, int numP
     // scratch: [count u32][hist 4*256][tickets 4][status passes*tiles*256][k1][v1]
     L.oHist = 256; L.oTickets = L.oHist + 4 * 256 * 4; L.oStatus = up(L.oTickets + 16, 256);
     L.oGStatus = up(L.oStatus + (size_t)numPasses * L.tiles * 256 * 4, 256);
-    L.oK1 = up(L.oGStatus + (size_t)numPasses * ((L.tiles + 15) / 16) * 256 * 4, 256);
+    L.oK1 = up(L.oGStatus + (size_t)numPasses * sortGroupRows(L.tiles) * 256 * 4, 256);
     L.oV1 = up(L.oK1 + keyBytes, 256);
     L.total = up(L.oV1 + (size_t)count * 4, 256);
     return L;
@@ -213,8 +213,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     // the sorts' per-tile status words are part of the per-frame memset too (a few MB: cheaper than a reset kernel's launch)
     const size_t oDepthStatus = take((size_t)4 * res.depthTilesCap * 256 * 4);
     const size_t oTileStatus = take((size_t)(tile16 ? 2 : 4) * res.tileTilesCap * 256 * 4);
-    const size_t oDepthGStatus = take((size_t)4 * ((res.depthTilesCap + 15) / 16) * 256 * 4);
-    const size_t oTileGStatus = take((size_t)(tile16 ? 2 : 4) * ((res.tileTilesCap + 15) / 16) * 256 * 4);
+    const size_t oDepthGStatus = take((size_t)4 * sortGroupRows(res.depthTilesCap) * 256 * 4);
+    const size_t oTileGStatus = take((size_t)(tile16 ? 2 : 4) * sortGroupRows(res.tileTilesCap) * 256 * 4);
     const size_t zeroEnd = off;
     res.bytes = off;
 
@@ -274,7 +274,7 @@ SortReset tileSortReset(const gsm_renderer* r, const Resources& res, uint32_t ti
     const bool tile16 = r->cfg.tileIdPrecision == GSM_KEY_BITS16;
     SortReset reset;
     reset.status = res.tileSortStatus; reset.statusStride = res.tileTilesCap * 256u;
-    reset.gstatus = res.tileSortGStatus; reset.gstatusStride = ((res.tileTilesCap + 15u) / 16u) * 256u;
+    reset.gstatus = res.tileSortGStatus; reset.gstatusStride = sortGroupRows(res.tileTilesCap) * 256u;
     reset.passes = (uint32_t)tileSortPasses(tilesX * tilesY); reset.tileSize = sortTileSize(tile16 ? 16 : 32, largeSort(res.frameGaussians));
     return reset;
 }
@@ -457,7 +457,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
@@ -520,7 +520,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
@@ -618,7 +618,7 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "strip project+cull");
     GSM_CUDA(launchCompactVisible(s, gidCount, po, r->numSMs), "visibility compaction");
@@ -651,7 +651,7 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
     po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = ((res.depthTilesCap + 15u) / 16u) * 256u; po.depthKey16 = 0; po.gidFirst = 0;
+    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u; po.depthKey16 = 0; po.gidFirst = 0;
     GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po), "ingest records");
     GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances, tileSortReset(r, res, tilesX, tilesY), r->numSMs), "finalize header");
     st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, /*depthHistReady=*/false);  // records were compacted by the ingest kernel

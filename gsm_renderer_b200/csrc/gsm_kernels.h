@@ -43,12 +43,19 @@ cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthF
 
 // Onesweep radix sort (sort.cu). keys/vals ping-pong between (k0,v0) and (k1,v1); after numPasses the
 // result is in (k0,v0) if numPasses is even, else it is copied back. countPtr is read on the device.
+// Rows of 256 words of per-group state one sort pass owns for `tiles` tiles: one row of per-digit sums per group of 16 tiles,
+// followed by the groups' arrival masks (one word per group, see onesweep_pass_kernel).
+__host__ __device__ inline uint32_t sortGroupRows(uint32_t tiles) {
+    const uint32_t groups = (tiles + 15u) / 16u;
+    return groups + (groups + 255u) / 256u;
+}
+
 struct SortPlan {
     void* k0; void* k1; uint32_t* v0; uint32_t* v1;
     const uint32_t* countPtr; uint32_t countCap;
     uint32_t* hist;      // [numPasses][256] zeroed
     uint32_t* status;    // [numPasses][tilesCap][256] tile look-back words (zeroed by the histogram kernel)
-    uint32_t* gstatus;   // [numPasses][ceil(tilesCap/16)][256] group look-back words
+    uint32_t* gstatus;   // [numPasses][sortGroupRows(tilesCap)][256] per-group words
     uint32_t* tickets;   // [numPasses] zeroed
     uint32_t tilesCap;
     int keyBits;         // 16 or 32

@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(256) finalize_header_kernel(const FrameState* 
     if (threadIdx.x == 0 && blockIdx.x == 0) writeFrameHeader(header, fs->visibleCountRaw, fs->totalInstancesRaw, maxGaussians, maxInstances);
     // reset the tile sort's look-back words for exactly the tiles this frame's totalInstances needs
     const uint32_t words = ((i + reset.tileSize - 1u) / reset.tileSize) * 256u;
-    const uint32_t gwords = ((words / 256u + 15u) / 16u) * 256u;
+    const uint32_t gwords = sortGroupRows(words / 256u) * 256u;
     for (uint32_t p = 0; p < reset.passes; ++p) {
         for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < words; k += gridDim.x * 256u) reset.status[(size_t)p * reset.statusStride + k] = 0u;
         for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < gwords; k += gridDim.x * 256u) reset.gstatus[(size_t)p * reset.gstatusStride + k] = 0u;

@@ -38,9 +38,7 @@ constexpr uint32_t kStatusAggregate = 0x40000000u;
 constexpr uint32_t kStatusInclusive = 0x80000000u;
 constexpr int kLookBatch = 8;
 constexpr uint32_t kLookGroup = 16;
-constexpr uint32_t kFlatMaxTiles = 1024;       // <= 15 + 64 predecessor words per digit in the flat scheme
-constexpr uint32_t kGroupShift = 26;           // flat scheme group word: arrivals << 26 | sum of counts (<= 16 * 4096)
-constexpr uint32_t kGroupArrival = 1u << kGroupShift;
+constexpr uint32_t kFlatMaxTiles = 1024;       // direct summation: <= 15 + 64 predecessor words per digit, 64 arrival masks
 
 // Keys per thread: 8 (2048-key tiles) keeps enough tiles in flight when the whole input is a few hundred
 // thousand keys and the pass is latency-bound; 16 (4096-key tiles) halves the per-tile overhead (look-back, scans)
@@ -70,8 +68,8 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
     {   // reset the look-back words this frame's passes will use (sized by the device-side count, not the capacity)
         constexpr uint32_t TILE = kSortThreads * ITEMS;
         const uint32_t words = ((count + TILE - 1) / TILE) * 256u;
-        const uint32_t gwords = ((words / 256u + kLookGroup - 1) / kLookGroup) * 256u;
-        const uint32_t groupsCap = (tilesCap + kLookGroup - 1) / kLookGroup;
+        const uint32_t gwords = sortGroupRows(words / 256u) * 256u;
+        const uint32_t groupsCap = sortGroupRows(tilesCap);
         for (int p = 0; p < NPASS; ++p) {
             for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < words; i += gridDim.x * 256u)
                 status[(size_t)p * tilesCap * 256u + i] = 0u;
@@ -208,41 +206,50 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const Ke
         uint32_t* myGroup = gstatus + (size_t)group * 256u + tid;
         if (numTiles <= kFlatMaxTiles) {
             // Few tiles (every frame-sized sort): all of them are in flight at once, nothing is "inclusive" yet, and a
-            // chained look-back is a string of dependent L2 round trips (ncu r1_v3: ~17 of a 21 us pass). Instead each
-            // tile publishes its counts once -- a plain word per tile and a RED into its group's accumulator, whose
-            // top bits count arrivals -- and then sums every predecessor directly: the <= 15 earlier tiles of its own
-            // group plus every earlier group, all loads independent, re-polled until all have arrived. The chain is
-            // publish -> one round trip. Sums are order-independent, so no contiguity bookkeeping.
-            st_status32(myStatus, kStatusAggregate | validCount);
-            if ((group + 1u) * kLookGroup < numTiles) atomicAdd(myGroup, kGroupArrival | validCount);  // RED: result unused
+            // chained look-back is a string of dependent L2 round trips. Instead a tile publishes its counts once -- a
+            // word per digit and a RED into its group's per-digit sums -- and sets its bit in the group's ARRIVAL MASK;
+            // one warp polls the masks of the groups up to its own (one or two words per lane), and only when every
+            // predecessor has arrived do the 256 digit threads sum the published words, once. Polling the per-digit
+            // words themselves costs 256 threads x up to 79 loads per attempt: the pollers then starve the CTAs of their SM
+            // that are still ranking (at 5 CTAs per SM the tile sort took 1.1 ms instead of 76 us).
+            const uint32_t numGroups = (numTiles + kLookGroup - 1u) / kLookGroup;
+            uint32_t* arriveMask = gstatus + (size_t)numGroups * 256u;   // one word per group, after the sum rows
+            st_status32(myStatus, validCount);
+            if ((group + 1u) * kLookGroup < numTiles) atomicAdd(myGroup, validCount);  // RED: result unused
+            __threadfence();   // the counts are visible before the arrival bit
+            __syncthreads();
+            if (tid == 0) atomicOr(arriveMask + group, 1u << (tile % kLookGroup));
+            if (tid < 32u) {
+                const uint32_t mine = (1u << (tile % kLookGroup)) - 1u;   // earlier tiles of the own group
+                bool ok;
+                do {
+                    ok = true;
+                    for (uint32_t g = lane; g <= group; g += 32u) {
+                        const uint32_t m = ld_status32(arriveMask + g);
+                        const uint32_t need = g < group ? 0xFFFFu : mine;
+                        ok = ok && (m & need) == need;
+                    }
+                } while (!__all_sync(0xFFFFFFFFu, ok));
+                __threadfence();   // the arrival bits were read before the counts are
+            }
+            __syncthreads();
             const uint32_t groupStart = group * kLookGroup, nPred = tile - groupStart;
-            bool ok;
-            do {
-                ok = true;
-                exclusive = 0;
-                for (uint32_t b = 0; b < group; b += kLookBatch) {
-                    uint32_t sv[kLookBatch];
+            for (uint32_t b = 0; b < group; b += kLookBatch) {
+                uint32_t sv[kLookBatch];
 #pragma unroll
-                    for (int k = 0; k < kLookBatch; ++k)
-                        sv[k] = (b + k < group) ? ld_status32(gstatus + (size_t)(b + k) * 256u + tid) : (kGroupArrival * kLookGroup);
+                for (int k = 0; k < kLookBatch; ++k)
+                    sv[k] = (b + k < group) ? ld_status32(gstatus + (size_t)(b + k) * 256u + tid) : 0u;
 #pragma unroll
-                    for (int k = 0; k < kLookBatch; ++k) {
-                        ok &= (sv[k] >> kGroupShift) == kLookGroup;
-                        exclusive += sv[k] & (kGroupArrival - 1u);
-                    }
-                }
-                for (uint32_t b = 0; b < nPred; b += kLookBatch) {
-                    uint32_t sv[kLookBatch];
+                for (int k = 0; k < kLookBatch; ++k) exclusive += sv[k];
+            }
+            for (uint32_t b = 0; b < nPred; b += kLookBatch) {
+                uint32_t sv[kLookBatch];
 #pragma unroll
-                    for (int k = 0; k < kLookBatch; ++k)
-                        sv[k] = (b + k < nPred) ? ld_status32(status + (size_t)(groupStart + b + k) * 256u + tid) : kStatusAggregate;
+                for (int k = 0; k < kLookBatch; ++k)
+                    sv[k] = (b + k < nPred) ? ld_status32(status + (size_t)(groupStart + b + k) * 256u + tid) : 0u;
 #pragma unroll
-                    for (int k = 0; k < kLookBatch; ++k) {
-                        ok &= (sv[k] & kStatusAggregate) != 0u;
-                        exclusive += sv[k] & kStatusValueMask;
-                    }
-                }
-            } while (!ok);
+                for (int k = 0; k < kLookBatch; ++k) exclusive += sv[k];
+            }
         } else {
         // Many tiles (streaming): two-level decoupled look-back, one thread per digit. Level 1 walks the tiles of the
         // own group of kLookGroup tiles; level 2 walks per-GROUP words published by each group's last tile. In the
@@ -381,7 +388,7 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
         launchChained(kernel, grid, kSortThreads, s,
                       even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
                       p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u,
-                      p.gstatus + (size_t)pass * ((p.tilesCap + kLookGroup - 1) / kLookGroup) * 256u, p.tickets + pass, 8 * pass,
+                      p.gstatus + (size_t)pass * sortGroupRows(p.tilesCap) * 256u, p.tickets + pass, 8 * pass,
                       p.gatherSrc, p.gatherDst);
     }
     cudaError_t e = cudaGetLastError();

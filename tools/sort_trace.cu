@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&k0, keyBytes)); CK(cudaMalloc(&k1, keyBytes));
     CK(cudaMalloc(&v0, (size_t)n * 4)); CK(cudaMalloc(&v1, (size_t)n * 4));
     CK(cudaMalloc(&cnt, 4)); CK(cudaMalloc(&hist, 4 * 256 * 4)); CK(cudaMalloc(&tickets, 16));
-    const size_t stBytes = (size_t)passes * tiles * 256 * 4, gstBytes = (size_t)passes * ((tiles + 15) / 16) * 256 * 4;
+    const size_t stBytes = (size_t)passes * tiles * 256 * 4, gstBytes = (size_t)passes * sortGroupRows(tiles) * 256 * 4;
     CK(cudaMalloc(&status, stBytes)); CK(cudaMalloc(&gstatus, gstBytes));
     const size_t trBytes = (size_t)passes * tiles * 16 * 8;
     CK(cudaMalloc(&trace, trBytes));
