@@ -366,8 +366,17 @@ def main():
             traffic = json.load(open(tp)).get(dom["stage"])
         except Exception:
             traffic = None
+    pipes = None
+    pp = os.path.join(ROOT, "profiles", "pipes.json")
+    if os.path.exists(pp):
+        try:
+            pipes = json.load(open(pp)).get(dom["stage"])
+        except Exception:
+            pipes = None
     roofline = {"bound": "hbm", "kernel": dom["stage"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "pipes": pipes,  # ncu pipe utilisation of this kernel (profiles/pipes.json): what actually bounds it
+
                 "note": ("blend is FP16/FP32-pipe bound, not HBM bound (SURVEY.md 8d); see stage_roofline for the "
                          "HBM-bound sort/scan/expand stages") if dom["stage"] == "blend" else ""}
     sort_blend_ms = stage_ms.get("tileSort", 0) + stage_ms.get("ranges", 0) + stage_ms.get("blend", 0)
