@@ -270,15 +270,6 @@ int tileSortPasses(uint32_t tileCount) {  // TileSortEncoder.swift:61-62
     return (bits + 7) / 8;
 }
 
-SortReset tileSortReset(const gsm_renderer* r, const Resources& res, uint32_t tilesX, uint32_t tilesY) {
-    const bool tile16 = r->cfg.tileIdPrecision == GSM_KEY_BITS16;
-    SortReset reset;
-    reset.status = res.tileSortStatus; reset.statusStride = res.tileTilesCap * 256u;
-    reset.gstatus = res.tileSortGStatus; reset.gstatusStride = sortGroupRows(res.tileTilesCap) * 256u;
-    reset.passes = (uint32_t)tileSortPasses(tilesX * tilesY); reset.tileSize = sortTileSize(tile16 ? 16 : 32, largeSort(res.frameGaussians));
-    return reset;
-}
-
 bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 void recordStage(gsm_renderer* r, cudaStream_t s, int idx) {
@@ -287,7 +278,7 @@ void recordStage(gsm_renderer* r, cudaStream_t s, int idx) {
 
 // stages 2-7 shared by the mono and stereo frames (DFR.swift:325-430, :683-787)
 gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s, bool stereo, uint32_t tilesX, uint32_t tilesY,
-                                 bool depthHistReady = true) {
+                                 bool depthHistReady = true) {  // false: a histogram kernel runs first (no producer filled hist[0..3])
     const gsm_config& c = r->cfg;
     const bool tile16 = c.tileIdPrecision == GSM_KEY_BITS16;
     const bool key16 = c.depthSortKeyPrecision == GSM_KEY_BITS16;
@@ -399,7 +390,7 @@ gsm_status gsm_renderer_create(const gsm_config* cfg, gsm_renderer** out) {
     if (e != cudaSuccess) return fail(GSM_ERR_DEVICE_NOT_AVAILABLE, "cudaGetDeviceProperties", e);
     // the kernels are built for sm_100a only: fail loudly anywhere else (no fallback path exists)
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, (const void*)finalize_header_probe());
+    e = cudaFuncGetAttributes(&fa, (const void*)kernel_image_probe());
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(GSM_ERR_FAILED_TO_CREATE_PIPELINE, "sm_100a kernels cannot be loaded on this device", e);
@@ -455,9 +446,7 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
-    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
-    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u;
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
@@ -518,9 +507,7 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
-    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
-    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u;
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
@@ -616,13 +603,11 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
-    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
-    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u;
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "strip project+cull");
     GSM_CUDA(launchCompactVisible(s, gidCount, po, r->numSMs), "visibility compaction");
-    GSM_CUDA(launchPackRecords(s, res.fs, res.depthKeys[0], res.primIdx[0], res.renderData, res.bounds, res.nTouched, recordsOut,
+    GSM_CUDA(launchPackRecords(s, res.fs, res.depthKeys[0], res.primIdx[0], res.renderData, res.bounds, res.hitMask, recordsOut,
                                gidCount, r->numSMs), "pack records");
     GSM_CUDA(cudaMemcpyAsync(hostCount, &res.fs->visibleCountRaw, 4, cudaMemcpyDeviceToHost, s), "count readback");
     GSM_CUDA(cudaStreamSynchronize(s), "strip project sync");
@@ -649,12 +634,17 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
     po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
     po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
-    po.depthTileSize = sortTileSize(32, largeSort(res.frameGaussians)); po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
-    po.depthStatus = res.depthSortStatus; po.depthStatusStride = res.depthTilesCap * 256u;
-    po.depthGStatus = res.depthSortGStatus; po.depthGStatusStride = sortGroupRows(res.depthTilesCap) * 256u; po.depthKey16 = 0; po.gidFirst = 0;
-    GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po), "ingest records");
-    GSM_CUDA(launchFinalizeHeader(s, res.fs, res.header, res.maxGaussians, res.maxInstances, tileSortReset(r, res, tilesX, tilesY), r->numSMs), "finalize header");
-    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, /*depthHistReady=*/false);  // records were compacted by the ingest kernel
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthKey16 = 0; po.gidFirst = 0;
+    // per-record (count, key, gid) for the compaction: three arrays that are free until the depth sort runs
+    uint32_t* recTouched = res.offsets;
+    uint32_t* recKey = res.depthKeys[1];
+    uint32_t* recGid = (uint32_t*)res.primIdx[1];
+    GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po, recTouched, recKey, recGid), "ingest records");
+    po.recTouched = recTouched; po.recKey = recKey; po.recGid = recGid;
+    po.depthHist = &res.fs->hist[0][0];
+    GSM_CUDA(launchCompactVisible(s, recordCount, po, r->numSMs), "record compaction");  // also writes the header
+    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);  // same stages 2-7 as the single-GPU frame
     if (st != GSM_OK) return st;
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
                              tileRowCount, (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "strip blend");

@@ -5,7 +5,6 @@
 // the scan offset, row-major ty -> tx, bounded by maxAssignments (createInstancesKernel / ...32 DFS.metal:642-788,
 // createInstancesStereoKernel / ...32 DFS.metal:790-864). A tile publishes its aggregate before it starts walking,
 // so nobody waits on a neighbour's tile walk. The tile sort's digit histograms are accumulated on the way out.
-#include <cstdlib>
 #include "gsm_common.cuh"
 #include "gsm_kernels.h"
 #include "gsm_tiletest.cuh"
@@ -172,8 +171,8 @@ cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, co
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
                                   uint32_t* tileHist, uint32_t tilePasses, int numSMs) {
     uint32_t grid = (capVisible + 255u) / 256u;
-    static const uint32_t perSM = [] { const char* e = getenv("GSM_EXPAND_CTAS"); return e ? (uint32_t)atoi(e) : 6u; }();
-    if (grid > (uint32_t)numSMs * perSM) grid = (uint32_t)numSMs * perSM;  // persistent: few CTAs flush the fused histograms
+    // persistent, 6 CTAs per SM: 3 left the kernel 25 % slower, 8 changed nothing (profiles/README.md); few CTAs flush the histograms
+    if (grid > (uint32_t)numSMs * 6u) grid = (uint32_t)numSMs * 6u;
     if (grid == 0) grid = 1;
 #define GSM_LAUNCH(T, ST) launchChained(create_instances_kernel<T, ST>, grid, 256, s, sortedIdx, sortedTouched, hitMask, offsets, scanStatus, scanGroups, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
     if (tileId16) { if (stereo) GSM_LAUNCH(uint16_t, true); else GSM_LAUNCH(uint16_t, false); }

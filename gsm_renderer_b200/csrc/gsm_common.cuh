@@ -114,40 +114,6 @@ __device__ __forceinline__ uint32_t ld_status32(const uint32_t* p) {
     return v;
 }
 
-// Decoupled look-back over single-value tile aggregates, run by one full warp. Returns the exclusive
-// prefix of `tile` (sum of aggregates of tiles < tile) to every lane and publishes the inclusive value.
-__device__ __forceinline__ uint32_t lookback_exclusive(unsigned long long* status, uint32_t tile, uint32_t aggregate) {
-    const unsigned lane = threadIdx.x & 31u;
-    if (tile == 0) {
-        if (lane == 0) st_status64(&status[0], kFlagInclusive, aggregate);
-        return 0;
-    }
-    if (lane == 0) st_status64(&status[tile], kFlagAggregate, aggregate);
-    uint32_t exclusive = 0;
-    int look = (int)tile - 1;
-    while (true) {
-        int idx = look - (int)lane;
-        unsigned long long s = (idx >= 0) ? ld_status64(&status[idx]) : ((unsigned long long)kFlagInclusive << 32);
-        uint32_t flag = (uint32_t)(s >> 32);
-        // all lanes must have a published word before the window is consumed
-        if (__any_sync(0xFFFFFFFFu, flag == 0)) continue;
-        unsigned incl = __ballot_sync(0xFFFFFFFFu, flag == kFlagInclusive);
-        uint32_t v = (uint32_t)s;
-        if (incl) {
-            int first = __ffs(incl) - 1;  // nearest predecessor holding an inclusive prefix
-            uint32_t contrib = (lane <= (unsigned)first) ? v : 0u;
-            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
-            exclusive += contrib;
-            break;
-        }
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        exclusive += v;
-        look -= 32;
-    }
-    if (lane == 0) st_status64(&status[tile], kFlagInclusive, exclusive + aggregate);
-    return exclusive;
-}
-
 // Eager variant for software-pipelined consumers: a tile PUBLISHES as soon as its aggregate is known (a word per tile
 // and a RED into its group's accumulator, whose top bits count arrivals), goes on with other work, and RESOLVES its
 // exclusive prefix later -- by then every predecessor has long published, so the resolve is one round trip and no tile

@@ -13,6 +13,9 @@ struct ProjectOut {
     uint32_t* nTouched;
     uint2* hitMask;               // mono only: hit bits of the first 64 AABB tiles per Gaussian (gsm_tiletest.cuh)
     BlendSplat* blendSplats;      // mono only (may be null)
+    const uint32_t* recTouched = nullptr;  // strip ingest: the compaction runs over gathered records (count, key, gid per record)
+    const uint32_t* recKey = nullptr;
+    const uint32_t* recGid = nullptr;
     uint32_t* preDepthKeys;       // per gid, before compaction (the reference aliases the sort scratch for it, DFR.swift:282)
     uint32_t* depthKeys;          // compacted, ascending gid
     int32_t* primitiveIndices;
@@ -23,23 +26,16 @@ struct ProjectOut {
     uint32_t maxInstances;
     uint32_t depthKey16;
     uint32_t gidFirst;
-    // fused into the compaction kernel: digit histograms of the compacted depth keys and the reset of the depth
-    // sort's look-back words (bounded by N, known on the host)
+    // fused into the compaction kernel: digit histograms of the compacted depth keys
     uint32_t* depthHist;          // [4][256], zeroed with the frame state
     uint32_t depthPasses;
-    uint32_t depthTileSize;       // keys per onesweep tile of the depth sort (sortTileSize(32))
-    uint32_t* depthStatus; uint32_t depthStatusStride;   // words per pass (tilesCap*256)
-    uint32_t* depthGStatus; uint32_t depthGStatusStride;
 };
 
-struct SortReset;
 int shDegreeFromComponents(uint32_t n);
-const void* finalize_header_probe();  // a kernel symbol, to test that the sm_100a image loads
+const void* kernel_image_probe();  // a kernel symbol, to test that the sm_100a image loads
 cudaError_t launchProjectMono(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam, const ProjectOut& o);
 cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, const void* h, const StereoCam& cam, const ProjectOut& o);
 cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o, int numSMs);
-cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians, uint32_t maxInstances,
-                                 const SortReset& reset, int numSMs);
 
 // Onesweep radix sort (sort.cu). keys/vals ping-pong between (k0,v0) and (k1,v1); after numPasses the
 // result is in (k0,v0) if numPasses is even, else it is copied back. countPtr is read on the device.
@@ -69,10 +65,6 @@ struct SortPlan {
 uint32_t sortTileSize(int keyBits, bool large);
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p);
 
-// apply depth order + exclusive scan (scan.cu)
-struct SortReset {  // look-back words of the tile sort, reset by the header kernel (it knows totalInstances exactly)
-    uint32_t* status; uint32_t statusStride; uint32_t* gstatus; uint32_t gstatusStride; uint32_t passes; uint32_t tileSize;
-};
 
 // instance expansion (expand.cu)
 cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* sortedTouched,
@@ -102,9 +94,9 @@ gsm_status sortPairsStandalone(cudaStream_t s, int numSMs, void* keys, void* pay
 
 // strip-sharded frame (strip.cu)
 cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,
-                              const int32_t* bounds, const uint32_t* nTouched, void* out, uint32_t cap, int numSMs);
+                              const int32_t* bounds, const uint2* hitMask, void* out, uint32_t cap, int numSMs);
 cudaError_t launchIngestRecords(cudaStream_t s, const void* records, uint32_t recordCount, uint32_t rowFirst, uint32_t rowCount,
-                                const ProjectOut& o);
+                                const ProjectOut& o, uint32_t* recTouched, uint32_t* recKey, uint32_t* recGid);
 
 // math probes (probe.cu)
 cudaError_t launchProbe(cudaStream_t s, int op, const void* a, const void* b, void* out, uint32_t n);

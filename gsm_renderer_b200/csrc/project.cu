@@ -8,7 +8,6 @@
 #include "gsm_dmath.cuh"
 #include "gsm_kernels.h"
 #include "gsm_tiletest.cuh"
-#include "gsm_compact.cuh"
 
 namespace gsm {
 
@@ -402,6 +401,11 @@ __device__ __forceinline__ V3 computeSHColor(const void* harmonics, uint32_t gid
     return color;
 }
 
+__device__ __forceinline__ void writeCulled(const ProjectOut& o, uint32_t gid) {
+    o.nTouched[gid] = 0;
+    reinterpret_cast<int4*>(o.bounds)[gid] = make_int4(0, -1, 0, -1);
+}
+
 // The per-frame zero region (frame state, prefix and status words) is cleared by the frame's first kernel when its grid is
 // large enough to do it in a few stores per thread: one operation less on the stream, and nothing between the previous
 // frame's blend and this kernel, so the two chain with programmatic dependent launch. Consumers are later kernels.
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
 #pragma unroll
         for (int i = 0; i < kCompactItems; ++i) {
             const uint32_t l = first + i;
-            nt[i] = (l < N) ? o.nTouched[o.gidFirst + l] : 0u;
+            nt[i] = (l < N) ? (o.recTouched ? o.recTouched[l] : o.nTouched[o.gidFirst + l]) : 0u;
             cnt += nt[i] > 0u ? 1u : 0u;
             tsum += nt[i];
         }
@@ -766,8 +770,9 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
         for (int i = 0; i < kCompactItems; ++i) {
             if (nt[i] > 0u) {
                 if (dst < o.maxOut) {  // DFS.metal:605
-                    const uint32_t gid = o.gidFirst + first + i;
-                    uint32_t key = o.preDepthKeys[gid];
+                    // projection: element l is Gaussian gidFirst + l; strip ingest: element l is gathered record l
+                    const uint32_t gid = o.recTouched ? o.recGid[first + i] : o.gidFirst + first + i;
+                    uint32_t key = o.recTouched ? o.recKey[first + i] : o.preDepthKeys[gid];
                     if (o.depthKey16) {  // DFS.metal:607-612; key is float_to_sortable_uint of a depth > 0
                         uint32_t bits = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
                         key = (uint32_t)(__half_as_ushort(__float2half_rn(__uint_as_float(bits))) ^ 0x8000u);
@@ -795,24 +800,7 @@ cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o
     return cudaGetLastError();
 }
 
-// DFS.metal:2184-2203 (+ reset :1372-1385)
-__global__ void __launch_bounds__(256) finalize_header_kernel(const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians,
-                                                              uint32_t maxInstances, SortReset reset) {
-    pdlLaunchDependents();
-    pdlWait();
-    uint32_t i = fs->totalInstancesRaw;
-    if (i > maxInstances) i = maxInstances;
-    if (threadIdx.x == 0 && blockIdx.x == 0) writeFrameHeader(header, fs->visibleCountRaw, fs->totalInstancesRaw, maxGaussians, maxInstances);
-    // reset the tile sort's look-back words for exactly the tiles this frame's totalInstances needs
-    const uint32_t words = ((i + reset.tileSize - 1u) / reset.tileSize) * 256u;
-    const uint32_t gwords = sortGroupRows(words / 256u) * 256u;
-    for (uint32_t p = 0; p < reset.passes; ++p) {
-        for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < words; k += gridDim.x * 256u) reset.status[(size_t)p * reset.statusStride + k] = 0u;
-        for (uint32_t k = blockIdx.x * 256u + threadIdx.x; k < gwords; k += gridDim.x * 256u) reset.gstatus[(size_t)p * reset.gstatusStride + k] = 0u;
-    }
-}
-
-const void* finalize_header_probe() { return (const void*)finalize_header_kernel; }
+const void* kernel_image_probe() { return (const void*)compact_visible_kernel; }
 
 // ---------------------------------------------------------------- launchers
 template <bool HALF>
@@ -853,10 +841,4 @@ cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, c
     int deg = shDegreeFromComponents(cam.shComponents);
     return halfInput ? launchStereo<true>(deg, grid, s, g, h, cam, o) : launchStereo<false>(deg, grid, s, g, h, cam, o);
 }
-cudaError_t launchFinalizeHeader(cudaStream_t s, const FrameState* fs, GSMDepthFirstHeader* header, uint32_t maxGaussians,
-                                 uint32_t maxInstances, const SortReset& reset, int numSMs) {
-    launchChained(finalize_header_kernel, numSMs, 256, s, fs, header, maxGaussians, maxInstances, reset);
-    return cudaGetLastError();
-}
-
 }  // namespace gsm
