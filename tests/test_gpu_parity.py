@@ -253,3 +253,40 @@ def test_stereo_frame_gpu(oracle, pu, precision, deg, flip):
     pu.compare_white_box(r, fr, W, H, cl.count, stereo=True)
     pu.compare_pixels(out, ref, True, precision == "float16", "stereo colour")
     r.close()
+
+
+@pytest.mark.gpu
+def test_repeated_frames_are_identical_gpu():
+    """Every frame of the same input equals the first, with back-to-back frames chained on one stream: a race in the
+    publish / resolve prefix schemes, the arrival masks of the sort passes or the in-kernel clearing of the frame state
+    would show up as a differing image, key list or instance list."""
+    import torch
+    from gsm_renderer_b200.renderer import DepthFirstRenderer, GaussianColorSpace, GaussianInput, RendererConfig, RenderPrecision
+    cl = syn.synthetic_cloud(300_000, 3, seed=23, scale_median=0.015)
+    g, h = pu.make_scene_inputs(cl, "float16")
+    W, H = 1920, 1080
+    cam = pu.default_camera(W, H)
+    r = DepthFirstRenderer(device=0, config=RendererConfig(maxGaussians=cl.count, maxWidth=W, maxHeight=H,
+                                                           precision=RenderPrecision.float16, gaussianColorSpace=GaussianColorSpace.linear))
+    dev = torch.device("cuda:0")
+    tg = torch.from_numpy(g.view(np.uint8).reshape(-1)).to(dev)
+    th = torch.from_numpy(h.view(np.uint8).reshape(-1)).to(dev)
+    inp = GaussianInput(tg, th, cl.count, 16)
+    s = torch.cuda.current_stream()
+    ref = torch.zeros((H, W, 4), dtype=torch.int16, device=dev)
+    r.render(s, ref, None, inp, cam, W, H)
+    torch.cuda.synchronize()
+    hd = r.debugReadHeader()
+    keys = r.debugReadDepthKeys(hd.visibleCount).copy()
+    inst = r.debugReadInstanceGaussianIndices(hd.totalInstances).copy()
+    out = torch.zeros_like(ref)
+    for i in range(60):
+        r.render(s, out, None, inp, cam, W, H)
+        if i % 10 == 9:
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref), f"frame {i} differs from the first"
+            h2 = r.debugReadHeader()
+            assert (h2.visibleCount, h2.totalInstances) == (hd.visibleCount, hd.totalInstances)
+            assert np.array_equal(r.debugReadDepthKeys(hd.visibleCount), keys)
+            assert np.array_equal(r.debugReadInstanceGaussianIndices(hd.totalInstances), inst)
+    r.close()
