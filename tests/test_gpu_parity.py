@@ -255,8 +255,7 @@ def test_stereo_frame_gpu(oracle, pu, precision, deg, flip):
     r.close()
 
 
-@pytest.mark.gpu
-def test_repeated_frames_are_identical_gpu():
+def test_repeated_frames_are_identical_gpu(pu):
     """Every frame of the same input equals the first, with back-to-back frames chained on one stream: a race in the
     publish / resolve prefix schemes, the arrival masks of the sort passes or the in-kernel clearing of the frame state
     would show up as a differing image, key list or instance list."""
