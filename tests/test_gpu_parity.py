@@ -289,3 +289,28 @@ def test_repeated_frames_are_identical_gpu(pu):
             assert np.array_equal(r.debugReadDepthKeys(hd.visibleCount), keys)
             assert np.array_equal(r.debugReadInstanceGaussianIndices(hd.totalInstances), inst)
     r.close()
+
+
+def test_sorts_on_the_streaming_path_gpu(oracle):
+    """More than 1024 tiles per pass: the chained two-level look-back instead of the direct summation."""
+    rng = np.random.default_rng(77)
+    n = 6_000_000                                   # 1465 tiles of 4096 keys
+    keys = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    keys[rng.integers(0, n, n // 5)] = keys[7]      # a heavy tie class: stability shows in the payload
+    pay = np.arange(n, dtype=np.int32)
+    k, p = _gpu_sort(keys.view(np.int32), pay, 32, 4)
+    ok, op = oracle.sort_pairs_u32(keys, pay, 4)
+    assert np.array_equal(k.view(np.uint32), ok) and np.array_equal(p, op)
+    n = 5_000_000                                   # 1221 tiles of 4096 16-bit keys
+    k16 = rng.integers(0, 8160, n).astype(np.uint16)
+    pay = np.arange(n, dtype=np.int32)
+    k, p = _gpu_sort(k16.view(np.int16), pay, 16, 2)
+    ok, op = oracle.sort_pairs_u16(k16, pay, 2)
+    assert np.array_equal(k.view(np.uint16), ok) and np.array_equal(p, op)
+
+
+def test_three_million_gaussians_frame_gpu(oracle, pu):
+    """N >= 3 M switches the frame's 32-bit sorts to 4096-key tiles (and the last depth pass still gathers nTouched)."""
+    cl = syn.synthetic_cloud(3_100_000, 3, seed=9, scale_median=0.006)
+    res = pu.run_mono_case(oracle, cl, "float16", 1280, 720)
+    assert res["V"] > 1_000_000 and res["I"] > res["V"]
