@@ -43,6 +43,9 @@ constexpr uint32_t kFlatMaxTiles = 1024;       // direct summation: <= 15 + 64 p
 // Keys per thread: 8 (2048-key tiles) keeps enough tiles in flight when the whole input is a few hundred
 // thousand keys and the pass is latency-bound; 16 (4096-key tiles) halves the per-tile overhead (look-back, scans)
 // and lengthens the scatter runs once the input is large (profiles/r1_sort_sweep_*: +24 % at 48 M pairs, -35 % at 709 k).
+#ifndef GSM_SORT_CTAS_LARGE
+#define GSM_SORT_CTAS_LARGE 3   // resident CTAs per SM asked of the 4096-key u32 instance (register cap 85 / 64 / 51)
+#endif
 #ifndef GSM_SORT_ITEMS_SMALL
 #define GSM_SORT_ITEMS_SMALL 8
 #endif
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
 // gathering through the sorted indices at the head of its own dependency chain (expansion timeline: the scan
 // waited ~4.5 us per tile for the slowest in-flight predecessor's random gather).
 template <typename KeyT, int ITEMS, bool GATHER>
-__global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+__global__ void __launch_bounds__(kSortThreads, ((sizeof(KeyT) == 4 && ITEMS == 16) ? GSM_SORT_CTAS_LARGE : 3)) onesweep_pass_kernel(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
                                                                      KeyT* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
                                                                      const uint32_t* __restrict__ countPtr, uint32_t countCap,
                                                                      const uint32_t* __restrict__ digitHist, uint32_t* status,
