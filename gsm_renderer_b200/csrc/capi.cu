@@ -823,6 +823,15 @@ const char* gsm_status_string(gsm_status s) {
         case GSM_ERR_RENDER_FAILED: return "render failed";
         case GSM_ERR_INVALID_ARGUMENT: return "invalid argument";
     }
+    switch ((int)s) {  // PLYLoaderError.errorDescription (PLYLoader.swift:218-241), statuses of gsm_scene.h
+        case 20: return "Invalid PLY header";
+        case 21: return "Unsupported PLY format. Only binary_little_endian is supported.";
+        case 22: return "No 'vertex' element found in PLY";
+        case 23: return "Missing required properties";
+        case 24: return "List properties in vertex element are not supported";
+        case 25: return "PLY file has insufficient data for declared vertex count";
+        case 26: return "Compressed PLY requires 'chunk' element with bounding box data";
+    }
     return "unknown";
 }
 const char* gsm_last_error_string(void) { return g_lastError.c_str(); }

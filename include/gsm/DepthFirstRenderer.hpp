@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "gsm.h"
+#include "gsm_scene.h"
 #include "gsm_types.h"
 
 namespace gsm {
@@ -159,6 +160,44 @@ public:
 
 private:
     gsm_renderer* h_ = nullptr;
+};
+
+// ---- scene ingest (gsm_scene.h): PLYLoader.load(url:) + GaussianSceneBuilder (PLYLoader.swift:246-281, Scene.swift:73-190).
+// The caller supplies the file in host memory (mmap or read); the records are decoded on the device, straight into the
+// renderer's input layout. PLYLoaderError cases arrive as RendererError with the GSM_ERR_PLY_* status.
+struct GaussianDataset {
+    void* gaussians = nullptr;   // device: PackedWorldGaussian (48 B) or PackedWorldGaussianHalf (32 B) x count
+    void* harmonics = nullptr;   // device: float / half, count x harmonicsStride, planar per Gaussian
+    gsm_scene_info info{};
+    gsm_precision precision = GSM_PRECISION_FLOAT16;
+    GaussianInput input() const { return GaussianInput{gaussians, harmonics, (int)info.count, (int)info.shComponents}; }
+    void release() { if (gaussians) gsm_buffer_free(gaussians); if (harmonics) gsm_buffer_free(harmonics); gaussians = harmonics = nullptr; }
+};
+
+struct PLYLoader {
+    static GaussianDataset load(const void* fileBytes, size_t fileSize, int device = -1, void* stream = nullptr,
+                                gsm_precision precision = GSM_PRECISION_FLOAT16) {
+        gsm_ply_info probe{};
+        gsm_status st = gsm_ply_probe(fileBytes, fileSize, &probe);
+        if (st != GSM_OK) throw RendererError(st, gsm_last_error_string());
+        GaussianDataset d;
+        d.precision = precision;
+        const size_t n = probe.vertexCount ? probe.vertexCount : 1, sh = probe.shProperties ? probe.shProperties : 1;
+        const size_t rec = precision == GSM_PRECISION_FLOAT16 ? 32 : 48, el = precision == GSM_PRECISION_FLOAT16 ? 2 : 4;
+        if ((st = gsm_buffer_alloc(device, n * rec, &d.gaussians)) != GSM_OK) throw RendererError(st, gsm_last_error_string());
+        if ((st = gsm_buffer_alloc(device, n * sh * el, &d.harmonics)) != GSM_OK) { d.release(); throw RendererError(st, gsm_last_error_string()); }
+        st = gsm_ply_load(device, stream, fileBytes, fileSize, (int)precision, d.gaussians, d.harmonics, probe.vertexCount,
+                          (size_t)probe.vertexCount * sh, &d.info);
+        if (st != GSM_OK) { d.release(); throw RendererError(st, gsm_last_error_string()); }
+        return d;
+    }
+};
+
+struct GaussianSceneBuilder {
+    static void sortByMortonCode(GaussianDataset& d, int device = -1, void* stream = nullptr) {
+        gsm_status st = gsm_scene_morton_sort(device, stream, d.gaussians, d.harmonics, d.info.count, d.info.harmonicsStride, (int)d.precision);
+        if (st != GSM_OK) throw RendererError(st, gsm_last_error_string());
+    }
 };
 
 }  // namespace gsm
