@@ -162,3 +162,22 @@ def test_render_loaded_scene_matches_oracle_frame(ob):
     r.close()
     assert V > 1000
     assert np.array_equal(c, np.asarray(oc).view(np.uint16).reshape(c.shape)) and np.array_equal(d, np.asarray(od).view(np.uint16).reshape(d.shape))
+
+
+def test_empty_file_and_very_wide_records(ob):
+    from gsm_renderer_b200.scene import PLYLoader
+    # no vertices at all: count 0, bounds (zero, 1.0) like GaussianSceneBuilder.bounds(of: [])
+    data = pu.write_ply([("float", "x"), ("float", "y"), ("float", "z")], {"x": np.zeros(0), "y": np.zeros(0), "z": np.zeros(0)}, count=0)
+    ds = PLYLoader.load(data)
+    ref = ob.ply_load(data)
+    assert ds.count == 0 == ref["result"].count and ds.boundsRadius == 1.0 == ref["result"].boundsRadius
+    # records too wide to stage 128 of them in shared memory (> 1090 B): the direct-read path
+    props, cols = pu.standard_scene(3000, 3, seed=3, placeholders=4)
+    rng = np.random.default_rng(1)
+    for k in range(140):
+        cols[f"junk_{k}"] = rng.normal(0, 1, 3000)
+        props.insert(3 + k, ("double", f"junk_{k}"))
+    data = pu.write_ply(props, cols)
+    for half in (True, False):
+        ds, ref = _load_both(ob, data, half)
+        _assert_same(ob, ds, ref, half)
