@@ -291,7 +291,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     dp.hist = &res.fs->hist[0][0]; dp.status = res.depthSortStatus; dp.gstatus = res.depthSortGStatus; dp.tickets = &res.fs->ticketSort[0];
     dp.largeTiles = largeSort(res.frameGaussians);
     dp.tilesCap = res.depthTilesCap; dp.keyBits = 32; dp.numPasses = key16 ? 2 : 4; dp.numSMs = r->numSMs;
-    dp.histogramReady = depthHistReady;  // compact_visible_kernel filled hist[0..3] and reset the look-back words
+    dp.histogramReady = depthHistReady;  // compact_visible_kernel filled hist[0..3]; the status words were cleared with the frame state
     GSM_CUDA(launchSort(s, dp), "depth sort");
     recordStage(r, s, 2);
     // stages 3+4
@@ -310,7 +310,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     tp.hist = &res.fs->hist[4][0]; tp.status = res.tileSortStatus; tp.gstatus = res.tileSortGStatus; tp.tickets = &res.fs->ticketSort[4];
     tp.largeTiles = largeSort(res.frameGaussians);
     tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tilePasses;
-    tp.numSMs = r->numSMs; tp.histogramReady = true;  // create_instances_kernel filled hist[4..7], the scan kernel reset the words
+    tp.numSMs = r->numSMs; tp.histogramReady = true;  // create_instances_kernel filled hist[4..7]; the status words were cleared with the frame state
     GSM_CUDA(launchSort(s, tp), "tile sort");
     recordStage(r, s, 5);
     // stage 7

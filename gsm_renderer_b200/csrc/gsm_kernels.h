@@ -22,7 +22,7 @@ struct ProjectOut {
     uint4* zeroBase = nullptr;    // if set, the projection kernel clears the frame's zero region (zeroVecs 16-byte words) itself
     size_t zeroVecs = 0;
     uint32_t maxOut;              // capacity of the compacted arrays (maxGaussians)
-    GSMDepthFirstHeader* header;  // if set, the projection's last block also writes the frame header (no finalize kernel)
+    GSMDepthFirstHeader* header;  // if set, the compaction's last tile also writes the frame header (DFS.metal:2184-2203)
     uint32_t maxInstances;
     uint32_t depthKey16;
     uint32_t gidFirst;
@@ -50,7 +50,7 @@ struct SortPlan {
     void* k0; void* k1; uint32_t* v0; uint32_t* v1;
     const uint32_t* countPtr; uint32_t countCap;
     uint32_t* hist;      // [numPasses][256] zeroed
-    uint32_t* status;    // [numPasses][tilesCap][256] tile look-back words (zeroed by the histogram kernel)
+    uint32_t* status;    // [numPasses][tilesCap][256] per-tile count / look-back words (zeroed with the frame state, or by the histogram kernel)
     uint32_t* gstatus;   // [numPasses][sortGroupRows(tilesCap)][256] per-group words
     uint32_t* tickets;   // [numPasses] zeroed
     uint32_t tilesCap;
