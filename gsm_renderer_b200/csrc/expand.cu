@@ -146,13 +146,13 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
             warpEmitMasked<TileT>(s_warpWork[warp].replay, mask, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
                                   tileIds, instanceIdx, &s_hist[0][0], tilePasses);
         if (STEREO) {
-            // every tile of the union AABB, no ellipse test (DFS.metal:816-825): a splat whose mean is inside every
-            // tile makes tileHitP return true for all of them without changing the walk
-            q.meanX = 0.0f; q.meanY = 0.0f; q.ca = 0.0f; q.cb = 0.0f; q.cc = 0.0f;
-            q.d2Cutoff = __uint_as_float(0x7F800000u);  // d2min <= +inf always (d2min is never NaN for a = b = c = 0)
+            // every tile of the union AABB is an instance, no ellipse test (DFS.metal:816-825)
+            warpEmitBox<TileT>(s_warpWork[warp].replay, n, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
+                               tileIds, instanceIdx, &s_hist[0][0], tilePasses);
+        } else {
+            warpEmitTiles<TileT>(s_warpWork[warp].test, n, q, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
+                                 tileIds, instanceIdx, s_base[warp], s_idx[warp], &s_hist[0][0], tilePasses);
         }
-        warpEmitTiles<TileT>(s_warpWork[warp].test, n, q, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
-                             tileIds, instanceIdx, s_base[warp], s_idx[warp], &s_hist[0][0], tilePasses);
 #ifdef GSM_EXPAND_TRACE
         GSM_XTRACE(tile, 5);
         __syncthreads();

@@ -254,6 +254,55 @@ __device__ __forceinline__ void warpEmitMasked(WarpMaskWork& s, uint2 mask, int 
     __syncwarp();
 }
 
+// Stereo expansion (createInstancesStereoKernel, DFS.metal:790-864): EVERY tile of the union AABB is an instance, so
+// instance r of a splat is simply the r-th tile of its box in row-major order -- no test, no ranking. Lanes take
+// instances (coalesced stores, balanced work); same bound and histogram accumulation as warpEmitMasked.
+template <typename TileT>
+__device__ __forceinline__ void warpEmitBox(WarpMaskWork& s, uint32_t n, int minTX, int minTY, int w, uint32_t writeBase,
+                                            int32_t originalIdx, uint32_t tilesX, uint32_t maxAssignments,
+                                            TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx, uint32_t* sHist,
+                                            uint32_t histPasses) {
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t total;
+    const uint32_t excl = warpExclusiveScan(n, total);
+    if (total == 0) return;
+    s.prefix[lane] = excl;
+    s.minTX[lane] = minTX; s.minTY[lane] = minTY;
+    s.w[lane] = (uint32_t)(w > 0 ? w : 1);
+    s.base[lane] = writeBase;
+    s.idx[lane] = originalIdx;
+    __syncwarp();
+    for (uint32_t j0 = 0; j0 < total; j0 += 32u) {
+        const uint32_t j = j0 + lane;
+        bool stored = false;
+        uint32_t tileId = 0xFFFFFFFFu;
+        if (j < total) {
+            uint32_t o = 0;  // largest lane with prefix <= j
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (s.prefix[o + step] <= j) o += step;
+            const uint32_t r = j - s.prefix[o];
+            const uint32_t ww = s.w[o], row = r / ww;
+            const int ty = s.minTY[o] + (int)row, tx = s.minTX[o] + (int)(r - row * ww);
+            tileId = (uint32_t)(ty * (int)tilesX + tx);
+            const uint32_t dst = s.base[o] + r;
+            if (dst < maxAssignments) {  // DFS.metal:832
+                tileIds[dst] = (TileT)tileId;
+                instanceIdx[dst] = s.idx[o];
+                atomicAdd(&sHist[tileId & 0xFFu], 1u);
+                stored = true;
+            }
+        }
+        if (histPasses > 1) {  // upper digits are shared by most lanes: one shared-memory atomic per distinct value
+            const uint32_t hi = stored ? (tileId >> 8) : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, hi);
+            if (stored && (peers & ((1u << lane) - 1u)) == 0u)
+                for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], (uint32_t)__popc(peers));
+        }
+    }
+    __syncwarp();
+}
+
 // Emits the hit tiles of every lane's splat in row-major order at offsets[lane] + rank (DFS.metal:692-715).
 // Items of one owner sit in consecutive lanes, so a match-any group + ballot ranks them in order.
 template <typename TileT>
