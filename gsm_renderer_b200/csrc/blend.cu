@@ -220,6 +220,29 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
     accumulate(q, a0, a1, cr, cg, cb, zero, false);
 }
 
+// Exact whole-tile cutoff test for one eye of one splat, run once by the staging thread. The stereo instance lists hold
+// every tile of the union box (DFS.metal:816-825), so for most (splat, tile) pairs every pixel fails p > r2Max and each of
+// the 64 threads would find that out on its own. With cxx, cyy >= 0 the rounded evaluation
+//   p = RN(m * cxy2 + inner),  m = RN(dx * dy),  inner = RN(RN(dy * dy) * cyy + RN(RN(dx * dx) * cxx))
+// is monotone: inner is smallest at the tile's smallest |dx|, |dy| (0 if the tile straddles the mean), m lies between the
+// extremes of its four corner products, and RN is monotone, so every pixel's p is >= min(RN(mMin * cxy2 + innerMin),
+// RN(mMax * cxy2 + innerMin)). If that bound exceeds r2Max, every alpha is exactly 0 and the eye is skipped. Any NaN in the
+// bound (0 * inf, inf - inf) makes the comparison false: no skip, the per-pixel path decides.
+__device__ __forceinline__ bool eyeTileBeyondCutoff(__half2 mean, __half2 cxx_cyy, __half cxy2, uint32_t X0, uint32_t Y0) {
+    const __half zero = __float2half_rn(0.0f), r2Max = __float2half_rn(9.0f);
+    const __half mx = __low2half(mean), my = __high2half(mean), cxx = __low2half(cxx_cyy), cyy = __high2half(cxx_cyy);
+    if (!(__hge(cxx, zero) && __hge(cyy, zero))) return false;
+    const __half xa = __hsub_rn(__uint2half_rn(X0), mx), xb = __hsub_rn(__uint2half_rn(X0 + 15u), mx);
+    const __half ya = __hsub_rn(__uint2half_rn(Y0), my), yb = __hsub_rn(__uint2half_rn(Y0 + 15u), my);
+    const __half dxm = __hgt(xa, zero) ? xa : (__hlt(xb, zero) ? xb : zero);
+    const __half dym = __hgt(ya, zero) ? ya : (__hlt(yb, zero) ? yb : zero);
+    const __half inner = __hfma(__hmul_rn(dym, dym), cyy, __hmul_rn(__hmul_rn(dxm, dxm), cxx));
+    const __half m1 = __hmul_rn(xa, ya), m2 = __hmul_rn(xa, yb), m3 = __hmul_rn(xb, ya), m4 = __hmul_rn(xb, yb);
+    if (__hisnan(m1) || __hisnan(m2) || __hisnan(m3) || __hisnan(m4)) return false;
+    const __half mMin = __hmin(__hmin(m1, m2), __hmin(m3, m4)), mMax = __hmax(__hmax(m1, m2), __hmax(m3, m4));
+    return __hgt(__hfma(mMin, cxy2, inner), r2Max) && __hgt(__hfma(mMax, cxy2, inner), r2Max);
+}
+
 __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint32_t* __restrict__ lowerBounds,
                                                                      const GSMStereoTiledRenderData* __restrict__ splats,
                                                                      const int32_t* __restrict__ instanceIdx, uint32_t width,
@@ -251,12 +274,18 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
         const uint32_t n = min((uint32_t)kBlendChunk, count - base);
         if (tid < n) {
             const int32_t gi = __ldg(instanceIdx + start + base + tid);
-            s_valid[tid] = gi >= 0 ? 1u : 0u;
+            uint32_t flags = gi >= 0 ? 1u : 0u;  // bit 0 valid, bit 1 / 2: left / right eye provably beyond the cutoff on this tile
             if (gi >= 0) {
                 const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
-                s_rec[tid][0] = __ldg(src);
+                const uint4 ra = __ldg(src);
+                s_rec[tid][0] = ra;
                 const uint4 rb = __ldg(src + 1);
                 s_rec[tid][1] = rb;
+                // halfs: ra = {LmeanX,LmeanY | Lcxx,Lcyy | Lcxy2,Ldepth | RmeanX,RmeanY}; rb = {Rcxx,Rcyy | Rcxy2,Rdepth | ...}
+                if (eyeTileBeyondCutoff(*reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&ra.y),
+                                        __low2half(*reinterpret_cast<const __half2*>(&ra.z)), tileX * 16u, tileY * 16u)) flags |= 2u;
+                if (eyeTileBeyondCutoff(*reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
+                                        __low2half(*reinterpret_cast<const __half2*>(&rb.y)), tileX * 16u, tileY * 16u)) flags |= 4u;
                 // every thread of the tile would otherwise redo these IEEE divisions for every splat (703 -> 506 us at C4).
                 // Staging the per-column / per-row terms of p as the mono kernel does was tried and is slower here (577 us):
                 // the stereo lists hold every AABB tile, most splats leave at the cutoff test, and the staging is not repaid.
@@ -265,21 +294,25 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
                                         h2bits(__half2half2(__float2half_rn((float)((rb.z >> 8) & 0xFFu) / 255.0f))),
                                         h2bits(__half2half2(__float2half_rn((float)((rb.z >> 16) & 0xFFu) / 255.0f))));
             }
+            s_valid[tid] = flags;
         }
         __syncthreads();
         if (!done) {
             for (uint32_t j = 0; j < n; ++j) {
                 const bool closedL = !doL || quadClosed(qL.T0, qL.T1, thr), closedR = !doR || quadClosed(qR.T0, qR.T1, thr);
                 if (closedL && closedR) { done = true; break; }  // DFS.metal:1868-1871
-                if (!s_valid[j]) continue;
+                const uint32_t flags = s_valid[j];
+                if (!(flags & 1u)) continue;
+                const bool skipL = closedL || (flags & 2u), skipR = closedR || (flags & 4u);
+                if (skipL && skipR) continue;  // nothing this splat can change on this tile
                 const uint4 ra = s_rec[j][0], rb = s_rec[j][1];
                 // halfs: ra = {LmeanX,LmeanY | Lcxx,Lcyy | Lcxy2,Ldepth | RmeanX,RmeanY}; rb = {Rcxx,Rcyy | Rcxy2,Rdepth | r,g,b,op | cDepth,pad}
                 const uint4 sc = s_col[j];
                 const __half2 op = *reinterpret_cast<const __half2*>(&sc.x), cr = *reinterpret_cast<const __half2*>(&sc.y);
                 const __half2 cg = *reinterpret_cast<const __half2*>(&sc.z), cb = *reinterpret_cast<const __half2*>(&sc.w);
-                stereoEye(qL, !closedL, *reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&ra.y),
+                stereoEye(qL, !skipL, *reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&ra.y),
                           __low2half(*reinterpret_cast<const __half2*>(&ra.z)), op, cr, cg, cb, px, py0, py1);
-                stereoEye(qR, !closedR, *reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
+                stereoEye(qR, !skipR, *reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
                           __low2half(*reinterpret_cast<const __half2*>(&rb.y)), op, cr, cg, cb, px, py0, py1);
             }
         }
