@@ -27,6 +27,32 @@ class gsm_camera(C.Structure):
                 ("nearPlane", C.c_float), ("farPlane", C.c_float)]
 
 
+class gsm_viewport(C.Structure):
+    _fields_ = [("originX", C.c_double), ("originY", C.c_double), ("width", C.c_double), ("height", C.c_double)]
+
+
+class gsm_eye_view(C.Structure):
+    _fields_ = [("viewport", gsm_viewport), ("camera", gsm_camera)]
+
+
+class gsm_stereo_configuration(C.Structure):
+    _fields_ = [("leftEye", gsm_eye_view), ("rightEye", gsm_eye_view), ("sceneTransform", C.c_float * 16)]
+
+
+class gsm_rate_map_layer(C.Structure):
+    _fields_ = [("physicalWidth", C.c_uint32), ("physicalHeight", C.c_uint32), ("screenX", C.c_void_p), ("screenY", C.c_void_p)]
+
+
+class gsm_rate_map(C.Structure):
+    _fields_ = [("layerCount", C.c_uint32), ("layers", gsm_rate_map_layer * 2)]
+
+
+class gsm_foveated_drawable(C.Structure):
+    _fields_ = [("colorTexture", C.c_void_p), ("textureWidth", C.c_uint32), ("textureHeight", C.c_uint32),
+                ("arrayLength", C.c_uint32), ("rowBytes", C.c_size_t), ("sliceBytes", C.c_size_t),
+                ("colorPixelFormat", C.c_uint32), ("rasterizationRateMap", C.POINTER(gsm_rate_map))]
+
+
 class gsm_ply_info(C.Structure):  # include/gsm/gsm_scene.h
     _fields_ = [("vertexCount", C.c_uint32), ("format", C.c_uint32), ("compressed", C.c_uint32),
                 ("shProperties", C.c_uint32), ("bodyOffset", C.c_uint64)]
@@ -54,6 +80,10 @@ EXPORTS = {
     "gsm_render_stereo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_uint32, C.c_uint32, C.POINTER(gsm_camera), C.POINTER(gsm_camera),
                                     C.c_uint32, C.c_uint32]),
+    "gsm_render_stereo_foveated": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(gsm_foveated_drawable), C.c_void_p, C.c_void_p,
+                                             C.c_uint32, C.c_uint32, C.POINTER(gsm_stereo_configuration), C.c_uint32, C.c_uint32]),
+    "gsm_stereo_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(gsm_foveated_drawable),
+                                  C.POINTER(gsm_viewport), C.POINTER(gsm_viewport)]),
     "gsm_render_stereo_eyes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint32, C.c_uint32, C.POINTER(gsm_camera), C.POINTER(gsm_camera),
                                          C.c_uint32, C.c_uint32, C.c_uint32]),

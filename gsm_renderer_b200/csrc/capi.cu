@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include <cstdlib>
 #include "gsm_common.cuh"
@@ -152,6 +153,10 @@ struct gsm_renderer {
     void* stDepth = nullptr; size_t stDepthBytes = 0;
     uint32_t lastTilesX = 0, lastTilesY = 0;
     bool lastStereo = false;
+    // StereoRenderTarget.foveated: intermediate image (ensureStereoIntermediateColor, DFR.swift:139-164), rate-map tables, sRGB table
+    void* stereoIntermediate = nullptr; size_t stereoIntermediateBytes = 0;
+    float* rateTables = nullptr; size_t rateTableFloats = 0;
+    uint8_t* srgbLut = nullptr;
 };
 
 namespace gsm {
@@ -417,6 +422,9 @@ void gsm_renderer_destroy(gsm_renderer* r) {
     if (r->stColor) cudaFree(r->stColor);
     if (r->stDepth) cudaFree(r->stDepth);
     if (r->hostStream) cudaStreamDestroy(r->hostStream);
+    if (r->stereoIntermediate) cudaFree(r->stereoIntermediate);
+    if (r->rateTables) cudaFree(r->rateTables);
+    if (r->srgbLut) cudaFree(r->srgbLut);
     delete r;
 }
 
@@ -470,12 +478,12 @@ gsm_status gsm_render_stereo(gsm_renderer* r, void* stream, void* colorSideBySid
                                   width, height, 3u);
 }
 
-gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians,
-                                  const void* harmonics, uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* leftEye,
-                                  const gsm_camera* rightEye, uint32_t width, uint32_t height, uint32_t eyeMask) {
-    if (!r || !leftEye || !rightEye) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
-    if ((eyeMask & 3u) == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "eyeMask selects no eye");
-    if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;  // DFR.swift:478,607
+// encodeStereoPipeline (DFR.swift:595-831) up to and including the blend. sceneTransform == nullptr: identity (sideBySide).
+// The blend writes both eyes side by side into `colorSideBySide` ((2*width) x height rgba16f), rows flipped iff flipY.
+static gsm_status encodeStereoFrame(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians,
+                                    const void* harmonics, uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* leftEye,
+                                    const gsm_camera* rightEye, const float* sceneTransform, uint32_t width, uint32_t height,
+                                    uint32_t eyeMask, bool flipY) {
     gsm_status st = validateFrame(r, width, height, gaussians, harmonics, colorSideBySide);
     if (st != GSM_OK) return st;
     DeviceGuard guard(r->device);
@@ -490,14 +498,18 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     recordStage(r, s, 0);
     const bool zeroInKernel = gaussianCount >= 65536u;  // enough CTAs to clear the region in a few stores per thread
     if (!zeroInKernel) GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
-    // makeStereoCameraUniforms (DFR.swift:554-591): near/far from the left eye, sceneTransform = identity for sideBySide
+    // makeStereoCameraUniforms (DFR.swift:554-591): near/far from the left eye; sceneTransform is the configuration's
+    // (identity for sideBySide, GRP.swift:111)
     StereoCam sc;
     memcpy(sc.leftView, leftEye->viewMatrix, 64); memcpy(sc.leftProj, leftEye->projectionMatrix, 64);
     memcpy(sc.leftCenter, leftEye->position, 12);
     memcpy(sc.rightView, rightEye->viewMatrix, 64); memcpy(sc.rightProj, rightEye->projectionMatrix, 64);
     memcpy(sc.rightCenter, rightEye->position, 12);
-    memset(sc.sceneTransform, 0, 64);
-    sc.sceneTransform[0] = sc.sceneTransform[5] = sc.sceneTransform[10] = sc.sceneTransform[15] = 1.0f;
+    if (sceneTransform) memcpy(sc.sceneTransform, sceneTransform, 64);
+    else {
+        memset(sc.sceneTransform, 0, 64);
+        sc.sceneTransform[0] = sc.sceneTransform[5] = sc.sceneTransform[10] = sc.sceneTransform[15] = 1.0f;
+    }
     sc.width = (float)width; sc.height = (float)height;
     sc.nearPlane = leftEye->nearPlane; sc.farPlane = leftEye->farPlane;
     sc.shComponents = shComponents; sc.gaussianCount = gaussianCount;
@@ -517,9 +529,133 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
     if (st != GSM_OK) return st;
     // steps 9+10: clear, blend both eyes, copy into the side-by-side target (DFR.swift:789-830), fused
     GSM_CUDA(launchBlendStereo(s, res.lowerBounds, (const GSMStereoTiledRenderData*)res.renderData, res.instIdx[0], width, height,
-                               tilesX, tilesY, (__half*)colorSideBySide, (int)(eyeMask & 3u), r->cfg.stereoCopyFlipY ? 1 : 0,
+                               tilesX, tilesY, (__half*)colorSideBySide, (int)(eyeMask & 3u), flipY ? 1 : 0,
                                TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "stereo blend");
     recordStage(r, s, 7);
+    return GSM_OK;
+}
+
+gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSideBySide, const void* gaussians,
+                                  const void* harmonics, uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* leftEye,
+                                  const gsm_camera* rightEye, uint32_t width, uint32_t height, uint32_t eyeMask) {
+    if (!r || !leftEye || !rightEye) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if ((eyeMask & 3u) == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "eyeMask selects no eye");
+    if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;  // DFR.swift:478,607
+    // steps 9+10 fused: at 1:1 the copy (DFR.swift:823-830) is the identity up to the row flip, so the blend writes the target
+    gsm_status st = encodeStereoFrame(r, stream, colorSideBySide, gaussians, harmonics, gaussianCount, shComponents, leftEye, rightEye,
+                                      nullptr, width, height, eyeMask, r->cfg.stereoCopyFlipY != 0);
+    if (st != GSM_OK) return st;
+    recordStage(r, (cudaStream_t)stream, 8);
+    if (r->profiling) r->evRecorded = true;
+    return GSM_OK;
+}
+
+// ---- StereoRenderTarget.foveated
+static size_t pixelBytes(uint32_t format) { return format == GSM_PIXEL_RGBA16F ? 8u : 4u; }
+
+static gsm_status validateDrawable(const gsm_foveated_drawable* d) {
+    if (!d || !d->colorTexture) return fail(GSM_ERR_INVALID_ARGUMENT, "null drawable");
+    if (d->colorPixelFormat > GSM_PIXEL_RGBA8_SRGB) return fail(GSM_ERR_INVALID_ARGUMENT, "unsupported drawable pixel format");
+    if (d->arrayLength < 1 || d->arrayLength > 2) return fail(GSM_ERR_INVALID_ARGUMENT, "drawable arrayLength must be 1 or 2");
+    const size_t px = pixelBytes(d->colorPixelFormat);
+    if (d->textureWidth == 0 || d->textureHeight == 0 || d->rowBytes < (size_t)d->textureWidth * px || (d->rowBytes % px) != 0 ||
+        ((uintptr_t)d->colorTexture % px) != 0)
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "drawable rows must hold textureWidth texels and be texel-aligned");
+    if (d->arrayLength == 2 && (d->sliceBytes < d->rowBytes * d->textureHeight || (d->sliceBytes % px) != 0))
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "drawable slices overlap");
+    if (const gsm_rate_map* m = d->rasterizationRateMap) {
+        if (m->layerCount < 1 || m->layerCount > 2) return fail(GSM_ERR_INVALID_ARGUMENT, "rate map layerCount must be 1 or 2");
+        for (uint32_t l = 0; l < m->layerCount; ++l)
+            if (!m->layers[l].screenX || !m->layers[l].screenY || m->layers[l].physicalWidth == 0 || m->layers[l].physicalHeight == 0)
+                return fail(GSM_ERR_INVALID_ARGUMENT, "rate map layer without tables");
+    }
+    return GSM_OK;
+}
+
+// step 10 (DFR.swift:823-830, DepthFirstStereoCopyEncoder.swift:28-100) from a side-by-side intermediate image
+static gsm_status encodeStereoCopy(gsm_renderer* r, cudaStream_t s, const void* intermediate, uint32_t width, uint32_t height,
+                                   const gsm_foveated_drawable* d, const gsm_viewport* lv, const gsm_viewport* rv) {
+    StereoCopyParams p{};
+    p.src = (const __half*)intermediate; p.srcEyeStride = (size_t)width * 4; p.srcRowStride = (size_t)width * 8;
+    p.width = width; p.height = height;
+    p.dst = d->colorTexture; p.textureWidth = d->textureWidth; p.textureHeight = d->textureHeight; p.arrayLength = d->arrayLength;
+    p.rowBytes = d->rowBytes; p.sliceBytes = d->arrayLength == 2 ? d->sliceBytes : 0; p.format = d->colorPixelFormat;
+    p.flipY = r->cfg.stereoCopyFlipY ? 1 : 0;
+    const gsm_viewport* v[2] = {lv, rv};
+    for (int e = 0; e < 2; ++e) {
+        p.vp[e][0] = (float)v[e]->originX; p.vp[e][1] = (float)v[e]->originY;
+        p.vp[e][2] = (float)v[e]->width; p.vp[e][3] = (float)v[e]->height;
+    }
+    if (d->colorPixelFormat == GSM_PIXEL_BGRA8_SRGB || d->colorPixelFormat == GSM_PIXEL_RGBA8_SRGB) {
+        if (!r->srgbLut) {
+            std::vector<uint8_t> host(kSrgbTableSize);
+            buildSrgbEncodeTable(host.data());
+            GSM_CUDA(cudaMalloc(&r->srgbLut, kSrgbTableSize), "sRGB table");
+            GSM_CUDA(cudaMemcpy(r->srgbLut, host.data(), kSrgbTableSize, cudaMemcpyHostToDevice), "sRGB table upload");
+        }
+        p.srgbLut = r->srgbLut;
+    }
+    if (const gsm_rate_map* m = d->rasterizationRateMap) {
+        size_t need = 0;
+        for (uint32_t l = 0; l < m->layerCount; ++l) need += (size_t)m->layers[l].physicalWidth + m->layers[l].physicalHeight;
+        if (r->rateTableFloats < need) {
+            GSM_CUDA(cudaStreamSynchronize(s), "rate-map tables in use");
+            if (r->rateTables) cudaFree(r->rateTables);
+            r->rateTables = nullptr; r->rateTableFloats = 0;
+            GSM_CUDA(cudaMalloc(&r->rateTables, need * sizeof(float)), "rate-map tables");
+            r->rateTableFloats = need;
+        }
+        // pageable host memory: the copy has left the caller's arrays when the call returns
+        float* at = r->rateTables;
+        p.layerCount = m->layerCount;
+        for (uint32_t l = 0; l < m->layerCount; ++l) {
+            const gsm_rate_map_layer& L = m->layers[l];
+            GSM_CUDA(cudaMemcpyAsync(at, L.screenX, (size_t)L.physicalWidth * 4, cudaMemcpyHostToDevice, s), "rate-map upload");
+            p.screenX[l] = at; at += L.physicalWidth;
+            GSM_CUDA(cudaMemcpyAsync(at, L.screenY, (size_t)L.physicalHeight * 4, cudaMemcpyHostToDevice, s), "rate-map upload");
+            p.screenY[l] = at; at += L.physicalHeight;
+            p.physicalWidth[l] = L.physicalWidth; p.physicalHeight[l] = L.physicalHeight;
+        }
+    }
+    GSM_CUDA(launchStereoCopy(s, p), "stereo copy");
+    return GSM_OK;
+}
+
+gsm_status gsm_stereo_copy(gsm_renderer* r, void* stream, const void* intermediate, uint32_t width, uint32_t height,
+                           const gsm_foveated_drawable* drawable, const gsm_viewport* leftViewport, const gsm_viewport* rightViewport) {
+    if (!r || !intermediate || !leftViewport || !rightViewport) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (width == 0 || height == 0) return fail(GSM_ERR_INVALID_DIMENSIONS, "empty intermediate image");
+    if (((uintptr_t)intermediate & 7u) != 0) return fail(GSM_ERR_INVALID_ARGUMENT, "intermediate image must be 8-byte aligned");
+    gsm_status st = validateDrawable(drawable);
+    if (st != GSM_OK) return st;
+    DeviceGuard guard(r->device);
+    return encodeStereoCopy(r, (cudaStream_t)stream, intermediate, width, height, drawable, leftViewport, rightViewport);
+}
+
+gsm_status gsm_render_stereo_foveated(gsm_renderer* r, void* stream, const gsm_foveated_drawable* drawable, const void* gaussians,
+                                      const void* harmonics, uint32_t gaussianCount, uint32_t shComponents,
+                                      const gsm_stereo_configuration* cfg, uint32_t width, uint32_t height) {
+    if (!r || !cfg) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (gaussianCount == 0 || gaussianCount > r->cfg.maxGaussians) return GSM_OK;  // DFR.swift:524
+    gsm_status st = validateDrawable(drawable);
+    if (st != GSM_OK) return st;
+    if (width == 0 || height == 0 || width > r->cfg.maxWidth || height > r->cfg.maxHeight)
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "dimensions exceed RendererConfig.maxWidth/maxHeight");
+    DeviceGuard guard(r->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t need = (size_t)2 * width * height * 8;
+    if (r->stereoIntermediateBytes < need) {  // ensureStereoIntermediateColor (DFR.swift:139-164)
+        GSM_CUDA(cudaStreamSynchronize(s), "intermediate image in use");
+        if (r->stereoIntermediate) cudaFree(r->stereoIntermediate);
+        r->stereoIntermediate = nullptr; r->stereoIntermediateBytes = 0;
+        GSM_CUDA(cudaMalloc(&r->stereoIntermediate, need), "stereo intermediate image");
+        r->stereoIntermediateBytes = need;
+    }
+    st = encodeStereoFrame(r, stream, r->stereoIntermediate, gaussians, harmonics, gaussianCount, shComponents, &cfg->leftEye.camera,
+                           &cfg->rightEye.camera, cfg->sceneTransform, width, height, 3u, false);
+    if (st != GSM_OK) return st;
+    st = encodeStereoCopy(r, s, r->stereoIntermediate, width, height, drawable, &cfg->leftEye.viewport, &cfg->rightEye.viewport);
+    if (st != GSM_OK) return st;
     recordStage(r, s, 8);
     if (r->profiling) r->evRecorded = true;
     return GSM_OK;

@@ -85,6 +85,27 @@ cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
                               __half* dstSideBySide, int eyeMask, int flipY, TileOut tout);
 
+// foveated stereo copy (stereo_copy.cu): DepthFirstStereoCopyEncoder.swift:28-100 as one resampling kernel
+constexpr uint32_t kSrgbTableSize = 0x3C01u;  // one byte per half in [0, 1]
+struct StereoCopyParams {
+    const __half* src;            // intermediate rgba16f; eye e at src + e * srcEyeStride, rows srcRowStride halfs apart
+    size_t srcEyeStride, srcRowStride;
+    uint32_t width, height;       // per-eye size of the intermediate image
+    void* dst;
+    uint32_t textureWidth, textureHeight, arrayLength;
+    size_t rowBytes, sliceBytes;
+    uint32_t format;              // gsm_pixel_format
+    int flipY;
+    uint32_t layerCount;          // 0 = no rate map
+    uint32_t physicalWidth[2], physicalHeight[2];
+    const float* screenX[2];      // device
+    const float* screenY[2];
+    float vp[2][4];               // {originX, originY, width, height} per eye
+    const uint8_t* srgbLut;       // device, kSrgbTableSize bytes
+};
+void buildSrgbEncodeTable(uint8_t* table);
+cudaError_t launchStereoCopy(cudaStream_t s, const StereoCopyParams& p);
+
 // error reporting shared with scene.cu (thread-local message behind gsm_last_error_string)
 gsm_status reportFailure(gsm_status s, const char* what, cudaError_t e = cudaSuccess);
 // callerScratch: optional device buffer of sortScratchBytes(...) bytes (then nothing is allocated and the stream is not synchronised)

@@ -104,16 +104,125 @@ class RendererConfig:
     backToFront: bool = False                 # ignored by DepthFirst
 
 
+class PixelFormat(enum.IntEnum):
+    """MTLPixelFormat values a drawable's colour texture can have here (gsm_pixel_format)."""
+    rgba16Float = 0
+    bgra8Unorm = 1
+    bgra8Unorm_srgb = 2
+    rgba8Unorm = 3
+    rgba8Unorm_srgb = 4
+
+    @property
+    def bytesPerPixel(self) -> int:
+        return 8 if self == PixelFormat.rgba16Float else 4
+
+
+@dataclass
+class Viewport:
+    """MTLViewport (znear / zfar do not matter to the copy)."""
+    originX: float
+    originY: float
+    width: float
+    height: float
+
+    def to_native(self) -> N.gsm_viewport:
+        return N.gsm_viewport(float(self.originX), float(self.originY), float(self.width), float(self.height))
+
+
+@dataclass
+class EyeView:
+    """EyeView (GRP.swift:68-97)."""
+    viewport: Viewport
+    viewMatrix: Any
+    projectionMatrix: Any
+    cameraPosition: Any
+    focalX: float
+    focalY: float
+    near: float = 0.1
+    far: float = 10.0
+
+    def to_native(self) -> N.gsm_eye_view:
+        cam = CameraParams(self.viewMatrix, self.projectionMatrix, self.cameraPosition, self.focalX, self.focalY, self.near, self.far)
+        return N.gsm_eye_view(self.viewport.to_native(), cam.to_native())
+
+
+@dataclass
+class StereoConfiguration:
+    """StereoConfiguration (GRP.swift:100-117); sceneTransform is a simd_float4x4 (m[col][row]), identity by default."""
+    leftEye: EyeView
+    rightEye: EyeView
+    sceneTransform: Any = None
+
+    def to_native(self) -> N.gsm_stereo_configuration:
+        c = N.gsm_stereo_configuration()
+        c.leftEye, c.rightEye = self.leftEye.to_native(), self.rightEye.to_native()
+        m = np.eye(4, dtype=np.float32) if self.sceneTransform is None else np.asarray(self.sceneTransform, np.float32)
+        c.sceneTransform[:] = m.reshape(16).tolist()
+        return c
+
+
+@dataclass
+class RasterizationRateMap:
+    """What MTLRasterizationRateMap.mapPhysicalToScreenCoordinates returns, tabulated per layer: (screenX float32[physical
+    width], screenY float32[physical height]) = screen coordinates of the physical column / row centres. 1 or 2 layers."""
+    layers: Any
+
+    def to_native(self):
+        m = N.gsm_rate_map()
+        keep = []
+        m.layerCount = len(self.layers)
+        for i, (sx, sy) in enumerate(self.layers):
+            sx, sy = np.ascontiguousarray(sx, np.float32), np.ascontiguousarray(sy, np.float32)
+            keep += [sx, sy]
+            m.layers[i] = N.gsm_rate_map_layer(sx.size, sy.size, sx.ctypes.data, sy.ctypes.data)
+        return m, keep
+
+
+@dataclass
+class FoveatedStereoDrawable:
+    """FoveatedStereoDrawable (GRP.swift:168-193). colorTexture: a device tensor of shape (arrayLength, textureHeight, rowBytes)
+    bytes or anything laid out that way; arrayLength 2 = layered, 1 = shared. The depth texture is not written on this path."""
+    colorTexture: Any
+    textureWidth: int
+    textureHeight: int
+    arrayLength: int = 2
+    rasterizationRateMap: Any = None
+    colorPixelFormat: PixelFormat = PixelFormat.bgra8Unorm_srgb
+    rowBytes: int = 0
+    sliceBytes: int = 0
+    depthTexture: Any = None
+
+    def to_native(self):
+        d = N.gsm_foveated_drawable()
+        d.colorTexture = N.ptr(self.colorTexture)
+        d.textureWidth, d.textureHeight, d.arrayLength = int(self.textureWidth), int(self.textureHeight), int(self.arrayLength)
+        d.rowBytes = int(self.rowBytes) or int(self.textureWidth) * PixelFormat(self.colorPixelFormat).bytesPerPixel
+        d.sliceBytes = int(self.sliceBytes) or d.rowBytes * int(self.textureHeight)
+        d.colorPixelFormat = int(self.colorPixelFormat)
+        keep = None
+        if self.rasterizationRateMap is not None:
+            m, tables = self.rasterizationRateMap.to_native()
+            keep = (m, tables)
+            d.rasterizationRateMap = C.pointer(m)
+        return d, keep
+
+
 @dataclass
 class StereoRenderTarget:
-    """.sideBySide(colorTexture:, depthTexture:) -- the only target on this path; .foveated is out of scope."""
-    colorTexture: Any
+    """StereoRenderTarget (GRP.swift:233-239): .sideBySide(colorTexture:, depthTexture:) or .foveated(drawable:, configuration:)."""
+    colorTexture: Any = None
     depthTexture: Any = None
     kind: str = "sideBySide"
+    drawable: Any = None
+    configuration: Any = None
 
     @staticmethod
     def sideBySide(colorTexture, depthTexture=None) -> "StereoRenderTarget":
         return StereoRenderTarget(colorTexture, depthTexture, "sideBySide")
+
+    @staticmethod
+    def foveated(drawable: FoveatedStereoDrawable, configuration: StereoConfiguration) -> "StereoRenderTarget":
+        return StereoRenderTarget(None, None, "foveated", drawable, configuration)
 
 
 # debugRead* ids (include/gsm/gsm.h gsm_debug_buffer)
@@ -189,14 +298,30 @@ class DepthFirstRenderer:
     def renderStereo(self, commandBuffer, target: StereoRenderTarget, input: GaussianInput,
                      camera: StereoCameraParams, width: int, height: int, eyeMask: int = 3) -> None:
         """eyeMask (bit 0 left, bit 1 right) is the one-eye-per-GPU extension; 3 is the reference behaviour."""
-        if target.kind != "sideBySide":
-            raise NotImplementedError("StereoRenderTarget.foveated needs a rasterization-rate map (visionOS only)")
+        if target.kind == "foveated":  # DFR.swift:225-233: the cameras come from the configuration, `camera` is not read
+            d, keep = target.drawable.to_native()
+            cfg = target.configuration.to_native()
+            _check(self._lib.gsm_render_stereo_foveated(self._h, N.stream_handle(commandBuffer), C.byref(d), N.ptr(input.gaussians),
+                                                        N.ptr(input.harmonics), int(input.gaussianCount), int(input.shComponents),
+                                                        C.byref(cfg), int(width), int(height)))
+            del keep
+            self._stereo_last = True
+            return
         l, r = camera.leftEye.to_native(), camera.rightEye.to_native()
         _check(self._lib.gsm_render_stereo_eyes(self._h, N.stream_handle(commandBuffer), N.ptr(target.colorTexture),
                                                 N.ptr(input.gaussians), N.ptr(input.harmonics),
                                                 int(input.gaussianCount), int(input.shComponents), C.byref(l),
                                                 C.byref(r), int(width), int(height), int(eyeMask)))
         self._stereo_last = True
+
+    def stereoCopy(self, commandBuffer, intermediate, width: int, height: int, drawable: FoveatedStereoDrawable,
+                   leftViewport: Viewport, rightViewport: Viewport) -> None:
+        """gsm_stereo_copy: step 10 alone (DepthFirstStereoCopyEncoder.encodeRender) from a (2*width) x height rgba16f image."""
+        d, keep = drawable.to_native()
+        lv, rv = leftViewport.to_native(), rightViewport.to_native()
+        _check(self._lib.gsm_stereo_copy(self._h, N.stream_handle(commandBuffer), N.ptr(intermediate), int(width), int(height),
+                                         C.byref(d), C.byref(lv), C.byref(rv)))
+        del keep
 
     # -- strip-sharded single frame (multi-GPU helper; gsm_strip_project / gsm_strip_render)
     def stripProject(self, commandBuffer, gaussiansShard, harmonicsShard, gidFirst: int, gidCount: int, shComponents: int,

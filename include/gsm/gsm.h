@@ -100,6 +100,75 @@ gsm_status gsm_render_stereo_eyes(gsm_renderer* r, void* stream, void* colorSide
                                   const gsm_camera* leftEye, const gsm_camera* rightEye, uint32_t width,
                                   uint32_t height, uint32_t eyeMask);
 
+/* ---- StereoRenderTarget.foveated (GRP.swift:168-193, :233-239; DFR.swift:516-551, :789-830;
+ * DepthFirstStereoCopyEncoder.swift:28-100; stereoCopyVertex/Fragment DFS.metal:1984-2018) ----
+ * The reference blends both eyes into an intermediate 2-slice rgba16f array and then draws one full-screen triangle
+ * per eye into the drawable, inside that eye's viewport, through the drawable's MTLRasterizationRateMap; the fragment
+ * samples the eye's slice with a linear, clamp-to-edge sampler. Here that draw is one resampling copy kernel. The rate
+ * map, which Metal keeps opaque, crosses the boundary as what its own mapPhysicalToScreenCoordinates returns: per layer,
+ * the screen-space x of the centre of every physical column and the screen-space y of the centre of every physical row
+ * (the map is separable: MTLRasterizationRateLayerDescriptor has one horizontal and one vertical rate array). */
+typedef enum {
+    GSM_PIXEL_RGBA16F = 0,    /* .rgba16Float */
+    GSM_PIXEL_BGRA8 = 1,      /* .bgra8Unorm */
+    GSM_PIXEL_BGRA8_SRGB = 2, /* .bgra8Unorm_srgb, FoveatedStereoDrawable's default (GRP.swift:184) */
+    GSM_PIXEL_RGBA8 = 3,      /* .rgba8Unorm */
+    GSM_PIXEL_RGBA8_SRGB = 4  /* .rgba8Unorm_srgb */
+} gsm_pixel_format;
+
+/* MTLViewport; znear/zfar do not affect the copy. */
+typedef struct { double originX, originY, width, height; } gsm_viewport;
+
+/* EyeView (GRP.swift:68-97). */
+typedef struct {
+    gsm_viewport viewport;
+    gsm_camera camera;
+} gsm_eye_view;
+
+/* StereoConfiguration (GRP.swift:100-117). sceneTransform: simd_float4x4, column-major. */
+typedef struct {
+    gsm_eye_view leftEye, rightEye;
+    float sceneTransform[16];
+} gsm_stereo_configuration;
+
+/* One layer of a tabulated MTLRasterizationRateMap. screenX[i] / screenY[j]: screen coordinates of the centre of
+ * physical column i / row j (HOST pointers, read during the call). */
+typedef struct {
+    uint32_t physicalWidth, physicalHeight;
+    const float* screenX;
+    const float* screenY;
+} gsm_rate_map_layer;
+
+typedef struct {
+    uint32_t layerCount; /* 1 or 2; slice k of the drawable uses layer min(k, layerCount-1) */
+    gsm_rate_map_layer layers[2];
+} gsm_rate_map;
+
+/* FoveatedStereoDrawable (GRP.swift:168-193). colorTexture: device memory, arrayLength slices of textureHeight rows of
+ * rowBytes bytes, sliceBytes apart. arrayLength 2 = layered (left eye -> slice 0, right eye -> slice 1), 1 = shared (both
+ * viewports in slice 0) (DepthFirstStereoCopyEncoder.swift:88-94). rasterizationRateMap NULL = no foveation. The depth
+ * texture of the drawable is not written on this path (DFR.swift:516-551) and has no field here. */
+typedef struct {
+    void* colorTexture;
+    uint32_t textureWidth, textureHeight, arrayLength;
+    size_t rowBytes, sliceBytes;
+    uint32_t colorPixelFormat; /* gsm_pixel_format */
+    const gsm_rate_map* rasterizationRateMap;
+} gsm_foveated_drawable;
+
+/* GaussianRenderer.renderStereo with StereoRenderTarget.foveated (DFR.swift:225-233, :516-551). width/height are the
+ * per-eye render size of the intermediate image. Texels of the drawable outside both viewports are left untouched. */
+gsm_status gsm_render_stereo_foveated(gsm_renderer* r, void* stream, const gsm_foveated_drawable* drawable,
+                                      const void* gaussians, const void* harmonics, uint32_t gaussianCount,
+                                      uint32_t shComponents, const gsm_stereo_configuration* configuration,
+                                      uint32_t width, uint32_t height);
+
+/* The copy alone (step 10, DFR.swift:823-830): intermediate = rgba16f, (2*width) x height, left eye in columns
+ * [0, width), right eye in [width, 2*width). Exposed for tests and for hosts that keep the intermediate image. */
+gsm_status gsm_stereo_copy(gsm_renderer* r, void* stream, const void* intermediate, uint32_t width, uint32_t height,
+                           const gsm_foveated_drawable* drawable, const gsm_viewport* leftViewport,
+                           const gsm_viewport* rightViewport);
+
 /* Same frame as gsm_render but with HOST buffers: copies inputs host->device, renders, copies the images
  * device->host and synchronises. This is what a host with no device allocator of its own calls (and what
  * bench.py times as `e2e`). hostDepth may be NULL. */

@@ -77,7 +77,7 @@ STAGE_NAMES = ("project", "compact", "depthSort", "applyScan", "expand", "tileSo
 
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (gcc). Building the checker is not using it."""
-    src = [os.path.join(_HERE, f) for f in ("gsm_oracle.c", "gsm_oracle_ply.c", "gsm_oracle.h", "gsmo_math.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("gsm_oracle.c", "gsm_oracle_ply.c", "gsm_oracle_copy.c", "gsm_oracle.h", "gsmo_math.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -273,6 +273,37 @@ class OracleFrame:
                                  C.byref(cam), C.c_uint32(width), C.c_uint32(height), C.c_int(int(flip_y)),
                                  _p(scratch), _p(dst))
         return dst, scratch
+
+
+# ---------------------------------------------------------------- foveated stereo copy (gsm_oracle_copy.c)
+PIXEL_BYTES = {0: 8, 1: 4, 2: 4, 3: 4, 4: 4}
+
+
+def stereo_copy_foveated(color2, flip_y, tex_w, tex_h, array_length, fmt, viewports, rate_layers=None, dst=None, row_bytes=None):
+    """color2: (2, H, W, 4) uint16 halfs. viewports: ((ox, oy, w, h), (ox, oy, w, h)). rate_layers: None or a list of 1-2
+    (screenX float32[physW], screenY float32[physH]). Returns the drawable bytes (array_length, tex_h, row_bytes) uint8;
+    texels no viewport covers keep what `dst` held (0xAB if not given)."""
+    color2 = np.ascontiguousarray(color2, np.uint16)
+    _, H, W, _ = color2.shape
+    px = PIXEL_BYTES[fmt]
+    row_bytes = row_bytes or tex_w * px
+    if dst is None:
+        dst = np.full((array_length, tex_h, row_bytes), 0xAB, np.uint8)
+    layers = rate_layers or []
+    sx = [np.ascontiguousarray(l[0], np.float32) for l in layers]
+    sy = [np.ascontiguousarray(l[1], np.float32) for l in layers]
+    pw = (C.c_uint32 * 2)(*([a.size for a in sx] + [0, 0])[:2])
+    ph = (C.c_uint32 * 2)(*([a.size for a in sy] + [0, 0])[:2])
+    fx = (C.c_void_p * 2)(*([a.ctypes.data for a in sx] + [None, None])[:2])
+    fy = (C.c_void_p * 2)(*([a.ctypes.data for a in sy] + [None, None])[:2])
+    vp = (C.c_double * 8)(*[float(v) for e in viewports for v in e])
+    f = lib().gsmo_stereo_copy_foveated
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t,
+                  C.c_size_t, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(color2), W, H, int(flip_y), _p(dst), tex_w, tex_h, array_length, row_bytes, tex_h * row_bytes, fmt, len(layers),
+      pw, ph, fx, fy, vp)
+    return dst
 
 
 # ---------------------------------------------------------------- scene ingest (gsm_oracle_ply.c)

@@ -20,6 +20,7 @@
 #ifndef GSM_ORACLE_H
 #define GSM_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -193,6 +194,15 @@ void gsmo_blend_stereo(const gsmo_tile_header* headers, const gsmo_stereo_render
  * (NDC(-1,-1) -> uv(0,0): dst row y = src row H-1-y), flipY == 0 copies rows straight. */
 void gsmo_stereo_copy(const gsmo_half* color2, uint32_t width, uint32_t height, int flipY,
                       gsmo_half* dstSideBySide);
+
+/* The same copy through a drawable (FoveatedStereoDrawable, GRP.swift:168-193): any viewports, an optional tabulated
+ * rasterization-rate map, five attachment formats (0 rgba16f, 1 bgra8, 2 bgra8_srgb, 3 rgba8, 4 rgba8_srgb). color2 as
+ * above (two slices). layerCount 0 = no rate map. viewports = {ox, oy, w, h} left then right. gsm_oracle_copy.c. */
+void gsmo_stereo_copy_foveated(const gsmo_half* color2, uint32_t width, uint32_t height, int flipY, uint8_t* dst,
+                               uint32_t textureWidth, uint32_t textureHeight, uint32_t arrayLength, size_t rowBytes,
+                               size_t sliceBytes, int format, uint32_t layerCount, const uint32_t physicalWidth[2],
+                               const uint32_t physicalHeight[2], const float* const screenX[2],
+                               const float* const screenY[2], const double viewports[8]);
 
 /* --- whole frames (DFR.swift:237-465 and :595-831); every intermediate is returned --- */
 typedef struct {
