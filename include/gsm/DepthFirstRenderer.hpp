@@ -71,11 +71,66 @@ struct CameraParams {
 
 struct StereoCameraParams { CameraParams leftEye, rightEye; };
 
-// StereoRenderTarget.sideBySide(colorTexture:depthTexture:) -- rgba16f (2*width) x height
+// MTLViewport / EyeView / StereoConfiguration (GaussianRendererProtocol.swift:68-117)
+struct Viewport { double originX = 0, originY = 0, width = 0, height = 0; };
+
+struct EyeView {
+    Viewport viewport;
+    std::array<float, 16> viewMatrix;
+    std::array<float, 16> projectionMatrix;
+    std::array<float, 3> cameraPosition;
+    float focalX = 0, focalY = 0;
+    float near = 0.1f, far = 10.0f;
+    gsm_eye_view native() const {
+        gsm_eye_view e{};
+        e.viewport = gsm_viewport{viewport.originX, viewport.originY, viewport.width, viewport.height};
+        e.camera = CameraParams{viewMatrix, projectionMatrix, cameraPosition, focalX, focalY, near, far}.native();
+        return e;
+    }
+};
+
+struct StereoConfiguration {
+    EyeView leftEye, rightEye;
+    std::array<float, 16> sceneTransform{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    gsm_stereo_configuration native() const {
+        gsm_stereo_configuration c{};
+        c.leftEye = leftEye.native(); c.rightEye = rightEye.native();
+        for (int i = 0; i < 16; ++i) c.sceneTransform[i] = sceneTransform[i];
+        return c;
+    }
+};
+
+// FoveatedStereoDrawable (GaussianRendererProtocol.swift:168-193); the rate map is the tabulated form of gsm.h
+struct FoveatedStereoDrawable {
+    void* colorTexture = nullptr;
+    uint32_t textureWidth = 0, textureHeight = 0, arrayLength = 2;
+    size_t rowBytes = 0, sliceBytes = 0;               // 0 = tightly packed
+    const gsm_rate_map* rasterizationRateMap = nullptr;
+    gsm_pixel_format colorPixelFormat = GSM_PIXEL_BGRA8_SRGB;
+    gsm_foveated_drawable native() const {
+        gsm_foveated_drawable d{};
+        const size_t px = colorPixelFormat == GSM_PIXEL_RGBA16F ? 8 : 4;
+        d.colorTexture = colorTexture; d.textureWidth = textureWidth; d.textureHeight = textureHeight; d.arrayLength = arrayLength;
+        d.rowBytes = rowBytes ? rowBytes : (size_t)textureWidth * px;
+        d.sliceBytes = sliceBytes ? sliceBytes : d.rowBytes * textureHeight;
+        d.colorPixelFormat = (uint32_t)colorPixelFormat; d.rasterizationRateMap = rasterizationRateMap;
+        return d;
+    }
+};
+
+// StereoRenderTarget (GaussianRendererProtocol.swift:233-239): .sideBySide -- rgba16f (2*width) x height -- or .foveated
 struct StereoRenderTarget {
-    void* colorTexture;
+    void* colorTexture = nullptr;
     void* depthTexture = nullptr;  // ignored by the reference too (DepthFirstRenderer.swift:472)
-    static StereoRenderTarget sideBySide(void* color, void* depth = nullptr) { return StereoRenderTarget{color, depth}; }
+    bool isFoveated = false;
+    FoveatedStereoDrawable drawable;
+    StereoConfiguration configuration;
+    static StereoRenderTarget sideBySide(void* color, void* depth = nullptr) {
+        StereoRenderTarget t; t.colorTexture = color; t.depthTexture = depth; return t;
+    }
+    static StereoRenderTarget foveated(const FoveatedStereoDrawable& drawable, const StereoConfiguration& configuration) {
+        StereoRenderTarget t; t.isFoveated = true; t.drawable = drawable; t.configuration = configuration; return t;
+    }
 };
 
 class DepthFirstRenderer {
@@ -108,6 +163,13 @@ public:
     }
     void renderStereo(void* commandBuffer, const StereoRenderTarget& target, const GaussianInput& input,
                       const StereoCameraParams& camera, int width, int height) {
+        if (target.isFoveated) {  // DepthFirstRenderer.swift:225-233: the eyes come from the configuration
+            gsm_foveated_drawable d = target.drawable.native();
+            gsm_stereo_configuration c = target.configuration.native();
+            check(gsm_render_stereo_foveated(h_, commandBuffer, &d, input.gaussians, input.harmonics, (uint32_t)input.gaussianCount,
+                                             (uint32_t)input.shComponents, &c, (uint32_t)width, (uint32_t)height));
+            return;
+        }
         gsm_camera l = camera.leftEye.native(), r = camera.rightEye.native();
         check(gsm_render_stereo(h_, commandBuffer, target.colorTexture, input.gaussians, input.harmonics,
                                 (uint32_t)input.gaussianCount, (uint32_t)input.shComponents, &l, &r, (uint32_t)width,

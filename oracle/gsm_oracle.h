@@ -15,7 +15,10 @@
  *     (DepthFirstUnitTests.swift:21-117: overflow==0, 0<V<=1000, I>0);
  *   - tile counts, instance order, tile ranges, pixels: PARITY UNPINNED by the reference --
  *     its tests hold no values for them and the Metal path cannot run here, so this oracle
- *     is the sole definition, as BASELINE.json's north_star prescribes.
+ *     is the sole definition, as BASELINE.json's north_star prescribes;
+ *   - foveated stereo copy (gsm_oracle_copy.c): PARITY UNPINNED -- no reference test, and the rate map,
+ *     filter weights and attachment conversion are Metal implementation behaviour; pinned only at 1:1
+ *     against the literal copy (tests/test_foveated_oracle.py).
  */
 #ifndef GSM_ORACLE_H
 #define GSM_ORACLE_H

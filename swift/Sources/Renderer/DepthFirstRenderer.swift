@@ -142,9 +142,75 @@ public struct RendererConfig: Sendable {
     }
 }
 
+/// MTLViewport (znear / zfar do not matter to the copy)
+public struct Viewport: Sendable {
+    public let originX, originY, width, height: Double
+    public init(originX: Double, originY: Double, width: Double, height: Double) {
+        self.originX = originX; self.originY = originY; self.width = width; self.height = height
+    }
+}
+
+public struct EyeView: Sendable {
+    public let viewport: Viewport
+    public let viewMatrix: [Float]
+    public let projectionMatrix: [Float]
+    public let cameraPosition: SIMD3<Float>
+    public let focalX, focalY, near, far: Float
+    public init(viewport: Viewport, viewMatrix: [Float], projectionMatrix: [Float], cameraPosition: SIMD3<Float>,
+                focalX: Float, focalY: Float, near: Float = 0.1, far: Float = 10.0) {
+        self.viewport = viewport; self.viewMatrix = viewMatrix; self.projectionMatrix = projectionMatrix
+        self.cameraPosition = cameraPosition; self.focalX = focalX; self.focalY = focalY; self.near = near; self.far = far
+    }
+    func native() -> gsm_eye_view {
+        var e = gsm_eye_view()
+        e.viewport = gsm_viewport(originX: viewport.originX, originY: viewport.originY, width: viewport.width, height: viewport.height)
+        e.camera = CameraParams(viewMatrix: viewMatrix, projectionMatrix: projectionMatrix, position: cameraPosition,
+                                focalX: focalX, focalY: focalY, near: near, far: far).native()
+        return e
+    }
+}
+
+public struct StereoConfiguration: Sendable {
+    public let leftEye: EyeView
+    public let rightEye: EyeView
+    public let sceneTransform: [Float]   // 16 floats, column-major; identity by default
+    public init(leftEye: EyeView, rightEye: EyeView,
+                sceneTransform: [Float] = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]) {
+        self.leftEye = leftEye; self.rightEye = rightEye; self.sceneTransform = sceneTransform
+    }
+    func native() -> gsm_stereo_configuration {
+        var c = gsm_stereo_configuration()
+        c.leftEye = leftEye.native(); c.rightEye = rightEye.native()
+        withUnsafeMutableBytes(of: &c.sceneTransform) { $0.copyBytes(from: sceneTransform.withUnsafeBytes { Array($0) }) }
+        return c
+    }
+}
+
+/// One layer of MTLRasterizationRateMap, tabulated with its own mapPhysicalToScreenCoordinates: the screen coordinate of the
+/// centre of every physical column / row.
+public struct RasterizationRateLayer: Sendable {
+    public let screenX: [Float]
+    public let screenY: [Float]
+    public init(screenX: [Float], screenY: [Float]) { self.screenX = screenX; self.screenY = screenY }
+}
+
+public struct FoveatedStereoDrawable: Sendable {
+    public let colorTexture: DeviceBuffer
+    public let textureWidth, textureHeight, arrayLength: Int
+    public let rasterizationRateMap: [RasterizationRateLayer]?
+    public let colorPixelFormat: gsm_pixel_format
+    public init(colorTexture: DeviceBuffer, textureWidth: Int, textureHeight: Int, arrayLength: Int = 2,
+                rasterizationRateMap: [RasterizationRateLayer]?, colorPixelFormat: gsm_pixel_format = GSM_PIXEL_BGRA8_SRGB) {
+        self.colorTexture = colorTexture; self.textureWidth = textureWidth; self.textureHeight = textureHeight
+        self.arrayLength = arrayLength; self.rasterizationRateMap = rasterizationRateMap; self.colorPixelFormat = colorPixelFormat
+    }
+}
+
 public enum StereoRenderTarget: Sendable {
     /// left eye on the left half, right eye on the right half of an rgba16f (2*width) x height buffer
     case sideBySide(colorTexture: DeviceBuffer, depthTexture: DeviceBuffer?)
+    /// a drawable with per-eye viewports and an optional rasterization-rate map
+    case foveated(drawable: FoveatedStereoDrawable, configuration: StereoConfiguration)
 }
 
 public protocol GaussianRenderer: AnyObject, Sendable {
@@ -208,11 +274,45 @@ public final class DepthFirstRenderer: GaussianRenderer, @unchecked Sendable {
 
     public func renderStereo(commandBuffer: CommandBuffer, target: StereoRenderTarget, input: GaussianInput,
                              camera: StereoCameraParams, width: Int, height: Int) {
+        if case let .foveated(drawable, configuration) = target {
+            renderFoveated(commandBuffer: commandBuffer, drawable: drawable, configuration: configuration, input: input,
+                           width: width, height: height)
+            return
+        }
         guard case let .sideBySide(colorTexture, _) = target else { return }
         var l = camera.leftEye.native(), r = camera.rightEye.native()
         _ = gsm_render_stereo(handle, commandBuffer.stream, colorTexture.pointer, input.gaussians.pointer,
                               input.harmonics.pointer, UInt32(input.gaussianCount), UInt32(input.shComponents), &l, &r,
                               UInt32(width), UInt32(height))
+    }
+
+    private func renderFoveated(commandBuffer: CommandBuffer, drawable: FoveatedStereoDrawable, configuration: StereoConfiguration,
+                                input: GaussianInput, width: Int, height: Int) {
+        let px = drawable.colorPixelFormat == GSM_PIXEL_RGBA16F ? 8 : 4
+        var d = gsm_foveated_drawable()
+        d.colorTexture = drawable.colorTexture.pointer
+        d.textureWidth = UInt32(drawable.textureWidth); d.textureHeight = UInt32(drawable.textureHeight)
+        d.arrayLength = UInt32(drawable.arrayLength)
+        d.rowBytes = drawable.textureWidth * px; d.sliceBytes = d.rowBytes * drawable.textureHeight
+        d.colorPixelFormat = drawable.colorPixelFormat.rawValue
+        var cfg = configuration.native()
+        func submit(_ map: UnsafePointer<gsm_rate_map>?) {
+            d.rasterizationRateMap = map
+            _ = gsm_render_stereo_foveated(handle, commandBuffer.stream, &d, input.gaussians.pointer, input.harmonics.pointer,
+                                           UInt32(input.gaussianCount), UInt32(input.shComponents), &cfg, UInt32(width), UInt32(height))
+        }
+        guard let layers = drawable.rasterizationRateMap, let first = layers.first else { submit(nil); return }
+        let second = layers.count > 1 ? layers[1] : first
+        first.screenX.withUnsafeBufferPointer { x0 in first.screenY.withUnsafeBufferPointer { y0 in
+        second.screenX.withUnsafeBufferPointer { x1 in second.screenY.withUnsafeBufferPointer { y1 in
+            var m = gsm_rate_map()
+            m.layerCount = UInt32(min(layers.count, 2))
+            m.layers.0 = gsm_rate_map_layer(physicalWidth: UInt32(x0.count), physicalHeight: UInt32(y0.count),
+                                            screenX: x0.baseAddress, screenY: y0.baseAddress)
+            m.layers.1 = gsm_rate_map_layer(physicalWidth: UInt32(x1.count), physicalHeight: UInt32(y1.count),
+                                            screenX: x1.baseAddress, screenY: y1.baseAddress)
+            withUnsafePointer(to: &m) { submit($0) }
+        } } } }
     }
 
     // debugRead* (Tests/RendererTests/DepthFirstUnitTests.swift:911-1252)

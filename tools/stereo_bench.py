@@ -8,8 +8,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gsm_renderer_b200 import synthetic as syn  # noqa: E402
-from gsm_renderer_b200.renderer import (CameraParams, DepthFirstRenderer, GaussianColorSpace, GaussianInput,  # noqa: E402
-                                        RendererConfig, RenderPrecision, StereoCameraParams, StereoRenderTarget)
+from gsm_renderer_b200.renderer import (CameraParams, DepthFirstRenderer, EyeView, FoveatedStereoDrawable,  # noqa: E402
+                                        GaussianColorSpace, GaussianInput, PixelFormat, RasterizationRateMap, RendererConfig,
+                                        RenderPrecision, StereoCameraParams, StereoConfiguration, StereoRenderTarget, Viewport)
+from tests import foveation_util as fv  # noqa: E402
 
 NEAR, FAR = 0.1, 100.0
 
@@ -56,6 +58,43 @@ def main():
         out["stages_ms"] = str(e)
     hd = r.debugReadHeader()
     out["instances"] = int(hd.totalInstances)
+    # StereoRenderTarget.foveated: layered bgra8Unorm_srgb drawable behind a rate map
+    sx, sy = fv.layer(W, H, fv.FOVEATED_H, fv.FOVEATED_V)
+    tw, thh = sx.size, sy.size
+    dst = torch.zeros((2, thh, tw * 4), dtype=torch.uint8, device=dev)
+    d = FoveatedStereoDrawable(dst, tw, thh, 2, RasterizationRateMap([(sx, sy)]), PixelFormat.bgra8Unorm_srgb)
+    L, R = cams.leftEye, cams.rightEye
+    vp = Viewport(0, 0, W, H)
+    cfgs = StereoConfiguration(EyeView(vp, L.viewMatrix, L.projectionMatrix, L.position, L.focalX, L.focalY, L.near, L.far),
+                               EyeView(vp, R.viewMatrix, R.projectionMatrix, R.position, R.focalX, R.focalY, R.near, R.far))
+    target = StereoRenderTarget.foveated(d, cfgs)
+    r.setProfiling(False)
+    ms = []
+    for i in range(13):
+        flush.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s)
+        r.renderStereo(s, target, inp, None, W, H)
+        b.record(s)
+        b.synchronize()
+        if i >= 3:
+            ms.append(a.elapsed_time(b))
+    inter = torch.zeros((H, 2 * W, 4), dtype=torch.int16, device=dev)
+    cp = []
+    for i in range(13):
+        flush.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s)
+        r.stereoCopy(s, inter, W, H, d, vp, vp)
+        b.record(s)
+        b.synchronize()
+        if i >= 3:
+            cp.append(a.elapsed_time(b))
+    copy_bytes = 2 * W * H * 8 + 2 * tw * thh * 4   # every intermediate texel read once + every drawable texel written once
+    out["foveated"] = {"drawable": f"2 x {tw}x{thh} bgra8Unorm_srgb behind a {len(fv.FOVEATED_H)}x{len(fv.FOVEATED_V)}-cell rate map",
+                       "ms_median": float(np.median(ms)), "copy_ms_median": float(np.median(cp)),
+                       "copy_includes": "upload of the rate-map tables + the resampling kernel",
+                       "copy_algorithmic_bytes": copy_bytes, "copy_GBps": copy_bytes / (float(np.median(cp)) * 1e-3) / 1e9}
     print(json.dumps(out))
 
 
