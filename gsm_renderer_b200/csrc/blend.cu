@@ -83,6 +83,25 @@ __device__ __forceinline__ void publishTile(const TileOut& tout, uint32_t tile, 
     if (count > 0) tout.activeTiles[atomicAdd(tout.activeTileCount, 1u)] = tile;
 }
 
+// tools/blend_stats.py builds this file with GSM_BLEND_STATS to count, on the bench workload, how many (warp, splat)
+// evaluations of the inner loop find every lane's alphas zero (diagnostic; not in the product build).
+#ifdef GSM_BLEND_STATS
+__device__ unsigned long long g_blendStats[4];  // warp-evaluations, of those no lane uses the splat, lane-evaluations, of those used
+__device__ __forceinline__ void blendStat(bool use) {
+    const unsigned act = __activemask();
+    const unsigned useMask = __ballot_sync(act, use);
+    if ((threadIdx.x & 31u) == (unsigned)(__ffs(act) - 1)) {
+        atomicAdd(&g_blendStats[0], 1ull);
+        if (useMask == 0u) atomicAdd(&g_blendStats[1], 1ull);
+        atomicAdd(&g_blendStats[2], (unsigned long long)__popc(act));
+        atomicAdd(&g_blendStats[3], (unsigned long long)__popc(useMask));
+    }
+}
+#define GSM_BLEND_STAT(use) blendStat(use)
+#else
+#define GSM_BLEND_STAT(use) do { } while (0)
+#endif
+
 // Staged form of one splat for one tile. p = fma(dx*dy, cxy2, fma(dy*dy, cyy, (dx*dx)*cxx)) (DFS.metal:1770) has a
 // per-COLUMN part T0 = (dx*dx)*cxx and a per-ROW part dy*dy; T0, dy*dy, dx, dy are the same half operations on the
 // same operands whichever thread evaluates them, so they are computed once per (splat, column pair) and (splat,
@@ -94,6 +113,26 @@ struct StagedSplat {
     uint4 m0;      // cxy2|cxy2, op|op, r|r, g|g
     uint4 m1;      // b|b, depth|depth, valid, cyy|cyy
 };
+
+// Alphas of one staged splat on this thread's quad (DFS.metal:1770-1781), branch-free. Returns false when the splat does
+// nothing here: an invalid instance (DFS.metal:1750) or all four alphas zero (:1781) -- which covers p > 35, where
+// -0.5h * p < -17.5 makes the canonical exp exactly +0.
+__device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, unsigned lx, unsigned ly, __half2& a0, __half2& a1) {
+    const uint2 c = sp.col[lx], r = sp.row[ly];
+    const uint4 m0 = sp.m0;
+    const uint2 m1 = *reinterpret_cast<const uint2*>(&sp.m1.z);  // valid, cyy|cyy
+    const __half2 t0 = *reinterpret_cast<const __half2*>(&c.x), dx = *reinterpret_cast<const __half2*>(&c.y);
+    const __half2 dy2p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
+    const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x), cyy = *reinterpret_cast<const __half2*>(&m1.y);
+    const __half2 op = *reinterpret_cast<const __half2*>(&m0.y);
+    const __half2 negHalf = h2(-0.5f), h099 = h2(0.99f);
+    // fma(dx*dy, cxy2, fma(dy*dy, cyy, t0)) for the two rows of the quad
+    const __half2 p0 = __hfma2(__hmul2_rn(dx, __low2half2(dyp)), cxy2, __hfma2(__low2half2(dy2p), cyy, t0));
+    const __half2 p1 = __hfma2(__hmul2_rn(dx, __high2half2(dyp)), cxy2, __hfma2(__high2half2(dy2p), cyy, t0));
+    a0 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p0))), h099);
+    a1 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p1))), h099);
+    return m1.x != 0u && ((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) != 0u;
+}
 
 __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_t* __restrict__ lowerBounds,
                                                                    const BlendSplat* __restrict__ splats,
@@ -113,7 +152,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
 
     const uint32_t baseX = tileX * 16u + lx * 2u, baseY = tileY * 16u + ly * 2u;
     const __half thr = __float2half_rn(1.0f / 255.0f);  // half(1.0h/255.0h): both roundings agree (0x1C04)
-    const __half2 h099 = h2(0.99f), negHalf = h2(-0.5f), zero = h2(0.0f), one = h2(1.0f), farP = h2(35.0f);
+    const __half2 zero = h2(0.0f), one = h2(1.0f);
     // pixel coordinates of the tile as half (quirk Q7): pair k = (16*tile + 2k, +1)
     __half2 pxs[8], pys[8];
 #pragma unroll
@@ -159,28 +198,34 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
         }
         __syncthreads();
         if (!done) {
-            for (uint32_t j = 0; j < n; ++j) {
+            // Two splats per trip: the alphas of splat j+1 do not depend on splat j (only the accumulation does), and
+            // evaluating both before either is accumulated gives each warp four independent exp chains instead of two
+            // (ncu r1_v11: "wait" -- fixed-latency dependency -- was the largest stall, 2.7 warps per issue slot). The
+            // evaluation has no side effect, so doing it for a splat the quad then closes before is invisible. Three and
+            // four per trip were measured too and are slower (106 / 118 registers): profiles/README.md, v12.
+            for (uint32_t j = 0; j < n; j += 2) {
                 if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
-                const StagedSplat& sp = s_sp[j];
-                const uint4 m1 = sp.m1;
-                if (m1.z == 0u) continue;
-                const uint2 c = sp.col[lx], r = sp.row[ly];
-                const uint4 m0 = sp.m0;
-                const __half2 t0 = *reinterpret_cast<const __half2*>(&c.x), dx = *reinterpret_cast<const __half2*>(&c.y);
-                const __half2 dy2p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
-                const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x), cyy = *reinterpret_cast<const __half2*>(&m1.w);
-                // fma(dx*dy, cxy2, fma(dy*dy, cyy, t0)) for the two rows of the quad
-                const __half2 p0 = __hfma2(__hmul2_rn(dx, __low2half2(dyp)), cxy2, __hfma2(__low2half2(dy2p), cyy, t0));
-                const __half2 p1 = __hfma2(__hmul2_rn(dx, __high2half2(dyp)), cxy2, __hfma2(__high2half2(dy2p), cyy, t0));
-                // p > 35 on all four pixels => -0.5h*p < -17.5 => exp() is exactly +0 => alphas are 0 => "continue"
-                // (NaN compares false and takes the full path)
-                if (__hbgt2(p0, farP) && __hbgt2(p1, farP)) continue;
-                const __half2 op = *reinterpret_cast<const __half2*>(&m0.y);
-                const __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p0))), h099);
-                const __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p1))), h099);
-                if (((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) == 0u) continue;  // all(alphas == 0), DFS.metal:1781
-                accumulate(q, a0, a1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
-                           *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
+                const bool second = j + 1u < n;
+                __half2 aA0, aA1, aB0, aB1;
+                const bool useA = evalAlphas(s_sp[j], lx, ly, aA0, aA1);
+                const bool useB = evalAlphas(s_sp[second ? j + 1u : j], lx, ly, aB0, aB1) && second;
+                GSM_BLEND_STAT(useA);
+                if (useA) {
+                    const StagedSplat& sp = s_sp[j];
+                    const uint4 m0 = sp.m0, m1 = sp.m1;
+                    accumulate(q, aA0, aA1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
+                               *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
+                }
+                if (!second) break;
+                // DFS.metal:1746-1747 runs before every splat; T only moved if splat j was used
+                if (useA && quadClosed(q.T0, q.T1, thr)) { done = true; break; }
+                GSM_BLEND_STAT(useB);
+                if (useB) {
+                    const StagedSplat& sp = s_sp[j + 1u];
+                    const uint4 m0 = sp.m0, m1 = sp.m1;
+                    accumulate(q, aB0, aB1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
+                               *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
+                }
             }
         }
         if (__syncthreads_and(done ? 1 : 0)) break;
@@ -377,3 +422,12 @@ cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const
 }
 
 }  // namespace gsm
+
+#ifdef GSM_BLEND_STATS
+extern "C" int gsm_blend_stats_read(unsigned long long* out, int reset) {
+    unsigned long long zero[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out, gsm::g_blendStats, sizeof zero) != cudaSuccess) return 1;
+    if (reset && cudaMemcpyToSymbol(gsm::g_blendStats, zero, sizeof zero) != cudaSuccess) return 1;
+    return 0;
+}
+#endif
