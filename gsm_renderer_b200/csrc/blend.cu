@@ -125,12 +125,12 @@ __device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, unsigned lx, u
     const __half2 dy2p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
     const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x), cyy = *reinterpret_cast<const __half2*>(&m1.y);
     const __half2 op = *reinterpret_cast<const __half2*>(&m0.y);
-    const __half2 negHalf = h2(-0.5f), h099 = h2(0.99f);
+    const __half2 h099 = h2(0.99f);
     // fma(dx*dy, cxy2, fma(dy*dy, cyy, t0)) for the two rows of the quad
     const __half2 p0 = __hfma2(__hmul2_rn(dx, __low2half2(dyp)), cxy2, __hfma2(__low2half2(dy2p), cyy, t0));
     const __half2 p1 = __hfma2(__hmul2_rn(dx, __high2half2(dyp)), cxy2, __hfma2(__high2half2(dy2p), cyy, t0));
-    a0 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p0))), h099);
-    a1 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p1))), h099);
+    a0 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p0)), h099);
+    a1 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p1)), h099);
     return m1.x != 0u && ((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) != 0u;
 }
 
@@ -245,7 +245,7 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
                                           __half2 cr, __half2 cg, __half2 cb, __half2 px, __half2 py0, __half2 py1) {
     if (!eyeOpen) return;
     if (!__hge(__low2half(mean), __float2half_rn(-60000.0f))) return;  // invisible eye: mean = -inf
-    const __half2 negHalf = h2(-0.5f), h099 = h2(0.99f), r2Max = h2(9.0f), zero = h2(0.0f);
+    const __half2 h099 = h2(0.99f), r2Max = h2(9.0f), zero = h2(0.0f);
     const __half2 mx = __low2half2(mean), my = __high2half2(mean);
     const __half2 cxx = __low2half2(cxx_cyy), cyy = __high2half2(cxx_cyy), cxy2 = __half2half2(cxy2h);
     const __half2 dx = __hsub2_rn(px, mx);
@@ -253,8 +253,8 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
     const __half2 out0 = __hgt2(p0, r2Max), out1 = __hgt2(p1, r2Max);  // 1.0 where p > r2Max (false for NaN)
     const uint32_t o0 = h2bits(out0), o1 = h2bits(out1);
     if (o0 == 0x3C003C00u && o1 == 0x3C003C00u) return;  // all four beyond the cutoff: alphas stay 0
-    __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p0))), h099);
-    __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2_packed(__hmul2_rn(negHalf, p1))), h099);
+    __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p0)), h099);
+    __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p1)), h099);
     // per-pixel cutoff: alpha = 0 where p > r2Max
     uint32_t m0 = ((o0 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o0 >> 16) ? 0u : 0xFFFF0000u);
     uint32_t m1 = ((o1 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o1 >> 16) ? 0u : 0xFFFF0000u);

@@ -182,4 +182,26 @@ __device__ __forceinline__ __half2 dhexp2_packed(__half2 x) {
     return __floats2half2_rn(rx, ry);
 }
 
+// exp(-0.5h * p) for the blend's alpha (DFS.metal:1775), with the -0.5 folded into the binary32 constant: -0.5h * p is exact in
+// half except for the smallest subnormals of p (whose exp is 1.0h whichever way the product rounds), scaling a binary32 by 0.5
+// is exact, and the clamp of x to [-17.5, 11.5] is the clamp of p to [-23, 35]. Bit-identical to dhexp2_packed(-0.5h * p) on
+// all 65536 inputs (tests: gsm_probe_math op 12 against the oracle); two packed FMA-pipe multiplies fewer per splat.
+__device__ __forceinline__ __half2 dhexp2_neghalf_packed(__half2 p) {
+    const __half2 pc = __hmin2(__hmax2(p, __float2half2_rn(-23.0f)), __float2half2_rn(35.0f));
+    const float2 pf = __half22float2(pc);
+    const float2 t = __fmul2_rn(pf, make_float2(-0.5f * 1.44269504088896341f, -0.5f * 1.44269504088896341f));
+    const float2 zb = __fadd2_rn(t, make_float2(12582912.0f, 12582912.0f));
+    const float2 n = __fadd2_rn(zb, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), t);  // t - n (the product is exact)
+    float2 q = make_float2(0x1.5f0890p-10f, 0x1.5f0890p-10f);
+    q = __ffma2_rn(q, f, make_float2(0x1.3d1070p-7f, 0x1.3d1070p-7f));
+    q = __ffma2_rn(q, f, make_float2(0x1.c6af6cp-5f, 0x1.c6af6cp-5f));
+    q = __ffma2_rn(q, f, make_float2(0x1.ebf906p-3f, 0x1.ebf906p-3f));
+    q = __ffma2_rn(q, f, make_float2(0x1.62e430p-1f, 0x1.62e430p-1f));
+    q = __ffma2_rn(q, f, make_float2(0x1.000002p+0f, 0x1.000002p+0f));
+    const float rx = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(zb.x) << 23));
+    const float ry = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(zb.y) << 23));
+    return __floats2half2_rn(rx, ry);
+}
+
 }  // namespace gsm

@@ -32,6 +32,12 @@ __global__ void probe_kernel(int op, const void* a, const void* b, void* out, ui
             ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2_packed(v)));
             break;
         }
+        case 12: {  // exp(-0.5h * p), the -0.5 folded into the constant (blend kernels)
+            const unsigned short* ha = (const unsigned short*)a;
+            __half2 v = __halves2half2(__ushort_as_half(ha[i]), __ushort_as_half(ha[i ^ 1u]));
+            ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2_neghalf_packed(v)));
+            break;
+        }
         case 11: {  // fused half FMA: a holds (x, y, z) triples
             const unsigned short* ha = (const unsigned short*)a;
             ((unsigned short*)out)[i] = __half_as_ushort(__hfma(__ushort_as_half(ha[3 * i]), __ushort_as_half(ha[3 * i + 1]), __ushort_as_half(ha[3 * i + 2])));
