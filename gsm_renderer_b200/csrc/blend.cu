@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                                                                    const int32_t* __restrict__ instanceIdx, uint32_t width,
                                                                    uint32_t height, uint32_t tilesX, uint32_t tileRowFirst,
                                                                    __half* __restrict__ color, __half* __restrict__ depth, TileOut tout) {
-    __shared__ StagedSplat s_sp[kBlendChunk];
+    __shared__ StagedSplat s_sp[kBlendChunk + 1];  // + the invalid sentinel that ends an odd chunk
     const unsigned tid = threadIdx.x;
     const unsigned lx = tid & 7u, ly = tid >> 3;
     const uint32_t tileX = blockIdx.x % tilesX, tileY = tileRowFirst + blockIdx.x / tilesX;
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                 sp.m1 = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
             }
         }
+        if (tid == 0) s_sp[n].m1 = make_uint4(0, 0, 0, 0);  // the loop below reads slot j + 1 unconditionally
         __syncthreads();
         if (!done) {
             // Two splats per trip: the alphas of splat j+1 do not depend on splat j (only the accumulation does), and
@@ -205,10 +206,9 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
             // four per trip were measured too and are slower (106 / 118 registers): profiles/README.md, v12.
             for (uint32_t j = 0; j < n; j += 2) {
                 if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
-                const bool second = j + 1u < n;
                 __half2 aA0, aA1, aB0, aB1;
                 const bool useA = evalAlphas(s_sp[j], lx, ly, aA0, aA1);
-                const bool useB = evalAlphas(s_sp[second ? j + 1u : j], lx, ly, aB0, aB1) && second;
+                const bool useB = evalAlphas(s_sp[j + 1u], lx, ly, aB0, aB1);  // slot n is the invalid sentinel
                 GSM_BLEND_STAT(useA);
                 if (useA) {
                     const StagedSplat& sp = s_sp[j];
@@ -216,11 +216,11 @@ __global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_
                     accumulate(q, aA0, aA1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
                                *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
                 }
-                if (!second) break;
-                // DFS.metal:1746-1747 runs before every splat; T only moved if splat j was used
-                if (useA && quadClosed(q.T0, q.T1, thr)) { done = true; break; }
                 GSM_BLEND_STAT(useB);
                 if (useB) {
+                    // DFS.metal:1746-1747 runs before every splat; T only moved if splat j was used. (When splat j + 1 is
+                    // not used the test is simply the one at the top of the next trip.)
+                    if (useA && quadClosed(q.T0, q.T1, thr)) { done = true; break; }
                     const StagedSplat& sp = s_sp[j + 1u];
                     const uint4 m0 = sp.m0, m1 = sp.m1;
                     accumulate(q, aB0, aB1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
