@@ -8,6 +8,6 @@ for lib in "$@" ""; do
   python - "$name" <<'PY'
 import json, sys
 d = json.loads(open("gpurun_out/bench_ab.json").read().strip().splitlines()[-1])
-print(sys.argv[1], round(d["value"], 1), "fps", round(d["ms_per_step"], 4), "ms; blend", round(d["stage_ms"]["blend"], 4), "e2e", round(d["e2e"]["value"], 1))
+print(sys.argv[1], round(d["value"], 1), "fps", round(d["ms_per_step"], 4), "ms;", {k: round(v * 1e3, 1) for k, v in d["stage_ms"].items()}, "e2e", round(d["e2e"]["value"], 1))
 PY
 done
