@@ -130,10 +130,22 @@ def render_stereo_split(renderer, dist, rank: int, world: int, stream, target, g
         return target
     eye = rank % 2
     renderer.renderStereo(stream, StereoRenderTarget.sideBySide(target), gaussian_input, cameras, width, height, eyeMask=1 << eye)
+    # The right half travels as one contiguous byte buffer. With two ranks it goes as a broadcast from rank 1: a collective runs
+    # on all of NCCL's channels, while a point-to-point send of the same 16.6 MB was measured at 2.2-2.8 ms per frame.
+    right = target[:, width:]
+    stage = getattr(renderer, "_stereo_half_stage", None)
+    if stage is None or stage.numel() != right.numel() * right.element_size() or stage.device != target.device:
+        import torch
+        stage = torch.empty(right.numel() * right.element_size(), dtype=torch.uint8, device=target.device)
+        renderer._stereo_half_stage = stage
     if rank == 1:
-        dist.send(_bytes(target[:, width:]), dst=0)
+        stage.view(target.dtype).view(right.shape).copy_(right)
+    if world == 2:
+        dist.broadcast(stage, src=1)
+    elif rank == 1:
+        dist.send(stage, dst=0)
     elif rank == 0:
-        buf = _bytes(target[:, width:])
-        dist.recv(buf, src=1)
-        target[:, width:] = buf.view(target.dtype).view(target[:, width:].shape)
+        dist.recv(stage, src=1)
+    if rank == 0:
+        right.copy_(stage.view(target.dtype).view(right.shape))
     return target
