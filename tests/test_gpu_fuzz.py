@@ -22,3 +22,11 @@ def test_randomised_strip_sweep():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_strips.py"), "16", "11"], capture_output=True, text=True,
                        cwd=ROOT, timeout=600)
     assert r.returncode == 0 and "16 cases, 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_randomised_foveated_copy_sweep():
+    """tools/fuzz_copy.py: random drawables, formats, viewports and rate maps through gsm_stereo_copy, every byte against the oracle."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_copy.py"), "60", "3"], capture_output=True, text=True,
+                       cwd=ROOT, timeout=600)
+    assert r.returncode == 0 and "60 cases, 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
