@@ -265,7 +265,7 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
     accumulate(q, a0, a1, cr, cg, cb, zero, false);
 }
 
-// Exact whole-tile cutoff test for one eye of one splat, run once by the staging thread. The stereo instance lists hold
+// Exact cutoff test for one eye of one splat over a rectangle of the tile (16 columns x `rows` rows), run once by the staging thread. The stereo instance lists hold
 // every tile of the union box (DFS.metal:816-825), so for most (splat, tile) pairs every pixel fails p > r2Max and each of
 // the 64 threads would find that out on its own. With cxx, cyy >= 0 the rounded evaluation
 //   p = RN(m * cxy2 + inner),  m = RN(dx * dy),  inner = RN(RN(dy * dy) * cyy + RN(RN(dx * dx) * cxx))
@@ -273,12 +273,12 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
 // extremes of its four corner products, and RN is monotone, so every pixel's p is >= min(RN(mMin * cxy2 + innerMin),
 // RN(mMax * cxy2 + innerMin)). If that bound exceeds r2Max, every alpha is exactly 0 and the eye is skipped. Any NaN in the
 // bound (0 * inf, inf - inf) makes the comparison false: no skip, the per-pixel path decides.
-__device__ __forceinline__ bool eyeTileBeyondCutoff(__half2 mean, __half2 cxx_cyy, __half cxy2, uint32_t X0, uint32_t Y0) {
+__device__ __forceinline__ bool eyeRectBeyondCutoff(__half2 mean, __half2 cxx_cyy, __half cxy2, uint32_t X0, uint32_t Y0, uint32_t rows) {
     const __half zero = __float2half_rn(0.0f), r2Max = __float2half_rn(9.0f);
     const __half mx = __low2half(mean), my = __high2half(mean), cxx = __low2half(cxx_cyy), cyy = __high2half(cxx_cyy);
     if (!(__hge(cxx, zero) && __hge(cyy, zero))) return false;
     const __half xa = __hsub_rn(__uint2half_rn(X0), mx), xb = __hsub_rn(__uint2half_rn(X0 + 15u), mx);
-    const __half ya = __hsub_rn(__uint2half_rn(Y0), my), yb = __hsub_rn(__uint2half_rn(Y0 + 15u), my);
+    const __half ya = __hsub_rn(__uint2half_rn(Y0), my), yb = __hsub_rn(__uint2half_rn(Y0 + rows - 1u), my);
     const __half dxm = __hgt(xa, zero) ? xa : (__hlt(xb, zero) ? xb : zero);
     const __half dym = __hgt(ya, zero) ? ya : (__hlt(yb, zero) ? yb : zero);
     const __half inner = __hfma(__hmul_rn(dym, dym), cyy, __hmul_rn(__hmul_rn(dxm, dxm), cxx));
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
         const uint32_t n = min((uint32_t)kBlendChunk, count - base);
         if (tid < n) {
             const int32_t gi = __ldg(instanceIdx + start + base + tid);
-            uint32_t flags = gi >= 0 ? 1u : 0u;  // bit 0 valid, bit 1 / 2: left / right eye provably beyond the cutoff on this tile
+            uint32_t flags = gi >= 0 ? 1u : 0u;  // bit 0 valid; bits 1-4: an eye is provably beyond the cutoff on a warp's half of the tile
             if (gi >= 0) {
                 const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
                 const uint4 ra = __ldg(src);
@@ -327,10 +327,16 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
                 const uint4 rb = __ldg(src + 1);
                 s_rec[tid][1] = rb;
                 // halfs: ra = {LmeanX,LmeanY | Lcxx,Lcyy | Lcxy2,Ldepth | RmeanX,RmeanY}; rb = {Rcxx,Rcyy | Rcxy2,Rdepth | ...}
-                if (eyeTileBeyondCutoff(*reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&ra.y),
-                                        __low2half(*reinterpret_cast<const __half2*>(&ra.z)), tileX * 16u, tileY * 16u)) flags |= 2u;
-                if (eyeTileBeyondCutoff(*reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
-                                        __low2half(*reinterpret_cast<const __half2*>(&rb.y)), tileX * 16u, tileY * 16u)) flags |= 4u;
+                // per eye and per warp (warp w blends rows 8w .. 8w+7 of the tile): bits 1,2 = warp 0 left/right, bits 3,4 = warp 1
+                const __half2 mL = *reinterpret_cast<const __half2*>(&ra.x), cL = *reinterpret_cast<const __half2*>(&ra.y);
+                const __half xL = __low2half(*reinterpret_cast<const __half2*>(&ra.z));
+                const __half2 mR = *reinterpret_cast<const __half2*>(&ra.w), cR = *reinterpret_cast<const __half2*>(&rb.x);
+                const __half xR = __low2half(*reinterpret_cast<const __half2*>(&rb.y));
+#pragma unroll
+                for (uint32_t w = 0; w < 2u; ++w) {
+                    if (eyeRectBeyondCutoff(mL, cL, xL, tileX * 16u, tileY * 16u + 8u * w, 8u)) flags |= 2u << (2u * w);
+                    if (eyeRectBeyondCutoff(mR, cR, xR, tileX * 16u, tileY * 16u + 8u * w, 8u)) flags |= 4u << (2u * w);
+                }
                 // every thread of the tile would otherwise redo these IEEE divisions for every splat (703 -> 506 us at C4).
                 // Staging the per-column / per-row terms of p as the mono kernel does was tried and is slower here (577 us):
                 // the stereo lists hold every AABB tile, most splats leave at the cutoff test, and the staging is not repaid.
@@ -348,7 +354,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
                 if (closedL && closedR) { done = true; break; }  // DFS.metal:1868-1871
                 const uint32_t flags = s_valid[j];
                 if (!(flags & 1u)) continue;
-                const bool skipL = closedL || (flags & 2u), skipR = closedR || (flags & 4u);
+                const uint32_t wf = flags >> (2u * (tid >> 5));  // this warp's pair of bits
+                const bool skipL = closedL || (wf & 2u), skipR = closedR || (wf & 4u);
                 if (skipL && skipR) continue;  // nothing this splat can change on this tile
                 const uint4 ra = s_rec[j][0], rb = s_rec[j][1];
                 // halfs: ra = {LmeanX,LmeanY | Lcxx,Lcyy | Lcxy2,Ldepth | RmeanX,RmeanY}; rb = {Rcxx,Rcyy | Rcxy2,Rdepth | r,g,b,op | cDepth,pad}
