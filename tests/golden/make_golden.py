@@ -3,6 +3,8 @@
 Two kinds of fixtures:
   * reference_kats.json -- the known-answer vectors the reference's own tests hold for this path, restated
     (DepthFirstUnitTests.swift:125-145,304 ; :309-317 ; GlobalUnitTests.swift:31-39 ; DepthFirstUnitTests.swift:21-117).
+  * foveated_copy_digests.json -- SHA-256 of the drawable bytes the oracle's foveated stereo copy writes for three seeded cases
+    (oracle self-regression digests, like the next one).
   * oracle_digests.json -- SHA-256 of every white-box buffer and of the pixels of a few small frames rendered by
     the CPU oracle. These are ORACLE self-regression digests (the reference pins no such values); they freeze the
     canonical semantics between rounds and let the CUDA path be checked without re-running the oracle.
@@ -65,6 +67,39 @@ def oracle_digests():
     return out
 
 
+COPY_CASES = {
+    # name: (W, H, format, arrayLength, flip, texture (w, h) or None = from the rate map, viewports, rate-map cell rates or None)
+    "sbs_rgba16f_1to1": (96, 54, 0, 1, True, (192, 54), ((0, 0, 96, 54), (96, 0, 96, 54)), None),
+    "layered_bgra8_srgb_ratemap": (120, 68, 2, 2, True, None, ((0, 0, 120, 68), (0, 0, 120, 68)), ((0.25, 0.5, 1.0, 1.0, 0.5, 0.25), (0.3, 0.75, 1.0, 0.6))),
+    "shared_rgba8_scaled_overlap": (77, 41, 3, 1, False, (150, 60), ((3.25, 2.5, 90.5, 50.75), (60, 5, 80, 44)), None),
+}
+
+
+def copy_case_inputs(name):
+    """Seeded intermediate image + drawable description of one COPY_CASES entry (shared by the CPU and GPU tests)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests")) if os.path.join(ROOT, "tests") not in sys.path else None
+    import foveation_util as fv
+    W, H, fmt, array_length, flip, tex, vps, rates = COPY_CASES[name]
+    rng = np.random.default_rng(sum(name.encode()))
+    c2 = (rng.uniform(-0.1, 1.1, (2, H, W, 4)) if fmt else rng.standard_normal((2, H, W, 4)) * 3).astype(np.float16).view(np.uint16)
+    layers = None
+    if rates:
+        sw, sh_ = max(v[0] + v[2] for v in vps), max(v[1] + v[3] for v in vps)
+        layers = [fv.layer(sw, sh_, rates[0], rates[1])]
+        tex = (layers[0][0].size, layers[0][1].size)
+    return c2, W, H, fmt, array_length, flip, tex, vps, layers
+
+
+def copy_digests():
+    from oracle import binding as ob
+    ob.build()
+    out = {}
+    for name in COPY_CASES:
+        c2, W, H, fmt, array_length, flip, tex, vps, layers = copy_case_inputs(name)
+        out[name] = sha(ob.stereo_copy_foveated(c2, flip, tex[0], tex[1], array_length, fmt, vps, rate_layers=layers))
+    return out
+
+
 def reference_kats():
     r = syn.Drand48(42)
     keys = []
@@ -91,4 +126,5 @@ def reference_kats():
 if __name__ == "__main__":
     json.dump(reference_kats(), open(os.path.join(HERE, "reference_kats.json"), "w"), indent=1, sort_keys=True)
     json.dump(oracle_digests(), open(os.path.join(HERE, "oracle_digests.json"), "w"), indent=1, sort_keys=True)
+    json.dump(copy_digests(), open(os.path.join(HERE, "foveated_copy_digests.json"), "w"), indent=1, sort_keys=True)
     print("wrote", HERE)
