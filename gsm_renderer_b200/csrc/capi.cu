@@ -776,6 +776,9 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     uint32_t* recTouched = res.offsets;
     uint32_t* recKey = res.depthKeys[1];
     uint32_t* recGid = (uint32_t*)res.primIdx[1];
+    // no record at all: nothing below writes the frame header (the compaction's last tile does, and it has no tile), and the
+    // header lies outside the zeroed region -- clear it so that stages 2-7 and the blend see an empty frame, not the previous one
+    if (recordCount == 0) GSM_CUDA(cudaMemsetAsync(res.header, 0, sizeof(GSMDepthFirstHeader), s), "empty-frame header");
     GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po, recTouched, recKey, recGid), "ingest records");
     po.recTouched = recTouched; po.recKey = recKey; po.recGid = recGid;
     po.depthHist = &res.fs->hist[0][0];

@@ -1018,10 +1018,20 @@ static inline int h_eq0(gsmo_half a) { return gsmo_h2f(a) == 0.0f; }
 
 /* d.x*d.x*cxx + d.y*d.y*cyy + d.x*d.y*cxy2 (DFS.metal:1770) with the contraction a fast-math compiler applies
  * to (m0 + m1) + m2: fma(dx*dy, cxy2, fma(dy*dy, cyy, (dx*dx)*cxx)); every other product is a rounded half mul */
+/* Test-only switch (tests/test_blend_conventions.py): 1 = the canonical contracted form (default), 0 = every product
+ * and sum rounded separately -- what SURVEY.md H2 first prescribed. It exists so the distance between the two
+ * conventions is measured instead of asserted; the device implements the contracted form only. */
+static int g_blendContract = 1;
+void gsmo_set_blend_contraction(int on) { g_blendContract = on ? 1 : 0; }
+int gsmo_get_blend_contraction(void) { return g_blendContract; }
+static inline gsmo_half h_mad(gsmo_half a, gsmo_half b, gsmo_half c) {
+    return g_blendContract ? gsmo_hfma(a, b, c) : gsmo_hadd(gsmo_hmul(a, b), c);
+}
+
 static inline gsmo_half h_power(gsmo_half dx, gsmo_half dy, gsmo_half cxx, gsmo_half cyy, gsmo_half cxy2) {
     gsmo_half t0 = gsmo_hmul(gsmo_hmul(dx, dx), cxx);
-    gsmo_half in = gsmo_hfma(gsmo_hmul(dy, dy), cyy, t0);
-    return gsmo_hfma(gsmo_hmul(dx, dy), cxy2, in);
+    gsmo_half in = h_mad(gsmo_hmul(dy, dy), cyy, t0);
+    return h_mad(gsmo_hmul(dx, dy), cxy2, in);
 }
 
 /* DFS.metal:1703-1811 */
@@ -1074,8 +1084,8 @@ void gsmo_blend(const gsmo_tile_header* headers, const gsmo_render_data* gaussia
                     if (allZero) continue;
                     for (int k = 0; k < 4; ++k) {
                         gsmo_half w = gsmo_hmul(a[k], trans[k]);
-                        for (int c = 0; c < 3; ++c) col[k][c] = gsmo_hfma(gc[c], w, col[k][c]);  /* color += gColor * (a*T), contracted */
-                        dep[k] = gsmo_hfma(g.depth, w, dep[k]);
+                        for (int c = 0; c < 3; ++c) col[k][c] = h_mad(gc[c], w, col[k][c]);  /* color += gColor * (a*T), contracted */
+                        dep[k] = h_mad(g.depth, w, dep[k]);
                     }
                     for (int k = 0; k < 4; ++k) trans[k] = gsmo_hmul(trans[k], gsmo_hsub(H_ONE, a[k]));
                 }
@@ -1156,7 +1166,7 @@ void gsmo_blend_stereo(const gsmo_tile_header* headers, const gsmo_stereo_render
                         if (allZero) continue;
                         for (int k = 0; k < 4; ++k) {
                             gsmo_half w = gsmo_hmul(a[k], trans[e][k]);
-                            for (int c = 0; c < 3; ++c) col[e][k][c] = gsmo_hfma(gc[c], w, col[e][k][c]);
+                            for (int c = 0; c < 3; ++c) col[e][k][c] = h_mad(gc[c], w, col[e][k][c]);
                         }
                         for (int k = 0; k < 4; ++k) trans[e][k] = gsmo_hmul(trans[e][k], gsmo_hsub(H_ONE, a[k]));
                     }

@@ -241,6 +241,10 @@ void gsmo_render_stereo(gsmo_frame* f, const void* gaussians, const void* harmon
                         const gsmo_stereo_camera* cam, uint32_t width, uint32_t height, int flipY,
                         gsmo_half* scratchColor2, gsmo_half* dstSideBySide);
 
+/* test-only: blend contraction convention (1 = canonical fused half FMA, 0 = separately rounded mul/add) */
+void gsmo_set_blend_contraction(int on);
+int gsmo_get_blend_contraction(void);
+
 #ifdef __cplusplus
 }
 #endif

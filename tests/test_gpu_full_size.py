@@ -43,11 +43,10 @@ def test_config3_6m_at_4k_gpu(oracle, pu):
     assert res["V"] > 3_000_000 and res["I"] > 10_000_000
 
 
-def test_config4_stereo_1m_gpu(oracle, pu):
+def _stereo_case(oracle, pu, cl, prec, W, H, max_gaussians):
     import torch
     from gsm_renderer_b200.renderer import (CameraParams, DepthFirstRenderer, GaussianColorSpace, GaussianInput, RendererConfig,
                                             RenderPrecision, StereoCameraParams, StereoRenderTarget)
-    cl, prec, W, H = _workload("C2")
     g, h = pu.make_scene_inputs(cl, prec)
     proj = syn.make_projection_matrix(W, H, bench.NEAR, bench.FAR)
     fx, fy = syn.focal_lengths(W, H)
@@ -57,9 +56,9 @@ def test_config4_stereo_1m_gpu(oracle, pu):
                               CameraParams(rv, proj, (0.032, 0, 0), fx, fy, bench.NEAR, bench.FAR))
     ocam = oracle.make_stereo_camera(lv, proj, (-0.032, 0, 0), rv, proj, (0.032, 0, 0), W, H, bench.NEAR, bench.FAR,
                                      cl.sh_components, cl.count, False)
-    fr = oracle.OracleFrame(cl.count, W, H, stereo=True)
+    fr = oracle.OracleFrame(max_gaussians, W, H, stereo=True)
     ref, _ = fr.render_stereo(g, h, oracle.F16, ocam, W, H, flip_y=True)
-    r = DepthFirstRenderer(device=0, config=RendererConfig(maxGaussians=cl.count, maxWidth=W, maxHeight=H,
+    r = DepthFirstRenderer(device=0, config=RendererConfig(maxGaussians=max_gaussians, maxWidth=W, maxHeight=H,
                                                            precision=RenderPrecision.float16,
                                                            gaussianColorSpace=GaussianColorSpace.linear), stereoCopyFlipY=True)
     dev = torch.device("cuda:0")
@@ -71,5 +70,22 @@ def test_config4_stereo_1m_gpu(oracle, pu):
     torch.cuda.synchronize()
     pu.compare_white_box(r, fr, W, H, cl.count, stereo=True)
     pu.compare_pixels(sbs.cpu().numpy().view(np.uint16), ref, True, True, "stereo colour")
-    assert r.debugReadHeader().overflow == 1  # the union boxes exceed 4 * maxGaussians, in the reference too
+    hd = r.debugReadHeader()
+    out = (hd.visibleCount, hd.totalInstances, hd.overflow)
     r.close()
+    return out
+
+
+def test_config4_stereo_1m_gpu(oracle, pu):
+    """C4 at the reference's default capacity (RendererConfig.maxGaussians = 6 000 000, GRP.swift:211-218 => 24 M instances):
+    the union boxes of the 1 M cloud fit, so the frame is complete (overflow == 0), not the nearest 4 M instances."""
+    cl, prec, W, H = _workload("C2")
+    V, I, overflow = _stereo_case(oracle, pu, cl, prec, W, H, 6_000_000)
+    assert overflow == 0 and I > 4_000_000, (V, I, overflow)
+
+
+def test_stereo_instance_overflow_gpu(oracle, pu):
+    """The truncating case stays covered, small: capacity == count, union boxes exceed 4 * maxGaussians (DFS.metal:707)."""
+    cl = syn.synthetic_cloud(60_000, 3, seed=42, scale_median=0.03)
+    V, I, overflow = _stereo_case(oracle, pu, cl, "float16", 1920, 1080, cl.count)
+    assert overflow == 1 and I == 4 * cl.count, (V, I, overflow)
