@@ -115,6 +115,19 @@ EXPORTS = {
                                     C.POINTER(C.c_uint32)]),
     "gsm_strip_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "gsm_group_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "gsm_group_destroy": (None, [C.c_void_p]),
+    "gsm_group_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gsm_group_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gsm_group_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gsm_group_image": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "gsm_group_project_route": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "gsm_group_render_strip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "gsm_group_signal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "gsm_group_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "gsm_render_strips": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                    C.c_uint32, C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "gsm_probe_math": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "gsm_status_string": (C.c_char_p, [C.c_int]),
     "gsm_last_error_string": (C.c_char_p, []),

@@ -346,6 +346,55 @@ void fillMonoCam(MonoCam& mc, const gsm_camera* cam, uint32_t count, uint32_t sh
     mc.tilesX = (w + kTile - 1) / kTile; mc.tilesY = (h + kTile - 1) / kTile;
 }
 
+
+// ---- strip-sharded frame: what the ingest kernels (strip.cu, group.cu) write, and the stages after them
+ProjectOut stripIngestOutputs(gsm_renderer* r, Resources& res) {
+    ProjectOut po;
+    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthKey16 = 0; po.gidFirst = 0;
+    return po;
+}
+
+// Order-preserving compaction of the ingested records (per-record count, key, gid live in three arrays that are free until
+// the depth sort runs), then the same stages 2-8 as the single-GPU frame, blending only tile rows [rowFirst, rowFirst+rowCount).
+// recordCap: host-side bound on the record count; the exact count is read from po.countPtr on the device when that is set.
+gsm_status encodeStripTail(gsm_renderer* r, Resources& res, cudaStream_t s, ProjectOut po, uint32_t recordCap, void* color, void* depth,
+                           uint32_t width, uint32_t height, uint32_t tileRowFirst, uint32_t tileRowCount) {
+    const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
+    po.recTouched = res.offsets; po.recKey = res.depthKeys[1]; po.recGid = (uint32_t*)res.primIdx[1];
+    GSM_CUDA(launchCompactVisible(s, recordCap, po, r->numSMs), "record compaction");  // also writes the header
+    gsm_status st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);  // same stages 2-7 as the single-GPU frame
+    if (st != GSM_OK) return st;
+    GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
+                             tileRowCount, (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "strip blend");
+    return GSM_OK;
+}
+
+
+// Stage 1 + compaction of the gid range [gidFirst, gidFirst+gidCount) of a sharded frame: per-gid outputs keyed by the GLOBAL
+// gid, compacted (key, gid) pairs in ascending gid order in depthKeys[0] / primIdx[0], count in fs->visibleCountRaw.
+gsm_status encodeShardProject(gsm_renderer* r, Resources& res, cudaStream_t s, const void* gaussians, const void* harmonics,
+                              uint32_t gidFirst, uint32_t gidCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width,
+                              uint32_t height) {
+    res.frameGaussians = gidCount;
+    r->lastStereo = false;
+    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    MonoCam mc;
+    fillMonoCam(mc, camera, gidCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
+    ProjectOut po;
+    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
+    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
+    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
+    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
+    po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
+    GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "strip project+cull");
+    GSM_CUDA(launchCompactVisible(s, gidCount, po, r->numSMs), "visibility compaction");
+    return GSM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -729,20 +778,9 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
     st = ensureResources(r, r->mono, false);
     if (st != GSM_OK) return st;
     Resources& res = r->mono;
-    res.frameGaussians = gidCount;
     cudaStream_t s = (cudaStream_t)stream;
-    r->lastStereo = false;
-    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
-    MonoCam mc;
-    fillMonoCam(mc, camera, gidCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
-    ProjectOut po;
-    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
-    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = nullptr; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
-    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
-    po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = gidFirst;
-    GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "strip project+cull");
-    GSM_CUDA(launchCompactVisible(s, gidCount, po, r->numSMs), "visibility compaction");
+    st = encodeShardProject(r, res, s, gaussians, harmonics, gidFirst, gidCount, shComponents, camera, width, height);
+    if (st != GSM_OK) return st;
     GSM_CUDA(launchPackRecords(s, res.fs, res.depthKeys[0], res.primIdx[0], res.renderData, res.bounds, res.hitMask, recordsOut,
                                gidCount, r->numSMs), "pack records");
     GSM_CUDA(cudaMemcpyAsync(hostCount, &res.fs->visibleCountRaw, 4, cudaMemcpyDeviceToHost, s), "count readback");
@@ -766,28 +804,249 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
     cudaStream_t s = (cudaStream_t)stream;
     r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = false;
     GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
-    ProjectOut po;
-    po.fs = res.fs; po.status = res.projStatus; po.statusGroups = res.projGroups; po.renderData = res.renderData; po.bounds = res.bounds;
-    po.nTouched = res.nTouched; po.hitMask = res.hitMask; po.blendSplats = res.blendSplats; po.depthKeys = res.depthKeys[0];
-    po.primitiveIndices = res.primIdx[0]; po.maxOut = res.maxGaussians; po.header = res.header; po.maxInstances = res.maxInstances; po.preDepthKeys = res.depthKeys[1];
-    po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
-    po.depthKey16 = 0; po.gidFirst = 0;
-    // per-record (count, key, gid) for the compaction: three arrays that are free until the depth sort runs
-    uint32_t* recTouched = res.offsets;
-    uint32_t* recKey = res.depthKeys[1];
-    uint32_t* recGid = (uint32_t*)res.primIdx[1];
+    ProjectOut po = stripIngestOutputs(r, res);
     // no record at all: nothing below writes the frame header (the compaction's last tile does, and it has no tile), and the
     // header lies outside the zeroed region -- clear it so that stages 2-7 and the blend see an empty frame, not the previous one
     if (recordCount == 0) GSM_CUDA(cudaMemsetAsync(res.header, 0, sizeof(GSMDepthFirstHeader), s), "empty-frame header");
-    GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po, recTouched, recKey, recGid), "ingest records");
-    po.recTouched = recTouched; po.recKey = recKey; po.recGid = recGid;
-    po.depthHist = &res.fs->hist[0][0];
-    GSM_CUDA(launchCompactVisible(s, recordCount, po, r->numSMs), "record compaction");  // also writes the header
-    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);  // same stages 2-7 as the single-GPU frame
-    if (st != GSM_OK) return st;
-    GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
-                             tileRowCount, (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "strip blend");
+    GSM_CUDA(launchIngestRecords(s, records, recordCount, tileRowFirst, tileRowCount, po, res.offsets, res.depthKeys[1],
+                                 (uint32_t*)res.primIdx[1]), "ingest records");
+    return encodeStripTail(r, res, s, po, recordCount, color, depth, width, height, tileRowFirst, tileRowCount);
+}
+
+// ---------------------------------------------------------------- gsm_group: the strip-sharded frame over peer memory (group.cu)
+struct gsm_group {
+    gsm_renderer* r = nullptr;
+    uint32_t rank = 0, world = 1, regionCap = 0, seq = 0;
+    char* window = nullptr;           // this rank's exchange window: [GroupMailbox | world receive regions | image colour | image depth]
+    size_t windowBytes = 0, oRegions = 0, oImage = 0, imageColorBytes = 0, imageDepthBytes = 0;
+    char* base[kGroupMaxRanks] = {};  // every rank's window as mapped here; base[rank] == window
+    bool ipcOpened[kGroupMaxRanks] = {};
+    uint32_t* routeStatus = nullptr;  // look-back words of the routing kernel
+    size_t routeStatusBytes = 0;
+    bool connected = false;
+};
+
+static gsm_status groupCheck(const gsm_group* g, bool needConnected) {
+    if (!g || !g->r) return fail(GSM_ERR_INVALID_ARGUMENT, "null group");
+    if (needConnected && !g->connected) return fail(GSM_ERR_INVALID_ARGUMENT, "group is not connected (gsm_group_connect / _connect_local)");
     return GSM_OK;
+}
+
+gsm_status gsm_group_create(gsm_renderer* r, uint32_t rank, uint32_t world, uint32_t maxRecordsPerSource, size_t imageColorBytes,
+                            size_t imageDepthBytes, gsm_group** out) {
+    if (!r || !out) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (world < 1 || world > kGroupMaxRanks || rank >= world) return fail(GSM_ERR_INVALID_ARGUMENT, "group of 1..8 ranks, rank < world");
+    if (maxRecordsPerSource == 0 || maxRecordsPerSource > r->cfg.maxGaussians)
+        return fail(GSM_ERR_INVALID_GAUSSIAN_COUNT, "maxRecordsPerSource must be in [1, maxGaussians]");
+    DeviceGuard guard(r->device);
+    gsm_group* g = new (std::nothrow) gsm_group();
+    if (!g) return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "host allocation failed");
+    g->r = r; g->rank = rank; g->world = world; g->regionCap = maxRecordsPerSource;
+    g->oRegions = alignUp(sizeof(GroupMailbox), 256);
+    g->oImage = alignUp(g->oRegions + (size_t)world * maxRecordsPerSource * sizeof(SplatRecord), 256);
+    g->imageColorBytes = alignUp(imageColorBytes, 256); g->imageDepthBytes = alignUp(imageDepthBytes, 256);
+    g->windowBytes = g->oImage + g->imageColorBytes + g->imageDepthBytes;
+    g->routeStatusBytes = (size_t)routeStatusWords(maxRecordsPerSource) * 4u;
+    cudaError_t e = cudaMalloc((void**)&g->window, g->windowBytes);   // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->routeStatus, g->routeStatusBytes);
+    if (e == cudaSuccess) e = cudaMemset(g->window, 0, g->oRegions);   // mailbox: sequence 0 = nothing sent, everything acked
+    if (e != cudaSuccess) {
+        if (g->window) cudaFree(g->window);
+        if (g->routeStatus) cudaFree(g->routeStatus);
+        delete g;
+        return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "exchange window", e);
+    }
+    g->base[rank] = g->window;
+    if (world == 1) g->connected = true;
+    *out = g;
+    return GSM_OK;
+}
+
+gsm_status gsm_group_export(gsm_group* g, void* handleOut) {
+    gsm_status st = groupCheck(g, false);
+    if (st != GSM_OK) return st;
+    if (!handleOut) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GSM_GROUP_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(g->r->device);
+    cudaIpcMemHandle_t h;
+    GSM_CUDA(cudaIpcGetMemHandle(&h, g->window), "cudaIpcGetMemHandle");
+    memcpy(handleOut, &h, sizeof h);
+    return GSM_OK;
+}
+
+gsm_status gsm_group_connect(gsm_group* g, const void* handles) {
+    gsm_status st = groupCheck(g, false);
+    if (st != GSM_OK) return st;
+    if (!handles) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(g->r->device);
+    for (uint32_t p = 0; p < g->world; ++p) {
+        if (p == g->rank || g->base[p]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)p * GSM_GROUP_HANDLE_BYTES, sizeof h);
+        void* mapped = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(GSM_ERR_DEVICE_NOT_AVAILABLE, "cudaIpcOpenMemHandle (peer window; needs NVLink/PCIe peer access)", e);
+        g->base[p] = (char*)mapped;
+        g->ipcOpened[p] = true;
+    }
+    g->connected = true;
+    return GSM_OK;
+}
+
+gsm_status gsm_group_connect_local(gsm_group* g, gsm_group* const* peers) {
+    gsm_status st = groupCheck(g, false);
+    if (st != GSM_OK) return st;
+    if (!peers) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(g->r->device);
+    for (uint32_t p = 0; p < g->world; ++p) {
+        if (p == g->rank) continue;
+        const gsm_group* q = peers[p];
+        if (!q || q->world != g->world || q->rank != p || q->regionCap != g->regionCap)
+            return fail(GSM_ERR_INVALID_ARGUMENT, "peer group does not match (world, rank, maxRecordsPerSource)");
+        if (q->r->device != g->r->device) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, g->r->device, q->r->device);
+            if (!can) return fail(GSM_ERR_DEVICE_NOT_AVAILABLE, "no peer access between the group's devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(q->r->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(GSM_ERR_DEVICE_NOT_AVAILABLE, "cudaDeviceEnablePeerAccess", e);
+            cudaGetLastError();
+        }
+        g->base[p] = q->window;
+    }
+    g->connected = true;
+    return GSM_OK;
+}
+
+void gsm_group_destroy(gsm_group* g) {
+    if (!g) return;
+    DeviceGuard guard(g->r->device);
+    cudaDeviceSynchronize();
+    for (uint32_t p = 0; p < kGroupMaxRanks; ++p)
+        if (g->ipcOpened[p] && g->base[p]) cudaIpcCloseMemHandle(g->base[p]);
+    if (g->window) cudaFree(g->window);
+    if (g->routeStatus) cudaFree(g->routeStatus);
+    delete g;
+}
+
+gsm_status gsm_group_image(gsm_group* g, uint32_t ofRank, void** color, void** depth) {
+    gsm_status st = groupCheck(g, true);
+    if (st != GSM_OK) return st;
+    if (ofRank >= g->world || !g->base[ofRank]) return fail(GSM_ERR_INVALID_ARGUMENT, "rank out of range");
+    if (color) *color = g->imageColorBytes ? g->base[ofRank] + g->oImage : nullptr;
+    if (depth) *depth = g->imageDepthBytes ? g->base[ofRank] + g->oImage + g->imageColorBytes : nullptr;
+    return GSM_OK;
+}
+
+static gsm_status checkStrips(const gsm_group* g, const uint32_t* rowStart, uint32_t tilesY) {
+    if (!rowStart) return fail(GSM_ERR_INVALID_ARGUMENT, "null strip table");
+    if (rowStart[0] != 0 || rowStart[g->world] != tilesY) return fail(GSM_ERR_INVALID_ARGUMENT, "strips must cover tile rows [0, tilesY)");
+    for (uint32_t d = 0; d < g->world; ++d)
+        if (rowStart[d] > rowStart[d + 1]) return fail(GSM_ERR_INVALID_ARGUMENT, "strip table must be non-decreasing");
+    return GSM_OK;
+}
+
+gsm_status gsm_group_project_route(gsm_group* g, void* stream, const void* gaussians, const void* harmonics, uint32_t gidFirst,
+                                   uint32_t gidCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height,
+                                   const uint32_t* stripRowStart) {
+    gsm_status st = groupCheck(g, true);
+    if (st != GSM_OK) return st;
+    gsm_renderer* r = g->r;
+    if (!camera) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (gidCount > g->regionCap) return fail(GSM_ERR_INVALID_GAUSSIAN_COUNT, "shard larger than the group's maxRecordsPerSource");
+    if ((uint64_t)gidFirst + gidCount > r->cfg.maxGaussians) return fail(GSM_ERR_INVALID_GAUSSIAN_COUNT, "gid range exceeds maxGaussians");
+    if (width == 0 || height == 0 || width > r->cfg.maxWidth || height > r->cfg.maxHeight)
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "dimensions exceed RendererConfig.maxWidth/maxHeight");
+    if (gidCount && (!gaussians || !harmonics || !aligned16(gaussians) || !aligned16(harmonics)))
+        return fail(GSM_ERR_INVALID_ARGUMENT, "input buffers must be non-null and 16-byte aligned");
+    st = checkStrips(g, stripRowStart, (height + kTile - 1) / kTile);
+    if (st != GSM_OK) return st;
+    DeviceGuard guard(r->device);
+    st = ensureResources(r, r->mono, false);
+    if (st != GSM_OK) return st;
+    Resources& res = r->mono;
+    cudaStream_t s = (cudaStream_t)stream;
+    g->seq++;   // every rank calls this once per frame: the sequence numbers agree without being exchanged
+    if (gidCount) {
+        st = encodeShardProject(r, res, s, gaussians, harmonics, gidFirst, gidCount, shComponents, camera, width, height);
+        if (st != GSM_OK) return st;
+    } else {
+        GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");  // visibleCountRaw = 0: the routing kernel publishes zero counts
+    }
+    GSM_CUDA(cudaMemsetAsync(g->routeStatus, 0, g->routeStatusBytes, s), "route status memset");
+    RouteParams P{};
+    P.world = g->world; P.rank = g->rank; P.seq = g->seq; P.regionCap = g->regionCap;
+    for (uint32_t d = 0; d <= g->world; ++d) P.rowStart[d] = stripRowStart[d];
+    for (uint32_t d = 0; d < g->world; ++d) {
+        P.region[d] = (SplatRecord*)(g->base[d] + g->oRegions) + (size_t)g->rank * g->regionCap;
+        P.mailbox[d] = (GroupMailbox*)g->base[d];
+    }
+    P.mine = (GroupMailbox*)g->window;
+    GSM_CUDA(launchRouteRecords(s, res.fs, res.depthKeys[0], res.primIdx[0], res.renderData, res.bounds, res.hitMask,
+                                gidCount ? gidCount : 1u, g->routeStatus, P, r->numSMs), "route records");
+    return GSM_OK;
+}
+
+gsm_status gsm_group_render_strip(gsm_group* g, void* stream, void* color, void* depth, uint32_t width, uint32_t height,
+                                  const uint32_t* stripRowStart) {
+    gsm_status st = groupCheck(g, true);
+    if (st != GSM_OK) return st;
+    gsm_renderer* r = g->r;
+    if (!color) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (width == 0 || height == 0 || width > r->cfg.maxWidth || height > r->cfg.maxHeight)
+        return fail(GSM_ERR_INVALID_DIMENSIONS, "dimensions exceed RendererConfig.maxWidth/maxHeight");
+    const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
+    st = checkStrips(g, stripRowStart, tilesY);
+    if (st != GSM_OK) return st;
+    if (g->seq == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "gsm_group_render_strip before gsm_group_project_route");
+    DeviceGuard guard(r->device);
+    st = ensureResources(r, r->mono, false);
+    if (st != GSM_OK) return st;
+    Resources& res = r->mono;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t rowFirst = stripRowStart[g->rank], rowCount = stripRowStart[g->rank + 1] - rowFirst;
+    // a strip receives about 1/world of the frame's splats plus those straddling its borders: picks the sorts' tile size only
+    res.frameGaussians = g->regionCap;
+    r->lastTilesX = tilesX; r->lastTilesY = tilesY; r->lastStereo = false;
+    GSM_CUDA(cudaMemsetAsync(res.fs, 0, res.zeroBytes, s), "frame-state memset");
+    ProjectOut po = stripIngestOutputs(r, res);
+    IngestParams P{};
+    P.world = g->world; P.rank = g->rank; P.seq = g->seq; P.regionCap = g->regionCap;
+    P.rowFirst = (int)rowFirst; P.rowLast = (int)(rowFirst + rowCount) - 1;
+    for (uint32_t sR = 0; sR < g->world; ++sR) {
+        P.region[sR] = (const SplatRecord*)(g->window + g->oRegions) + (size_t)sR * g->regionCap;
+        P.mailbox[sR] = (GroupMailbox*)g->base[sR];
+    }
+    P.mine = (GroupMailbox*)g->window;
+    GSM_CUDA(launchIngestRouted(s, P, po, res.offsets, res.depthKeys[1], (uint32_t*)res.primIdx[1], r->numSMs), "ingest routed records");
+    po.countPtr = &res.fs->recordTotal;
+    return encodeStripTail(r, res, s, po, res.maxGaussians, color, depth, width, height, rowFirst, rowCount);
+}
+
+gsm_status gsm_group_signal(gsm_group* g, void* stream, uint32_t toRank, uint32_t frameId) {
+    gsm_status st = groupCheck(g, true);
+    if (st != GSM_OK) return st;
+    if (toRank >= g->world) return fail(GSM_ERR_INVALID_ARGUMENT, "rank out of range");
+    DeviceGuard guard(g->r->device);
+    GSM_CUDA(launchGroupSignal((cudaStream_t)stream, (GroupMailbox*)g->base[toRank], g->rank, frameId), "group signal");
+    return GSM_OK;
+}
+
+gsm_status gsm_group_wait(gsm_group* g, void* stream, uint32_t fromMask, uint32_t frameId) {
+    gsm_status st = groupCheck(g, true);
+    if (st != GSM_OK) return st;
+    DeviceGuard guard(g->r->device);
+    GSM_CUDA(launchGroupWait((cudaStream_t)stream, (const GroupMailbox*)g->window, fromMask & ((1u << g->world) - 1u), frameId), "group wait");
+    return GSM_OK;
+}
+
+gsm_status gsm_render_strips(gsm_group* g, void* stream, void* color, void* depth, const void* gaussians, const void* harmonics,
+                             uint32_t gidFirst, uint32_t gidCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width,
+                             uint32_t height, const uint32_t* stripRowStart) {
+    gsm_status st = gsm_group_project_route(g, stream, gaussians, harmonics, gidFirst, gidCount, shComponents, camera, width, height,
+                                            stripRowStart);
+    if (st != GSM_OK) return st;
+    return gsm_group_render_strip(g, stream, color, depth, width, height, stripRowStart);
 }
 
 double gsm_last_gpu_time_ms(gsm_renderer* r) {

@@ -52,8 +52,13 @@ struct FrameState {
     uint32_t ticketScan;
     uint32_t ticketSort[8];      // depth passes 0-3, tile passes 4-7
     uint32_t rangesDone;         // CTAs of the tile-range kernel that finished their boundary scan
-    uint32_t _pad[2];
+    uint32_t ticketRoute;        // group.cu: tiles of the record-routing kernel
+    uint32_t routeDone;          // group.cu: CTAs of the routing kernel that have issued all their (remote) stores
     uint32_t hist[8][256];       // global digit histograms: depth passes 0-3, tile passes 4-7
+    uint32_t routeTotals[8];     // group.cu: records routed to each destination rank this frame
+    uint32_t ingestDone;         // group.cu: CTAs of the ingest kernel that have read all their records
+    uint32_t recordTotal;        // group.cu: records received from all sources this frame (device-side N of the compaction)
+    uint32_t _pad2[6];
 };
 
 // What the blend stage reads per splat: the quantised record pre-expanded once per visible Gaussian
@@ -69,6 +74,28 @@ struct __align__(16) BlendSplat {
     uint32_t _pad[2];
 };
 static_assert(sizeof(BlendSplat) == 32, "BlendSplat is 32 bytes");
+
+// What travels between ranks in the strip-sharded frame (strip.cu, group.cu): one compacted, projected splat.
+// Records stay in ascending global gid order per source, so the stable depth sort breaks ties as on one GPU.
+struct __align__(16) SplatRecord {
+    uint4 renderData;
+    int4 bounds;
+    uint32_t key, maskLo, maskHi, gid;  // mask: stage 1's hit bits of the first 64 AABB tiles (gsm_tiletest.cuh)
+};
+static_assert(sizeof(SplatRecord) == GSM_SPLAT_RECORD_BYTES, "record size");
+
+// system-scope flag traffic between GPUs (mailboxes in peer memory, group.cu)
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Camera constants as the kernels take them (by value, __grid_constant__).
 struct MonoCam {

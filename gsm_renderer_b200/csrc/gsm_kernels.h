@@ -16,6 +16,7 @@ struct ProjectOut {
     const uint32_t* recTouched = nullptr;  // strip ingest: the compaction runs over gathered records (count, key, gid per record)
     const uint32_t* recKey = nullptr;
     const uint32_t* recGid = nullptr;
+    const uint32_t* countPtr = nullptr;    // if set, the compaction reads its element count from the device (routed records, group.cu)
     uint32_t* preDepthKeys;       // per gid, before compaction (the reference aliases the sort scratch for it, DFR.swift:282)
     uint32_t* depthKeys;          // compacted, ascending gid
     int32_t* primitiveIndices;
@@ -118,6 +119,37 @@ cudaError_t launchPackRecords(cudaStream_t s, const FrameState* fs, const uint32
                               const int32_t* bounds, const uint2* hitMask, void* out, uint32_t cap, int numSMs);
 cudaError_t launchIngestRecords(cudaStream_t s, const void* records, uint32_t recordCount, uint32_t rowFirst, uint32_t rowCount,
                                 const ProjectOut& o, uint32_t* recTouched, uint32_t* recKey, uint32_t* recGid);
+
+// strip-sharded frame over peer memory (group.cu): the exchange is the routing kernel's own stores into the peers' windows
+constexpr uint32_t kGroupMaxRanks = 8;
+struct GroupMailbox {                      // head of every rank's exchange window; written by peers over NVLink
+    uint32_t recordCount[kGroupMaxRanks];  // [s]: records source s routed to this rank ...
+    uint32_t recordSeq[kGroupMaxRanks];    // [s]: ... for frame recordSeq[s] (release-stored after the records and the count)
+    uint32_t ack[kGroupMaxRanks];          // [d]: destination d has consumed this rank's records of frame ack[d]
+    uint32_t frameDone[kGroupMaxRanks];    // [s]: rank s's strip / eye of frame frameDone[s] is in this rank's image
+};
+struct RouteParams {
+    uint32_t world, rank, seq, regionCap;     // regionCap: records per (destination, source) region
+    uint32_t rowStart[kGroupMaxRanks + 1];    // strip d = tile rows [rowStart[d], rowStart[d+1])
+    SplatRecord* region[kGroupMaxRanks];      // [d]: THIS rank's region inside destination d's window (peer-mapped)
+    GroupMailbox* mailbox[kGroupMaxRanks];    // [d]: destination d's mailbox (peer-mapped)
+    GroupMailbox* mine;
+};
+struct IngestParams {
+    uint32_t world, rank, seq, regionCap;
+    int rowFirst, rowLast;
+    const SplatRecord* region[kGroupMaxRanks];  // [s]: source s's region inside THIS rank's window (local memory)
+    GroupMailbox* mailbox[kGroupMaxRanks];      // [s]: source s's mailbox (peer-mapped), for the ack
+    GroupMailbox* mine;
+};
+uint32_t routeStatusWords(uint32_t maxRecords);
+cudaError_t launchRouteRecords(cudaStream_t s, FrameState* fs, const uint32_t* keys, const int32_t* gids, const void* renderData,
+                               const int32_t* bounds, const uint2* hitMask, uint32_t cap, uint32_t* status, const RouteParams& P,
+                               int numSMs);
+cudaError_t launchIngestRouted(cudaStream_t s, const IngestParams& P, const ProjectOut& o, uint32_t* recTouched, uint32_t* recKey,
+                               uint32_t* recGid, int numSMs);
+cudaError_t launchGroupSignal(cudaStream_t s, GroupMailbox* to, uint32_t rank, uint32_t seq);
+cudaError_t launchGroupWait(cudaStream_t s, const GroupMailbox* mine, uint32_t mask, uint32_t seq);
 
 // math probes (probe.cu)
 cudaError_t launchProbe(cudaStream_t s, int op, const void* a, const void* b, void* out, uint32_t n);

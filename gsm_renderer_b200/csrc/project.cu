@@ -720,10 +720,19 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
     __shared__ uint32_t s_tile, s_baseVisible;
     __shared__ uint32_t s_hist[4][256];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t numTiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
     pdlLaunchDependents();
     for (int i = tid; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
     pdlWait();
+    if (o.countPtr) N = min(*o.countPtr, N);  // routed records: the count exists only on the device
+    const uint32_t numTiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
+    if (numTiles == 0u) {  // nothing arrived: no last tile will write the header
+        if (blockIdx.x == 0 && tid == 0) {
+            o.fs->visibleCountRaw = 0u;
+            o.fs->totalInstancesRaw = 0u;
+            if (o.header) writeFrameHeader(o.header, 0u, 0u, o.maxOut, o.maxInstances);
+        }
+        return;
+    }
     __syncthreads();
     while (true) {
         if (tid == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);

@@ -11,12 +11,7 @@
 
 namespace gsm {
 
-struct __align__(16) SplatRecord {
-    uint4 renderData;
-    int4 bounds;
-    uint32_t key, maskLo, maskHi, gid;  // mask: stage 1's hit bits of the first 64 AABB tiles (gsm_tiletest.cuh)
-};
-static_assert(sizeof(SplatRecord) == GSM_SPLAT_RECORD_BYTES, "record size");
+// SplatRecord: gsm_common.cuh
 
 __global__ void __launch_bounds__(256) pack_records_kernel(const FrameState* __restrict__ fs, const uint32_t* __restrict__ keys,
                                                            const int32_t* __restrict__ gids, const void* __restrict__ renderData,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GSM_ABI_VERSION 1
+#define GSM_ABI_VERSION 2
 
 /* RendererError (GRP.swift:274-324), one code per case that can arise on this path. */
 typedef enum {
@@ -236,7 +236,8 @@ gsm_status gsm_stream_destroy(void* stream);
 gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* payload, uint32_t count,
                           int keyBits, int numPasses);
 
-/* Multi-GPU helpers with no reference counterpart: a single large frame split into
+/* Strip-sharded frame, library-collective form (kept as the baseline the peer-memory path above is measured against, and for
+ * hosts without peer access): a single large frame split into
  * horizontal strips of whole tile rows. Step 1 (per rank): project+cull the gid range
  * [gidFirst, gidFirst+gidCount) and emit compacted 48-byte splat records (count in *hostCount after the
  * call synchronises). Step 2 (per rank, after an all-gather of the records in rank order): sort, expand,
@@ -249,6 +250,49 @@ gsm_status gsm_strip_project(gsm_renderer* r, void* stream, const void* gaussian
 gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* depth, const void* records,
                             uint32_t recordCount, uint32_t width, uint32_t height, uint32_t tileRowFirst,
                             uint32_t tileRowCount);
+
+/* ---- gsm_group: one frame split over the GPUs of one node by horizontal strips of whole tile rows (SURVEY.md 8e, config C3;
+ * no reference counterpart -- the reference is single-device). One process (or thread) per GPU, one renderer + one group
+ * handle per rank. Every rank owns an EXCHANGE WINDOW in its HBM -- a mailbox, one receive region per source rank and an
+ * optional frame image -- that every peer maps (cudaIpc between processes: gsm_group_export / gsm_group_connect carry the
+ * 64-byte handles over whatever channel the host has; gsm_group_connect_local for ranks living in one process). A frame:
+ *   gsm_group_project_route  projects + culls the rank's gid range and STORES each surviving 48-byte splat record straight
+ *                            into the window of every rank whose strip it touches (NVLink peer stores issued by the routing
+ *                            kernel itself, order-preserving per destination; counts and completion flags travel the same way);
+ *   gsm_group_render_strip   waits (on the device) for all sources, ingests only the records of its own strip in global gid
+ *                            order, then sorts, expands, tile-sorts and blends tile rows [rowStart[rank], rowStart[rank+1])
+ *                            into `color` / `depth` -- full-size images, which may be another rank's window image
+ *                            (gsm_group_image), so the frame is assembled by the blend's own stores;
+ *   gsm_group_signal / gsm_group_wait  "my part of frame `frameId` is in rank `toRank`'s image" / the image's owner waits, on
+ *                            the device, for the ranks in `fromMask`. frameId: any number that grows from frame to frame and
+ *                            is the same on all ranks.
+ * No call synchronises the host or returns a count to it; all ranks must issue the same sequence of frames (collective
+ * semantics). Per-strip lists are bit-identical to the single-GPU frame's (records arrive in global gid order, so the stable
+ * depth sort breaks ties the same way); the 4*maxGaussians instance cap applies per strip. */
+typedef struct gsm_group gsm_group;
+#define GSM_GROUP_HANDLE_BYTES 64
+#define GSM_GROUP_MAX_RANKS 8
+/* maxRecordsPerSource: the largest gid shard any rank will project (e.g. ceil(N / world)); imageColorBytes / imageDepthBytes:
+ * size of the window's frame image (0 = none). The renderer's maxGaussians must cover the WHOLE scene (global gids). */
+gsm_status gsm_group_create(gsm_renderer* r, uint32_t rank, uint32_t world, uint32_t maxRecordsPerSource,
+                            size_t imageColorBytes, size_t imageDepthBytes, gsm_group** out);
+void gsm_group_destroy(gsm_group* g);
+gsm_status gsm_group_export(gsm_group* g, void* handleOut /* GSM_GROUP_HANDLE_BYTES */);
+gsm_status gsm_group_connect(gsm_group* g, const void* handles /* world * GSM_GROUP_HANDLE_BYTES, rank order */);
+gsm_status gsm_group_connect_local(gsm_group* g, gsm_group* const* peers /* world handles of this process, rank order */);
+gsm_status gsm_group_image(gsm_group* g, uint32_t ofRank, void** color, void** depth);
+/* stripRowStart: world + 1 tile-row boundaries, stripRowStart[0] == 0, stripRowStart[world] == tilesY, non-decreasing. */
+gsm_status gsm_group_project_route(gsm_group* g, void* stream, const void* gaussiansShard, const void* harmonicsShard,
+                                   uint32_t gidFirst, uint32_t gidCount, uint32_t shComponents, const gsm_camera* camera,
+                                   uint32_t width, uint32_t height, const uint32_t* stripRowStart);
+gsm_status gsm_group_render_strip(gsm_group* g, void* stream, void* color, void* depth, uint32_t width, uint32_t height,
+                                  const uint32_t* stripRowStart);
+gsm_status gsm_group_signal(gsm_group* g, void* stream, uint32_t toRank, uint32_t frameId);
+gsm_status gsm_group_wait(gsm_group* g, void* stream, uint32_t fromMask, uint32_t frameId);
+/* gsm_group_project_route followed by gsm_group_render_strip (ranks in separate processes / on separate streams). */
+gsm_status gsm_render_strips(gsm_group* g, void* stream, void* color, void* depth, const void* gaussiansShard,
+                             const void* harmonicsShard, uint32_t gidFirst, uint32_t gidCount, uint32_t shComponents,
+                             const gsm_camera* camera, uint32_t width, uint32_t height, const uint32_t* stripRowStart);
 
 /* Math probes: run the device restatement of the canonical transcendental definitions on arrays, so the
  * tests can compare them bit-for-bit with the CPU oracle. op: 0 sin, 1 cos, 2 log, 3 atan2(a,b),

@@ -47,6 +47,43 @@ def main():
     assert torch.equal(out[y0:y1], ref[y0:y1]), f"rank {rank}: strip differs"
     if rank == 0:
         assert torch.equal(out, ref), "assembled frame differs from the single-GPU frame"
+    # ---- the same frame over peer memory (gsm_group): routing kernel stores records into the peers' windows, every rank blends
+    # its strip straight into rank 0's window image; several frames with moving cameras exercise the ack / sequence protocol
+    cap = max(cc for _, cc in mg.partition_range(cl.count, world))
+    grp = mg.RendererGroup(r, rank, world, cap, W * H * 8, W * H * 2)
+    grp.connect_distributed(dist)
+    rows = mg.strip_row_starts(strips)
+    pc, pd = grp.image_ptrs(0)                        # rank 0's image as mapped on this rank (raw device pointers)
+    if rank == 0:
+        img_c, img_d = grp.image_tensors(0, W, H, dev)
+    from tests.test_gpu_group import _cams
+    cams3 = _cams(W, H)
+    refd = torch.zeros((H, W), dtype=torch.int16, device=dev)
+    for f, camf in enumerate([cam, cams3[1], cams3[2], cam, cams3[1]], start=1):
+        r.render(s, ref, refd, GaussianInput(tg, th, cl.count, 16), camf, W, H)   # single-GPU frame (arena is re-used below)
+        torch.cuda.synchronize()
+        dist.barrier()                       # rank 0's previous comparison is over before anyone overwrites its image
+        grp.renderStrips(s, pc, pd, shard_g, shard_h, a, c, 16, camf, W, H, rows)
+        grp.signal(s, 0, f)
+        if rank == 0:
+            grp.wait(s, (1 << world) - 1, f)
+            torch.cuda.synchronize()
+            assert torch.equal(img_c, ref), f"peer-memory frame {f}: assembled colour differs from the single-GPU frame"
+            assert torch.equal(img_d, refd), f"peer-memory frame {f}: assembled depth differs from the single-GPU frame"
+        torch.cuda.synchronize()
+    # back to back without host synchronisation in between (flow control on the device only)
+    for f in range(6, 26):
+        grp.renderStrips(s, pc, pd, shard_g, shard_h, a, c, 16, cam if f % 2 else cams3[1], W, H, rows)
+        grp.signal(s, 0, f)
+        if rank == 0:
+            grp.wait(s, (1 << world) - 1, f)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        r.render(s, ref, refd, GaussianInput(tg, th, cl.count, 16), cam, W, H)
+        torch.cuda.synchronize()
+        assert torch.equal(img_c, ref) and torch.equal(img_d, refd), "peer-memory frames back to back: last frame differs"
+    dist.barrier()
     # stereo: one eye per GPU
     if world >= 2:
         cams = _stereo_inputs(960, 540)
@@ -62,10 +99,30 @@ def main():
         torch.cuda.synchronize()
         if rank == 0:
             assert torch.equal(tgt, joint), "eye-split stereo differs from the joint frame"
+        # the same split with the right eye blended straight into rank 0's window image over NVLink (no copy, no collective)
+        sgrp = mg.RendererGroup(rs, rank, world, 1, 540 * 1920 * 8, 0)
+        sgrp.connect_distributed(dist)
+        sp, _ = sgrp.image_ptrs(0)
+        if rank == 0:
+            simg, _ = sgrp.image_tensors(0, 1920, 540, dev, depth=False)
+            simg.fill_(0x7E00)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank < 2:
+            rs.renderStereo(s, StereoRenderTarget.sideBySide(sp), inp, cams, 960, 540, eyeMask=1 << rank)
+            sgrp.signal(s, 0, 1)
+        if rank == 0:
+            sgrp.wait(s, 0b11, 1)
+            torch.cuda.synchronize()
+            assert torch.equal(simg, joint), "peer-memory eye split differs from the joint frame"
+        torch.cuda.synchronize()
+        dist.barrier()
+        sgrp.close()
         rs.close()
     dist.barrier()
     if rank == 0:
         print("MGPU_OK", counts)
+    grp.close()
     r.close()
     dist.destroy_process_group()
 

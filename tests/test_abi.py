@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(native):
     for s in syms:
         assert hasattr(lib, s), f"libgsm_b200.so does not export {s}"
     assert set(syms) == set(native.EXPORTS), "python binding table and header diverged"
-    assert lib.gsm_abi_version() == 1
+    assert lib.gsm_abi_version() == 2
 
 
 def test_header_compiles_as_c_and_layouts_match():
