@@ -12,6 +12,10 @@ through gsm_render (C ABI). Prints ONE JSON line (rank 0):
   roofline     dominant kernel: algorithmic bytes / its measured duration vs the
                measured HBM peak of MEASURED_PEAKS.json; stage_roofline lists every stage
   cpu_baseline the CPU oracle (a port of the reference's Metal kernels) timed on this box's cores (rank 0, N=1)
+  modes        (bench_modes.py) the multi-GPU shard modes of SURVEY.md 8(e) measured in the same run: c3_strips (6 M, 3840x2160,
+               one frame split by strips over the ranks, exchange = the routing kernel's NVLink peer stores, assembled image
+               checked against rank 0's single-GPU frame), c5_views (256 orbit poses of 3 M at 720p split by view), c4_eyes
+               (stereo, one eye per GPU). At N=1 they report the single-GPU numbers the N>1 efficiencies are relative to.
 --impl reference times that CPU implementation alone on the same config (the Metal reference cannot run here).
 """
 from __future__ import annotations
@@ -56,8 +60,7 @@ def stage_bytes(N, V, Vp, I, T, P, rec_bytes, sh_bytes):
     return {
         "project": N * (rec_bytes + 24) + Vp * sh_bytes + 16 * V,
         "depthSort": 68 * V,
-        "applyScan": 20 * V,
-        "expand": 40 * V + 6 * I,
+        "expand": 60 * V + 6 * I,   # apply-order + prefix sum (20 V) run inside the expansion kernel: their bytes belong to it
         "tileSort": 26 * I,
         "ranges": 2 * I + 12 * T,
         "blend": 20 * I + 10 * P,
@@ -140,6 +143,11 @@ def build_workload(name, seed=42):
     return cloud, np.ascontiguousarray(g), np.ascontiguousarray(h), (N, deg, prec, W, H, desc)
 
 
+def base_config(spec, V, I):
+    """The `config` keys both arms print (the driver compares them)."""
+    return {"workload": spec[5], "seed": 42, "near": NEAR, "far": FAR, "N": spec[0], "V": int(V), "I": int(I)}
+
+
 def oracle_frame_runner(g, h, spec, threads=None):
     """Returns (run(), frame) for the CPU implementation of the whole frame (oracle/gsm_oracle.c)."""
     from oracle import binding as ob
@@ -159,6 +167,16 @@ def oracle_frame_runner(g, h, spec, threads=None):
     return run, fr, ob
 
 
+def cpu_baseline_dict(fps, cores, sample, fr):
+    st = {k: 1e3 * v for k, v in fr.stage_seconds.items()}
+    total = st.get("total") or sum(v for k, v in st.items() if k != "total")
+    share = st.get("clearBlend", 0.0) / total if total else None
+    return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample, "stage_ms": st,
+            "blend_share": share,
+            "note": "the port emulates binary16 arithmetic in software (one correctly rounded operation at a time): its clear+blend "
+                    "stage is that emulation's cost, so this is a parity definition timed, not a tuned CPU renderer"}
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host cores (CPU port; Metal cannot run here)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -176,15 +194,58 @@ def run_reference(args):
         "impl": "reference", "metric": "1080p frames/s at 1M Gaussians SH3 (DepthFirst mono frame)", "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": spec[5], "seed": 42, "near": NEAR, "far": FAR, "N": spec[0], "V": fr.header.visibleCount,
-                   "I": fr.header.totalInstances, "note": "CPU port of the reference's Metal kernels (oracle/), full frames"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full frames of the workload", "stage_ms": {k: 1e3 * v for k, v in fr.stage_seconds.items()}},
+        "config": base_config(spec, fr.header.visibleCount, fr.header.totalInstances),
+        "note": "CPU port of the reference's Metal kernels (oracle/), full frames",
+        "cpu_baseline": cpu_baseline_dict(fps, cores, f"{args.steps} full frames of the workload", fr),
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def e2e_sharded_upload(torch, dist, dev, rank, world, rs, pg, ph, N, K, cam, W, H, outs, steps, rec_bytes, sh_bytes):
+    """End to end at N GPUs with every input byte crossing PCIe ONCE per step instead of N times: each rank
+    uploads its 1/N slice of the step's scene from pinned host memory, the slices are replicated over NVLink with one NCCL
+    all-gather per array (a plain copy collective: there is no compute to fuse it with), then every rank renders its view and
+    downloads its frame. Two steps in flight on two streams / renderers / buffer sets. Returns seconds for `steps` steps."""
+    chunk = (N + world - 1) // world
+    lo, hi = min(rank * chunk, N), min((rank + 1) * chunk, N)
+    st = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    dg = [torch.zeros(chunk * world * rec_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    dh = [torch.zeros(chunk * world * sh_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    sg = [torch.zeros(chunk * rec_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    sh_ = [torch.zeros(chunk * sh_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    dc = [torch.zeros((H, W, 4), dtype=torch.float16, device=dev) for _ in range(2)]
+    dd = [torch.zeros((H, W), dtype=torch.float16, device=dev) for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    from gsm_renderer_b200.renderer import GaussianInput
+
+    def step(i):
+        j = i & 1
+        if i >= 2:
+            done[j].synchronize()
+        with torch.cuda.stream(st[j]):
+            sg[j][: (hi - lo) * rec_bytes].copy_(pg[lo * rec_bytes: hi * rec_bytes], non_blocking=True)
+            sh_[j][: (hi - lo) * sh_bytes].copy_(ph[lo * sh_bytes: hi * sh_bytes], non_blocking=True)
+            dist.all_gather_into_tensor(dg[j], sg[j])
+            dist.all_gather_into_tensor(dh[j], sh_[j])
+            rs[j].render(st[j], dc[j], dd[j], GaussianInput(dg[j], dh[j], N, K), cam, W, H)
+            outs[j][0].copy_(dc[j], non_blocking=True)
+            outs[j][1].copy_(dd[j], non_blocking=True)
+            done[j].record(st[j])
+
+    for i in range(4):
+        step(i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    done[0].synchronize()
+    done[1].synchronize()
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0, int((hi - lo) * (rec_bytes + sh_bytes))
 
 
 def main():
@@ -197,6 +258,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps")
     ap.add_argument("--check", action="store_true", help="also verify the frame against the oracle (slow)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the multi-GPU shard modes (c3_strips, c5_views, c4_eyes)")
+    ap.add_argument("--small-modes", action="store_true", help="run the modes on reduced clouds (smoke test of the plumbing)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -215,7 +278,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     cloud, g, h, spec = build_workload(args.workload)
     N, deg, prec, W, H, desc = spec
@@ -342,6 +406,21 @@ def main():
     h2d = int(pg.numel() + ph.numel())
     d2h = int(pc.numel() * 2 + pd.numel() * 2)
     same = bool(torch.equal(pc.to(dev), color)) and bool(torch.equal(pc2.to(dev), color))
+    e2e_extra = {"upload": "every rank uploads the whole scene" if world > 1 else "one GPU uploads the whole scene",
+                 "h2d_bytes_per_step_per_rank": h2d, "h2d_bytes_per_step_all_ranks": h2d * world}
+    if world > 1:
+        # every rank needs the same scene: upload 1/N of it per rank over PCIe, replicate over NVLink (NCCL all-gather)
+        rec_b, sh_b = (32 if prec == "float16" else 48), 3 * K * (2 if prec == "float16" else 4)
+        sh_steps = max(8, min(args.steps, 40))
+        sh_s, h2d_rank = e2e_sharded_upload(torch, dist, dev, rank, world, rs, pg, ph, N, K, cam, W, H, outs, sh_steps, rec_b, sh_b)
+        t = torch.tensor([sh_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sh_s = float(t.item())
+        same = same and bool(torch.equal(pc.to(dev), color)) and bool(torch.equal(pc2.to(dev), color))
+        e2e_extra = {"upload": f"each rank uploads 1/{world} of the scene over PCIe, one NCCL all-gather per array replicates it over NVLink",
+                     "h2d_bytes_per_step_per_rank": h2d_rank, "h2d_bytes_per_step_all_ranks": h2d, "steps_sharded": sh_steps,
+                     "replicated_upload_value": e2e_fps}
+        e2e_fps = world * sh_steps / sh_s
 
     # ---- device-resident throughput with two frames in flight (two renderers on two streams): what a multi-view batch
     # (config C5) gets per GPU -- one frame's latency-bound sorts run under the other's blend. Reported beside `value`
@@ -374,6 +453,15 @@ def main():
                      "note": "two renderers, two streams, no L2 flush between frames (frames overlap, so there is no 'between')"}
     del r2
 
+    # ---- the multi-GPU shard modes (all ranks take part; at N=1 they give the single-GPU numbers the efficiencies refer to)
+    modes = None
+    if not args.no_modes:
+        r.close()
+        del r, tg, th, inp, color2, depth2, flush
+        torch.cuda.empty_cache()
+        import bench_modes
+        modes = bench_modes.run_modes(torch, dist if world > 1 else None, rank, world, local, small=args.small_modes)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -384,31 +472,33 @@ def main():
     Vp = V  # Gaussians reaching the SH fetch >= V; the (9) exit after the fetch is rare. Lower bound used.
     sb = stage_bytes(N, V, Vp, I, T, W * H, 32 if prec == "float16" else 48, 3 * K * (2 if prec == "float16" else 4))
     stage_roofline = []
-    for k in ("project", "depthSort", "applyScan", "expand", "tileSort", "ranges", "blend"):
-        ms = stage_ms.get(k, 0.0)
+    for k in ("project", "depthSort", "expand", "tileSort", "ranges", "blend"):
+        ms = stage_ms.get(k, 0.0) + (stage_ms.get("applyScan", 0.0) if k == "expand" else 0.0)  # the scan runs inside the expansion kernel
         gbs = sb[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stage_roofline.append({"stage": k, "ms": ms, "bytes": int(sb[k]), "GBps": gbs, "frac": gbs / peak})
     dom = max(stage_roofline, key=lambda s: s["ms"])
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(dom["stage"])
-        except Exception:
-            traffic = None
-    pipes = None
-    pp = os.path.join(ROOT, "profiles", "pipes.json")
-    if os.path.exists(pp):
-        try:
-            pipes = json.load(open(pp)).get(dom["stage"])
-        except Exception:
-            pipes = None
-    roofline = {"bound": "hbm", "kernel": dom["stage"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
-                "pipes": pipes,  # ncu pipe utilisation of this kernel (profiles/pipes.json): what actually bounds it
 
-                "note": ("blend is FP16/FP32-pipe bound, not HBM bound (SURVEY.md 8d); see stage_roofline for the "
-                         "HBM-bound sort/scan/expand stages") if dom["stage"] == "blend" else ""}
+    def _profile_json(name):
+        pth = os.path.join(ROOT, "profiles", name)
+        try:
+            d = json.load(open(pth))
+            return d.get(dom["stage"]), d.get("_source") or d.get("note")
+        except Exception:
+            return None, None
+    traffic, traffic_src = _profile_json("traffic.json")
+    pipes, pipes_src = _profile_json("pipes.json")
+    hbm = {"achieved": dom["GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src,
+           "algorithmic_bytes": dom["bytes"], "ms": dom["ms"]}
+    if dom["stage"] == "blend" and pipes and pipes.get("fma_pipe_cycles_active_pct"):
+        # the blend is bound by the FMA pipe and issue slots, not by bytes: its roofline is the pipe's utilisation
+        # from the ncu capture named in pipes_source; the live HBM figure stays beside it
+        roofline = {"bound": "fp_pipe", "kernel": "blend", "achieved": pipes["fma_pipe_cycles_active_pct"], "peak": 100.0,
+                    "unit": "% of FMA-pipe cycles active (ncu sm__pipe_fma_cycles_active)", "frac": pipes["fma_pipe_cycles_active_pct"] / 100.0,
+                    "traffic": traffic, "traffic_source": traffic_src, "pipes": pipes, "pipes_source": pipes_src, "hbm": hbm}
+    else:
+        roofline = {"bound": "hbm", "kernel": dom["stage"], **hbm, "traffic": traffic, "traffic_source": traffic_src,
+                    "pipes": pipes, "pipes_source": pipes_src}
+    roofline["sort_stages_hbm_frac"] = {x["stage"]: x["frac"] for x in stage_roofline if x["stage"] in ("depthSort", "tileSort")}
     sort_blend_ms = stage_ms.get("tileSort", 0) + stage_ms.get("ranges", 0) + stage_ms.get("blend", 0)
 
     # ---- CPU baseline (bounded sample: whole frames of the same workload on this box's cores)
@@ -420,9 +510,7 @@ def main():
         while n_s < 3 and t_acc < 20.0:
             t_acc += run()
             n_s += 1
-        cpu_baseline = {"value": n_s / t_acc, "unit": "frames/s", "cores": ob.lib().gsmo_num_threads(), "kind": "port",
-                        "sample": f"{n_s} full frames of the workload after 1 warm-up",
-                        "stage_ms": {k: 1e3 * v for k, v in fr.stage_seconds.items()}}
+        cpu_baseline = cpu_baseline_dict(n_s / t_acc, ob.lib().gsmo_num_threads(), f"{n_s} full frames of the workload after 1 warm-up", fr)
         if args.check:
             assert fr.header.visibleCount == V and fr.header.totalInstances == I
 
@@ -430,12 +518,12 @@ def main():
         "metric": "1080p frames/s at 1M Gaussians SH3 (DepthFirst mono frame)", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": desc, "seed": 42, "near": NEAR, "far": FAR, "N": N, "V": V, "I": I, "activeTiles": active,
-                   "tiles": T, "maxInstancesPerTile": max_per_tile, "overflow": hd.overflow,
-                   "parallelism": f"views sharded over {world} GPU(s), one C2 view per GPU per step, no collective",
-                   "l2": "inputs+arena > L2 and " + ("no flush" if args.no_flush else "L2 flushed between steps (256 MiB write, untimed)"),
-                   "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
-                   "warmup_extra_steps": extra},
+        "config": base_config(spec, V, I),
+        "run": {"activeTiles": active, "tiles": T, "maxInstancesPerTile": max_per_tile, "overflow": hd.overflow,
+                "parallelism": f"views sharded over {world} GPU(s), one C2 view per GPU per step, no collective",
+                "l2": "inputs+arena > L2 and " + ("no flush" if args.no_flush else "L2 flushed between steps (256 MiB write, untimed)"),
+                "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
+                "warmup_extra_steps": extra},
         "mtile_instances_per_s": (I / (sort_blend_ms * 1e-3) / 1e6) if sort_blend_ms > 0 else None,
         "two_frames_in_flight": two_in_flight,
         "step_ms": {"min": float(min(step_ms)), "median": float(np.median(step_ms)), "max": float(max(step_ms))},
@@ -443,11 +531,12 @@ def main():
         "roofline": roofline,
         "stage_roofline": stage_roofline,
         "cpu_baseline": cpu_baseline,
-        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h * world,
                 "steps": e2e_steps, "matches_device_path": same, "frames_in_flight": 2,
-                "one_frame_in_flight": e2e_sync_fps,
-                "note": "gsm_render_host_async/_wait on two renderers, pinned host buffers; every frame uploads its "
-                        "inputs and downloads colour+depth; one_frame_in_flight = blocking gsm_render_host calls"},
+                "one_frame_in_flight": e2e_sync_fps, **e2e_extra,
+                "note": "pinned host buffers; every step uploads the scene and downloads colour+depth of every rank's frame, two "
+                        "steps in flight; N=1: gsm_render_host_async/_wait (one_frame_in_flight = blocking gsm_render_host)"},
+        "modes": modes,
         "gpu_launches": KERNELS_PER_FRAME * args.steps,
         "clocks": clocks,
         "wall_s_timed_region": wall,

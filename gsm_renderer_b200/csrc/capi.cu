@@ -1040,6 +1040,18 @@ gsm_status gsm_group_wait(gsm_group* g, void* stream, uint32_t fromMask, uint32_
     return GSM_OK;
 }
 
+gsm_status gsm_group_record_counts(gsm_group* g, void* stream, uint32_t* countsOut) {
+    gsm_status st = groupCheck(g, true);
+    if (st != GSM_OK) return st;
+    if (!countsOut) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(g->r->device);
+    uint32_t host[kGroupMaxRanks];
+    GSM_CUDA(cudaMemcpyAsync(host, ((GroupMailbox*)g->window)->recordCount, sizeof host, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "mailbox read");
+    GSM_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "mailbox read sync");
+    for (uint32_t s2 = 0; s2 < g->world; ++s2) countsOut[s2] = host[s2];
+    return GSM_OK;
+}
+
 gsm_status gsm_render_strips(gsm_group* g, void* stream, void* color, void* depth, const void* gaussians, const void* harmonics,
                              uint32_t gidFirst, uint32_t gidCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width,
                              uint32_t height, const uint32_t* stripRowStart) {

@@ -276,6 +276,12 @@ class RendererGroup:
                                                 self._C.byref(cam), int(width), int(height), self._rows(row_starts)))
         self.renderer._stereo_last = False
 
+    def recordCounts(self, stream=None) -> List[int]:
+        """Records each source rank routed to this rank in the last frame (diagnostic; synchronises the stream)."""
+        out = (self._C.c_uint32 * self.world)()
+        self._check(self._lib.gsm_group_record_counts(self._h, self._N.stream_handle(stream), out))
+        return [int(v) for v in out]
+
     def signal(self, stream, to_rank: int, frame_id: int) -> None:
         self._check(self._lib.gsm_group_signal(self._h, self._N.stream_handle(stream), int(to_rank), int(frame_id) & 0xFFFFFFFF))
 

@@ -289,6 +289,8 @@ gsm_status gsm_group_render_strip(gsm_group* g, void* stream, void* color, void*
                                   const uint32_t* stripRowStart);
 gsm_status gsm_group_signal(gsm_group* g, void* stream, uint32_t toRank, uint32_t frameId);
 gsm_status gsm_group_wait(gsm_group* g, void* stream, uint32_t fromMask, uint32_t frameId);
+/* Diagnostic (synchronises `stream`): how many records each source rank routed to this rank in the last frame. */
+gsm_status gsm_group_record_counts(gsm_group* g, void* stream, uint32_t* countsOut /* world */);
 /* gsm_group_project_route followed by gsm_group_render_strip (ranks in separate processes / on separate streams). */
 gsm_status gsm_render_strips(gsm_group* g, void* stream, void* color, void* depth, const void* gaussiansShard,
                              const void* harmonicsShard, uint32_t gidFirst, uint32_t gidCount, uint32_t shComponents,
