@@ -309,3 +309,25 @@ def run_modes(torch, dist, rank, world, local, small=False):
         if world > 1:
             dist.barrier()
     return modes
+
+
+if __name__ == "__main__":   # diagnostic entry: torchrun ... bench_modes.py [--small] [mode ...]
+    import json
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c3_strips", "c5_views", "c4_eyes"]
+    fns = {"c3_strips": mode_c3_strips, "c5_views": mode_c5_views, "c4_eyes": mode_c4_eyes}
+    for n in names:
+        res = fns[n](torch, dist if world > 1 else None, rank, world, local, small="--small" in sys.argv)
+        if rank == 0:
+            print(json.dumps({n: res}))
+    if world > 1:
+        dist.destroy_process_group()

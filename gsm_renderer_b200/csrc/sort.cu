@@ -122,21 +122,24 @@ __global__ void __launch_bounds__(kSortThreads, ((sizeof(KeyT) == 4 && ITEMS == 
 #endif
     // Prologue: the count and the digit histogram are two independent round trips; the histogram's prefix scan is only
     // needed after the look-back, so it runs under the first tile's key loads.
-    // The first tile of a CTA is its block index; later tiles come from the ticket, offset by the grid size. No global word
-    // is touched before pdlWait(): frames of >= 65 536 Gaussians zero the ticket inside their projection kernel, after that
-    // kernel's own wait, so an atomic issued here could still see the previous frame's value (the grid is sized to be
-    // co-resident, so block-index tiles keep the look-back's forward progress: every predecessor tile is held by a CTA that
-    // is resident or becomes resident as soon as the predecessor kernel drains).
+    // Nothing global is touched before pdlWait(): frames of >= 65 536 Gaussians zero the ticket inside their projection kernel,
+    // after that kernel's own wait, so an atomic issued earlier could still see the previous frame's value. The first ticket is
+    // taken right after the wait, together with the count and histogram loads (independent round trips, one latency).
+    // Tiles must come from the ticket, not from the block index: a CTA that holds a ticketed tile spins on its predecessors,
+    // and a predecessor owned by a not-yet-resident CTA (the grid shares the SMs with the early-launched CTAs of the chain's
+    // other kernels) would never run -- measured: stereo frames took seconds with block-index first tiles.
     pdlLaunchDependents();
     for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
     pdlWait();
+    uint32_t firstTicket = 0;
+    if (tid == 0) firstTicket = atomicAdd(ticket, 1u);
     const uint32_t digitTotal = digitHist[tid];
     const uint32_t count = min(*countPtr, countCap);
     const uint32_t numTiles = (count + TILE - 1) / TILE;
 #ifdef GSM_SORT_TRACE
     const size_t traceBase = (size_t)(shift >> 3) * numTiles;
 #endif
-    if (tid == 0) s_tile = blockIdx.x;
+    if (tid == 0) s_tile = firstTicket;
     __syncthreads();
     bool firstTile = true;
 
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kSortThreads, ((sizeof(KeyT) == 4 && ITEMS == 
         }
         __syncthreads();
         GSM_TRACE(tile, 7);  // stores issued
-        if (tid == 0) s_tile = gridDim.x + atomicAdd(ticket, 1u);
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
         for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
         __syncthreads();
     }

@@ -125,3 +125,41 @@ def test_cuda_graph_capture_mono_and_stereo_gpu(pu):
         torch.cuda.synchronize()
         assert torch.equal(sout, sref), "graph-replayed stereo frame differs from the stream-launched one"
     r.close()
+
+
+def test_stereo_chained_frames_do_not_stall_gpu(pu):
+    """Round 2 regression: with block-index first tiles in the sort passes, a stereo frame's dependent-launch chain starved
+    itself (CTAs holding ticketed tiles spun on tiles of CTAs that were not resident yet) and a frame took SECONDS while still
+    producing the right image. Frames chained on one stream must take milliseconds, and equal the synchronised frame."""
+    import torch
+    from gsm_renderer_b200.renderer import (CameraParams, DepthFirstRenderer, GaussianColorSpace, GaussianInput, RendererConfig,
+                                            RenderPrecision, StereoCameraParams, StereoRenderTarget)
+    W, H, n = 1920, 1080, 400_000
+    cl = syn.synthetic_cloud(n, 3, seed=42, scale_median=0.015)
+    g, h = pu.make_scene_inputs(cl, "float16")
+    dev = torch.device("cuda:0")
+    r = DepthFirstRenderer(device=0, config=RendererConfig(maxGaussians=2_000_000, maxWidth=W, maxHeight=H, precision=RenderPrecision.float16,
+                                                           gaussianColorSpace=GaussianColorSpace.linear))
+    tg = torch.from_numpy(g.view(np.uint8).reshape(-1)).to(dev)
+    th = torch.from_numpy(h.view(np.uint8).reshape(-1)).to(dev)
+    inp = GaussianInput(tg, th, n, 16)
+    proj = syn.make_projection_matrix(W, H, 0.1, 100.0)
+    fx, fy = syn.focal_lengths(W, H)
+    lv, rv = np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32)
+    lv[3, 0], rv[3, 0] = 0.032, -0.032
+    cams = StereoCameraParams(CameraParams(lv, proj, (-0.032, 0, 0), fx, fy, 0.1, 100.0), CameraParams(rv, proj, (0.032, 0, 0), fx, fy, 0.1, 100.0))
+    s = torch.cuda.current_stream()
+    ref = torch.zeros((H, 2 * W, 4), dtype=torch.int16, device=dev)
+    r.renderStereo(s, StereoRenderTarget.sideBySide(ref), inp, cams, W, H)
+    torch.cuda.synchronize()
+    out = torch.zeros_like(ref)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        r.renderStereo(s, StereoRenderTarget.sideBySide(out), inp, cams, W, H)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    assert torch.equal(out, ref)
+    assert ms < 20.0, f"{ms:.1f} ms per chained stereo frame: the dependent-launch chain is starving itself"
+    r.close()
