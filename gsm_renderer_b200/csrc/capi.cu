@@ -283,7 +283,7 @@ void recordStage(gsm_renderer* r, cudaStream_t s, int idx) {
 
 // stages 2-7 shared by the mono and stereo frames (DFR.swift:325-430, :683-787)
 gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s, bool stereo, uint32_t tilesX, uint32_t tilesY,
-                                 bool depthHistReady = true) {  // false: a histogram kernel runs first (no producer filled hist[0..3])
+                                 bool depthHistReady = true, uint32_t tileRowFirst = 0u, uint32_t tileRowCount = 0xFFFFFFFFu) {  // false: a histogram kernel runs first (no producer filled hist[0..3])
     const gsm_config& c = r->cfg;
     const bool tile16 = c.tileIdPrecision == GSM_KEY_BITS16;
     const bool key16 = c.depthSortKeyPrecision == GSM_KEY_BITS16;
@@ -319,7 +319,9 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     GSM_CUDA(launchSort(s, tp), "tile sort");
     recordStage(r, s, 5);
     // stage 7
-    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.maxInstances), "tile ranges");
+    const uint32_t rowEnd = tileRowCount > tilesY - tileRowFirst ? tilesY : tileRowFirst + tileRowCount;
+    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.maxInstances,
+                              tileRowFirst * tilesX, rowEnd * tilesX), "tile ranges");
     recordStage(r, s, 6);
     return GSM_OK;
 }
@@ -366,7 +368,7 @@ gsm_status encodeStripTail(gsm_renderer* r, Resources& res, cudaStream_t s, Proj
     const uint32_t tilesX = (width + kTile - 1) / kTile, tilesY = (height + kTile - 1) / kTile;
     po.recTouched = res.offsets; po.recKey = res.depthKeys[1]; po.recGid = (uint32_t*)res.primIdx[1];
     GSM_CUDA(launchCompactVisible(s, recordCap, po, r->numSMs), "record compaction");  // also writes the header
-    gsm_status st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);  // same stages 2-7 as the single-GPU frame
+    gsm_status st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, true, tileRowFirst, tileRowCount);  // same stages 2-7 as the single-GPU frame
     if (st != GSM_OK) return st;
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
                              tileRowCount, (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "strip blend");

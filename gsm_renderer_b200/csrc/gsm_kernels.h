@@ -75,7 +75,8 @@ cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, co
 
 // tile ranges (ranges.cu)
 cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,
-                             uint32_t tileCount, uint32_t* lowerBounds, uint32_t capInstances);
+                             uint32_t tileCount, uint32_t* lowerBounds, uint32_t capInstances, uint32_t tileLo = 0u,
+                             uint32_t tileHi = 0xFFFFFFFFu);  // only lowerBounds[tileLo .. tileHi] are written
 
 // blend (blend.cu). Each tile's CTA also writes its GaussianHeader and appends itself to the active list.
 struct TileOut { GSMGaussianHeader* tileHeaders; uint32_t* activeTiles; uint32_t* activeTileCount; };

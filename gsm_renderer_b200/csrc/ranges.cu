@@ -18,7 +18,8 @@ namespace gsm {
 template <typename TileT>
 __global__ void __launch_bounds__(256) tile_lower_bounds_kernel(const TileT* __restrict__ sortedTileIds,
                                                                 const GSMDepthFirstHeader* __restrict__ header,
-                                                                uint32_t tileCount, uint32_t* __restrict__ lowerBounds) {
+                                                                uint32_t tileCount, uint32_t* __restrict__ lowerBounds,
+                                                                uint32_t tileLo, uint32_t tileHi) {
     constexpr uint32_t PER = 16u / sizeof(TileT);
     pdlLaunchDependents();
     pdlWait();
@@ -39,7 +40,10 @@ __global__ void __launch_bounds__(256) tile_lower_bounds_kernel(const TileT* __r
         const uint32_t i = first + k;  // boundary i in [0, total]: i == total closes the last run
         if (i > total) break;
         const int cur = (i < total) ? (int)min((uint32_t)ids[k], tileCount) : (int)tileCount;
-        for (int t = prev + 1; t <= cur; ++t) lowerBounds[t] = i;
+        // only entries [tileLo, tileHi] are read (a strip's blend reads its own tiles and the end of the last one): the ids of a
+        // strip all lie inside it, so the run that closes everything below the strip would otherwise be one thread storing
+        // thousands of words in a row (62 us of a 4K half-frame strip before this clamp)
+        for (int t = max(prev + 1, (int)tileLo); t <= min(cur, (int)tileHi); ++t) lowerBounds[t] = i;
         prev = cur;
     }
     // the run that ends exactly at a thread's last id is closed by the next thread (its `prev`); the very last boundary
@@ -47,13 +51,14 @@ __global__ void __launch_bounds__(256) tile_lower_bounds_kernel(const TileT* __r
 }
 
 cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,
-                             uint32_t tileCount, uint32_t* lowerBounds, uint32_t capInstances) {
+                             uint32_t tileCount, uint32_t* lowerBounds, uint32_t capInstances, uint32_t tileLo, uint32_t tileHi) {
+    if (tileHi > tileCount) tileHi = tileCount;
     if (tileId16) {
         const uint32_t grid = (capInstances / 8u + 1u + 255u) / 256u;
-        return launchChained(tile_lower_bounds_kernel<uint16_t>, grid, 256, s, (const uint16_t*)sortedTileIds, header, tileCount, lowerBounds);
+        return launchChained(tile_lower_bounds_kernel<uint16_t>, grid, 256, s, (const uint16_t*)sortedTileIds, header, tileCount, lowerBounds, tileLo, tileHi);
     }
     const uint32_t grid = (capInstances / 4u + 1u + 255u) / 256u;
-    return launchChained(tile_lower_bounds_kernel<uint32_t>, grid, 256, s, (const uint32_t*)sortedTileIds, header, tileCount, lowerBounds);
+    return launchChained(tile_lower_bounds_kernel<uint32_t>, grid, 256, s, (const uint32_t*)sortedTileIds, header, tileCount, lowerBounds, tileLo, tileHi);
 }
 
 }  // namespace gsm
