@@ -110,6 +110,8 @@ EXPORTS = {
     "gsm_stream_synchronize": (C.c_int, [C.c_void_p]),
     "gsm_stream_destroy": (C.c_int, [C.c_void_p]),
     "gsm_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int]),
+    "gsm_sort_pairs_scratch_bytes": (C.c_size_t, [C.c_uint32, C.c_int, C.c_int]),
+    "gsm_sort_pairs_with_scratch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p]),
     "gsm_strip_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                     C.c_uint32, C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.c_void_p,
                                     C.POINTER(C.c_uint32)]),

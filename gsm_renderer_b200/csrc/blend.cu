@@ -13,6 +13,19 @@
 #include "gsm_dmath.cuh"
 #include "gsm_kernels.h"
 
+// A/B knobs of the mono blend (tools/build_variant.sh builds variants; the defaults are the measured best)
+#ifndef GSM_BLEND_GROUPS
+#define GSM_BLEND_GROUPS 4
+#endif
+#ifndef GSM_BLEND_CTAS
+#define GSM_BLEND_CTAS 2       // resident CTAs per SM the launch bounds ask for
+#endif
+#ifndef GSM_BLEND_TABLE
+#define GSM_BLEND_TABLE 0      // 1: exact exp table in shared memory instead of the polynomial. Measured SLOWER (C2 blend 162.8 us
+                               // against 146.8 us at the same shape, profiles/r2_blend_ab*.txt): four bank-conflicting 2-byte
+                               // loads per (thread, splat) cost more LSU time than the 28 FMA-pipe operations they replace
+#endif
+
 namespace gsm {
 
 constexpr int kBlendThreads = 64;
@@ -114,10 +127,26 @@ struct StagedSplat {
     uint4 m1;      // b|b, depth|depth, valid, cyy|cyy
 };
 
+// exp(-0.5h * p) of both halves of p from the exact table (tab[bits(p)] == dhexp2_neghalf_packed(p), built by
+// blend_exp_table_kernel from that very function, so bit-identical by construction and checked on all inputs by
+// gsm_probe_math op 13). The table covers the non-negative halfs, NaNs and +inf included; p is a sum of products of
+// non-negative terms plus a cross term, so a set sign bit is rare: that lane pair takes the polynomial.
+// Why a table was tried: 28 of the 47 FMA-pipe operations per (warp, splat) are this polynomial (ncu r1_v14: FMA pipe 66 % busy).
+// It is exact but slower (see GSM_BLEND_TABLE above), so the default build calls the polynomial; the table path stays as an
+// A/B build and as a probe (gsm_probe_math op 13) that proves its bit-equality on all 65 536 inputs.
+__device__ __forceinline__ __half2 expNegHalfTab(const unsigned short* __restrict__ tab, __half2 p) {
+    const uint32_t b = h2bits(p);
+    if (!GSM_BLEND_TABLE || (b & 0x80008000u)) return dhexp2_neghalf_packed(p);
+    const uint32_t lo = tab[b & 0xFFFFu], hi = tab[b >> 16];
+    const uint32_t r = lo | (hi << 16);
+    return *reinterpret_cast<const __half2*>(&r);
+}
+
 // Alphas of one staged splat on this thread's quad (DFS.metal:1770-1781), branch-free. Returns false when the splat does
 // nothing here: an invalid instance (DFS.metal:1750) or all four alphas zero (:1781) -- which covers p > 35, where
 // -0.5h * p < -17.5 makes the canonical exp exactly +0.
-__device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, unsigned lx, unsigned ly, __half2& a0, __half2& a1) {
+__device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, const unsigned short* __restrict__ tab, unsigned lx, unsigned ly,
+                                           __half2& a0, __half2& a1) {
     const uint2 c = sp.col[lx], r = sp.row[ly];
     const uint4 m0 = sp.m0;
     const uint2 m1 = *reinterpret_cast<const uint2*>(&sp.m1.z);  // valid, cyy|cyy
@@ -129,115 +158,173 @@ __device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, unsigned lx, u
     // fma(dx*dy, cxy2, fma(dy*dy, cyy, t0)) for the two rows of the quad
     const __half2 p0 = __hfma2(__hmul2_rn(dx, __low2half2(dyp)), cxy2, __hfma2(__low2half2(dy2p), cyy, t0));
     const __half2 p1 = __hfma2(__hmul2_rn(dx, __high2half2(dyp)), cxy2, __hfma2(__high2half2(dy2p), cyy, t0));
-    a0 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p0)), h099);
-    a1 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p1)), h099);
+    a0 = __hmin2(__hmul2_rn(op, expNegHalfTab(tab, p0)), h099);
+    a1 = __hmin2(__hmul2_rn(op, expNegHalfTab(tab, p1)), h099);
     return m1.x != 0u && ((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) != 0u;
 }
 
-__global__ void __launch_bounds__(kBlendThreads) blend_mono_kernel(const uint32_t* __restrict__ lowerBounds,
+// ---- persistent form: kBlendGroups tiles in flight per CTA (one 64-thread group each) sharing the CTA's exp table
+constexpr int kBlendGroups = GSM_BLEND_GROUPS;
+constexpr uint32_t kExpTableEntries = 32768u;                       // the non-negative halfs
+constexpr uint32_t kExpTableBytes = kExpTableEntries * 2u;          // 64 KB
+constexpr uint32_t kBlendTableSmem = GSM_BLEND_TABLE ? kExpTableBytes : 0u;
+constexpr size_t kBlendSmemBytes = kBlendTableSmem + (size_t)kBlendGroups * (kBlendChunk + 1) * sizeof(StagedSplat);
+
+__device__ __forceinline__ void groupBarrier(unsigned group) { asm volatile("bar.sync %0, 64;" ::"r"(group + 1u) : "memory"); }
+__device__ __forceinline__ bool groupAll(unsigned group, bool pred) {  // barrier + AND-reduction over the group's 64 threads
+    uint32_t r;
+    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; barrier.cta.red.and.pred p, %2, 64, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "r"(pred ? 1u : 0u), "r"(group + 1u) : "memory");
+    return r != 0u;
+}
+
+__global__ void __launch_bounds__(256) blend_exp_table_kernel(unsigned short* __restrict__ tab) {
+    const uint32_t i = (blockIdx.x * 256u + threadIdx.x) * 2u;  // two inputs per thread: the packed function is evaluated as it is in the blend
+    if (i >= kExpTableEntries) return;
+    const uint32_t in = i | ((i + 1u) << 16);
+    const __half2 r = dhexp2_neghalf_packed(*reinterpret_cast<const __half2*>(&in));
+    const uint32_t out = h2bits(r);
+    tab[i] = (unsigned short)(out & 0xFFFFu);
+    tab[i + 1u] = (unsigned short)(out >> 16);
+}
+
+// probe (gsm_probe_math op 13): the blend's table path on arbitrary half2 inputs, table staged in shared memory as in the blend
+__global__ void __launch_bounds__(256) blend_exp_probe_kernel(const unsigned short* __restrict__ tab, const unsigned short* __restrict__ in,
+                                                              unsigned short* __restrict__ out, uint32_t n) {
+    extern __shared__ uint4 s_raw[];
+    for (uint32_t i = threadIdx.x; i < kExpTableBytes / 16u; i += 256u) s_raw[i] = __ldg(reinterpret_cast<const uint4*>(tab) + i);
+    __syncthreads();
+    const unsigned short* s_tab = reinterpret_cast<const unsigned short*>(s_raw);
+    for (uint32_t i = (blockIdx.x * 256u + threadIdx.x) * 2u; i < n; i += gridDim.x * 512u) {
+        const uint32_t a = in[i], b = (i + 1u < n) ? in[i + 1u] : 0u;
+        const uint32_t pk = a | (b << 16);
+        const uint32_t r = h2bits(expNegHalfTab(s_tab, *reinterpret_cast<const __half2*>(&pk)));
+        out[i] = (unsigned short)(r & 0xFFFFu);
+        if (i + 1u < n) out[i + 1u] = (unsigned short)(r >> 16);
+    }
+}
+
+__global__ void __launch_bounds__(kBlendThreads * kBlendGroups, GSM_BLEND_CTAS) blend_mono_kernel(const uint32_t* __restrict__ lowerBounds,
                                                                    const BlendSplat* __restrict__ splats,
                                                                    const int32_t* __restrict__ instanceIdx, uint32_t width,
                                                                    uint32_t height, uint32_t tilesX, uint32_t tileRowFirst,
+                                                                   uint32_t numTiles, const unsigned short* __restrict__ expTable,
+                                                                   uint32_t* ticket,
                                                                    __half* __restrict__ color, __half* __restrict__ depth, TileOut tout) {
-    __shared__ StagedSplat s_sp[kBlendChunk + 1];  // + the invalid sentinel that ends an odd chunk
-    const unsigned tid = threadIdx.x;
+    extern __shared__ uint4 s_raw[];
+    __shared__ uint32_t s_tileOf[kBlendGroups];
+    const unsigned short* s_tab = reinterpret_cast<const unsigned short*>(s_raw);
+    const unsigned group = threadIdx.x >> 6, tid = threadIdx.x & 63u;
+    StagedSplat* s_sp = reinterpret_cast<StagedSplat*>(reinterpret_cast<char*>(s_raw) + kBlendTableSmem) + group * (kBlendChunk + 1);  // + the invalid sentinel that ends an odd chunk
     const unsigned lx = tid & 7u, ly = tid >> 3;
-    const uint32_t tileX = blockIdx.x % tilesX, tileY = tileRowFirst + blockIdx.x / tilesX;
-    const uint32_t tile = tileY * tilesX + tileX;
     pdlLaunchDependents();
+    // the table is immutable after gsm_renderer_create: staging it does not wait for the predecessor kernel
+    for (uint32_t i = threadIdx.x; i < kBlendTableSmem / 16u; i += kBlendThreads * kBlendGroups)
+        s_raw[i] = __ldg(reinterpret_cast<const uint4*>(expTable) + i);
+    __syncthreads();
     pdlWait();
-    const uint32_t start = lowerBounds[tile];
-    const uint32_t end = lowerBounds[tile + 1];
-    const uint32_t count = end > start ? end - start : 0u;
-
-    const uint32_t baseX = tileX * 16u + lx * 2u, baseY = tileY * 16u + ly * 2u;
     const __half thr = __float2half_rn(1.0f / 255.0f);  // half(1.0h/255.0h): both roundings agree (0x1C04)
     const __half2 zero = h2(0.0f), one = h2(1.0f);
-    // pixel coordinates of the tile as half (quirk Q7): pair k = (16*tile + 2k, +1)
-    __half2 pxs[8], pys[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        pxs[k] = __halves2half2(__uint2half_rn(tileX * 16u + 2u * k), __uint2half_rn(tileX * 16u + 2u * k + 1u));
-        pys[k] = __halves2half2(__uint2half_rn(tileY * 16u + 2u * k), __uint2half_rn(tileY * 16u + 2u * k + 1u));
-    }
 
-    QuadState q;
-    q.T0 = one; q.T1 = one;
-    q.r0 = q.g0 = q.b0 = q.d0 = q.r1 = q.g1 = q.b1 = q.d1 = zero;
-    bool done = false;
+    while (true) {
+        if (tid == 0) s_tileOf[group] = atomicAdd(ticket, 1u);
+        groupBarrier(group);
+        const uint32_t t = s_tileOf[group];
+        if (t >= numTiles) break;
+        const uint32_t tileX = t % tilesX, tileY = tileRowFirst + t / tilesX;
+        const uint32_t tile = tileY * tilesX + tileX;
+        const uint32_t start = lowerBounds[tile];
+        const uint32_t end = lowerBounds[tile + 1];
+        const uint32_t count = end > start ? end - start : 0u;
 
-    for (uint32_t base = 0; base < count; base += kBlendChunk) {
-        const uint32_t n = min((uint32_t)kBlendChunk, count - base);
-        if (tid < n) {
-            const int32_t gi = __ldg(instanceIdx + start + base + tid);
-            StagedSplat& sp = s_sp[tid];
-            if (gi >= 0) {
-                const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
-                const uint4 ra = __ldg(src), rb = __ldg(src + 1);
-                const __half2 mean = *reinterpret_cast<const __half2*>(&ra.x);
-                const __half2 cxx_cyy = *reinterpret_cast<const __half2*>(&ra.y);
-                const __half2 cxy2_op = *reinterpret_cast<const __half2*>(&ra.z);
-                const __half2 rg = *reinterpret_cast<const __half2*>(&ra.w);
-                const __half2 b_d = *reinterpret_cast<const __half2*>(&rb.x);
-                const __half2 mx = __low2half2(mean), my = __high2half2(mean);
-                const __half2 cxx = __low2half2(cxx_cyy), cyy = __high2half2(cxx_cyy);
+        const uint32_t baseX = tileX * 16u + lx * 2u, baseY = tileY * 16u + ly * 2u;
+        // pixel coordinates of the tile as half (quirk Q7): pair k = (16*tile + 2k, +1)
+        __half2 pxs[8], pys[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const __half2 dx = __hsub2_rn(pxs[k], mx);
-                    const __half2 t0 = __hmul2_rn(__hmul2_rn(dx, dx), cxx);
-                    sp.col[k] = make_uint2(h2bits(t0), h2bits(dx));
-                    const __half2 dy = __hsub2_rn(pys[k], my);
-                    sp.row[k] = make_uint2(h2bits(__hmul2_rn(dy, dy)), h2bits(dy));
-                }
-                sp.m0 = make_uint4(h2bits(__low2half2(cxy2_op)), h2bits(__high2half2(cxy2_op)), h2bits(__low2half2(rg)),
-                                   h2bits(__high2half2(rg)));
-                sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 1u, h2bits(cyy));
-            } else {
-                sp.m1 = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
-            }
+        for (int k = 0; k < 8; ++k) {
+            pxs[k] = __halves2half2(__uint2half_rn(tileX * 16u + 2u * k), __uint2half_rn(tileX * 16u + 2u * k + 1u));
+            pys[k] = __halves2half2(__uint2half_rn(tileY * 16u + 2u * k), __uint2half_rn(tileY * 16u + 2u * k + 1u));
         }
-        if (tid == 0) s_sp[n].m1 = make_uint4(0, 0, 0, 0);  // the loop below reads slot j + 1 unconditionally
-        __syncthreads();
-        if (!done) {
-            // Two splats per trip: the alphas of splat j+1 do not depend on splat j (only the accumulation does), and
-            // evaluating both before either is accumulated gives each warp four independent exp chains instead of two
-            // (ncu r1_v11: "wait" -- fixed-latency dependency -- was the largest stall, 2.7 warps per issue slot). The
-            // evaluation has no side effect, so doing it for a splat the quad then closes before is invisible. Three and
-            // four per trip were measured too and are slower (106 / 118 registers): profiles/README.md, v12.
-            for (uint32_t j = 0; j < n; j += 2) {
-                if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
-                __half2 aA0, aA1, aB0, aB1;
-                const bool useA = evalAlphas(s_sp[j], lx, ly, aA0, aA1);
-                const bool useB = evalAlphas(s_sp[j + 1u], lx, ly, aB0, aB1);  // slot n is the invalid sentinel
-                GSM_BLEND_STAT(useA);
-                if (useA) {
-                    const StagedSplat& sp = s_sp[j];
-                    const uint4 m0 = sp.m0, m1 = sp.m1;
-                    accumulate(q, aA0, aA1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
-                               *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
-                }
-                GSM_BLEND_STAT(useB);
-                if (useB) {
-                    // DFS.metal:1746-1747 runs before every splat; T only moved if splat j was used. (When splat j + 1 is
-                    // not used the test is simply the one at the top of the next trip.)
-                    if (useA && quadClosed(q.T0, q.T1, thr)) { done = true; break; }
-                    const StagedSplat& sp = s_sp[j + 1u];
-                    const uint4 m0 = sp.m0, m1 = sp.m1;
-                    accumulate(q, aB0, aB1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
-                               *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
+
+        QuadState q;
+        q.T0 = one; q.T1 = one;
+        q.r0 = q.g0 = q.b0 = q.d0 = q.r1 = q.g1 = q.b1 = q.d1 = zero;
+        bool done = false;
+
+        for (uint32_t base = 0; base < count; base += kBlendChunk) {
+            const uint32_t n = min((uint32_t)kBlendChunk, count - base);
+            if (tid < n) {
+                const int32_t gi = __ldg(instanceIdx + start + base + tid);
+                StagedSplat& sp = s_sp[tid];
+                if (gi >= 0) {
+                    const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
+                    const uint4 ra = __ldg(src), rb = __ldg(src + 1);
+                    const __half2 mean = *reinterpret_cast<const __half2*>(&ra.x);
+                    const __half2 cxx_cyy = *reinterpret_cast<const __half2*>(&ra.y);
+                    const __half2 cxy2_op = *reinterpret_cast<const __half2*>(&ra.z);
+                    const __half2 rg = *reinterpret_cast<const __half2*>(&ra.w);
+                    const __half2 b_d = *reinterpret_cast<const __half2*>(&rb.x);
+                    const __half2 mx = __low2half2(mean), my = __high2half2(mean);
+                    const __half2 cxx = __low2half2(cxx_cyy), cyy = __high2half2(cxx_cyy);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const __half2 dx = __hsub2_rn(pxs[k], mx);
+                        const __half2 t0 = __hmul2_rn(__hmul2_rn(dx, dx), cxx);
+                        sp.col[k] = make_uint2(h2bits(t0), h2bits(dx));
+                        const __half2 dy = __hsub2_rn(pys[k], my);
+                        sp.row[k] = make_uint2(h2bits(__hmul2_rn(dy, dy)), h2bits(dy));
+                    }
+                    sp.m0 = make_uint4(h2bits(__low2half2(cxy2_op)), h2bits(__high2half2(cxy2_op)), h2bits(__low2half2(rg)),
+                                       h2bits(__high2half2(rg)));
+                    sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 1u, h2bits(cyy));
+                } else {
+                    sp.m1 = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
                 }
             }
+            if (tid == 0) s_sp[n].m1 = make_uint4(0, 0, 0, 0);  // the loop below reads slot j + 1 unconditionally
+            groupBarrier(group);
+            if (!done) {
+                // Two splats per trip: the alphas of splat j+1 do not depend on splat j (only the accumulation does), and
+                // evaluating both before either is accumulated gives each warp four independent chains instead of two
+                // (ncu r1_v11: "wait" -- fixed-latency dependency -- was the largest stall, 2.7 warps per issue slot). The
+                // evaluation has no side effect, so doing it for a splat the quad then closes before is invisible. Three and
+                // four per trip were measured too and are slower (106 / 118 registers): profiles/README.md, v12.
+                for (uint32_t j = 0; j < n; j += 2) {
+                    if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
+                    __half2 aA0, aA1, aB0, aB1;
+                    const bool useA = evalAlphas(s_sp[j], s_tab, lx, ly, aA0, aA1);
+                    const bool useB = evalAlphas(s_sp[j + 1u], s_tab, lx, ly, aB0, aB1);  // slot n is the invalid sentinel
+                    GSM_BLEND_STAT(useA);
+                    if (useA) {
+                        const StagedSplat& sp = s_sp[j];
+                        const uint4 m0 = sp.m0, m1 = sp.m1;
+                        accumulate(q, aA0, aA1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
+                                   *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
+                    }
+                    GSM_BLEND_STAT(useB);
+                    if (useB) {
+                        // DFS.metal:1746-1747 runs before every splat; T only moved if splat j was used. (When splat j + 1 is
+                        // not used the test is simply the one at the top of the next trip.)
+                        if (useA && quadClosed(q.T0, q.T1, thr)) { done = true; break; }
+                        const StagedSplat& sp = s_sp[j + 1u];
+                        const uint4 m0 = sp.m0, m1 = sp.m1;
+                        accumulate(q, aB0, aB1, *reinterpret_cast<const __half2*>(&m0.z), *reinterpret_cast<const __half2*>(&m0.w),
+                                   *reinterpret_cast<const __half2*>(&m1.x), *reinterpret_cast<const __half2*>(&m1.y), true);
+                    }
+                }
+            }
+            if (groupAll(group, done)) break;
         }
-        if (__syncthreads_and(done ? 1 : 0)) break;
-    }
 
-    // active tiles: alpha = 1 - T; inactive tiles keep the clear value alpha = 1 (quirk Q6)
-    __half2 al0, al1;
-    if (count > 0) { al0 = __hsub2_rn(one, q.T0); al1 = __hsub2_rn(one, q.T1); }
-    else { al0 = one; al1 = one; }
-    storePixelRow(color, depth, width, height, baseX, baseY, q.r0, q.g0, q.b0, al0, q.d0);
-    storePixelRow(color, depth, width, height, baseX, baseY + 1u, q.r1, q.g1, q.b1, al1, q.d1);
-    if (tid == 0) publishTile(tout, tile, start, count);
+        // active tiles: alpha = 1 - T; inactive tiles keep the clear value alpha = 1 (quirk Q6)
+        __half2 al0, al1;
+        if (count > 0) { al0 = __hsub2_rn(one, q.T0); al1 = __hsub2_rn(one, q.T1); }
+        else { al0 = one; al1 = one; }
+        storePixelRow(color, depth, width, height, baseX, baseY, q.r0, q.g0, q.b0, al0, q.d0);
+        storePixelRow(color, depth, width, height, baseX, baseY + 1u, q.r1, q.g1, q.b1, al1, q.d1);
+        if (tid == 0) publishTile(tout, tile, start, count);
+        groupBarrier(group);  // the staging buffer and s_tileOf are reused by the next tile
+    }
 }
 
 // one eye of depthFirstStereoRender for one splat (DFS.metal:1881-1920)
@@ -414,11 +501,35 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
 
 cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,
                             uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY, uint32_t tileRowFirst,
-                            uint32_t tileRowCount, __half* color, __half* depth, TileOut tout) {
+                            uint32_t tileRowCount, __half* color, __half* depth, TileOut tout, const unsigned short* expTable,
+                            uint32_t* ticket, int numSMs) {
     (void)tilesY;
     if (tileRowCount == 0) return cudaSuccess;
-    return launchChained(blend_mono_kernel, tilesX * tileRowCount, kBlendThreads, s, lowerBounds, splats, instanceIdx, width, height,
-                         tilesX, tileRowFirst, color, depth, tout);
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(blend_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlendSmemBytes);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    const uint32_t numTiles = tilesX * tileRowCount;
+    uint32_t grid = (numTiles + kBlendGroups - 1) / kBlendGroups;
+    if (grid > (uint32_t)numSMs * GSM_BLEND_CTAS) grid = (uint32_t)numSMs * GSM_BLEND_CTAS;  // persistent: GSM_BLEND_CTAS CTAs of kBlendGroups tile groups per SM
+    return launchChainedSmem(blend_mono_kernel, grid, kBlendThreads * kBlendGroups, s, kBlendSmemBytes, lowerBounds, splats, instanceIdx,
+                         width, height, tilesX, tileRowFirst, numTiles, expTable, ticket, color, depth, tout);
+}
+
+cudaError_t buildBlendExpTable(cudaStream_t s, unsigned short* table) {
+    blend_exp_table_kernel<<<(kExpTableEntries / 2u + 255u) / 256u, 256, 0, s>>>(table);
+    return cudaGetLastError();
+}
+size_t blendExpTableBytes() { return kExpTableBytes; }
+bool blendUsesExpTable() { return GSM_BLEND_TABLE != 0; }
+
+cudaError_t launchBlendExpProbe(cudaStream_t s, const unsigned short* table, const unsigned short* in, unsigned short* out, uint32_t n) {
+    cudaError_t e = cudaFuncSetAttribute(blend_exp_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExpTableBytes);
+    if (e != cudaSuccess) return e;
+    blend_exp_probe_kernel<<<64, 256, kExpTableBytes, s>>>(table, in, out, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,

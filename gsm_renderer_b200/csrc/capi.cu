@@ -157,6 +157,7 @@ struct gsm_renderer {
     void* stereoIntermediate = nullptr; size_t stereoIntermediateBytes = 0;
     float* rateTables = nullptr; size_t rateTableFloats = 0;
     uint8_t* srgbLut = nullptr;
+    unsigned short* expTable = nullptr;  // exact exp(-0.5h * p) over the non-negative halfs, staged into shared memory by the mono blend
 };
 
 namespace gsm {
@@ -371,7 +372,8 @@ gsm_status encodeStripTail(gsm_renderer* r, Resources& res, cudaStream_t s, Proj
     gsm_status st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, true, tileRowFirst, tileRowCount);  // same stages 2-7 as the single-GPU frame
     if (st != GSM_OK) return st;
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, tileRowFirst,
-                             tileRowCount, (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "strip blend");
+                             tileRowCount, (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount},
+                             r->expTable, &res.fs->ticketBlend, r->numSMs), "strip blend");
     return GSM_OK;
 }
 
@@ -457,6 +459,16 @@ gsm_status gsm_renderer_create(const gsm_config* cfg, gsm_renderer** out) {
     r->cfg.device = dev;
     r->device = dev;
     r->numSMs = prop.multiProcessorCount;
+    if (blendUsesExpTable()) {
+        e = cudaMalloc((void**)&r->expTable, blendExpTableBytes());
+        if (e == cudaSuccess) e = buildBlendExpTable(nullptr, r->expTable);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    }
+    if (e != cudaSuccess) {
+        if (r->expTable) cudaFree(r->expTable);
+        delete r;
+        return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "blend exp table", e);
+    }
     *out = r;
     return GSM_OK;
 }
@@ -476,6 +488,7 @@ void gsm_renderer_destroy(gsm_renderer* r) {
     if (r->stereoIntermediate) cudaFree(r->stereoIntermediate);
     if (r->rateTables) cudaFree(r->rateTables);
     if (r->srgbLut) cudaFree(r->srgbLut);
+    if (r->expTable) cudaFree(r->expTable);
     delete r;
 }
 
@@ -515,7 +528,8 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     if (st != GSM_OK) return st;
     // step 8: clear + blend (DFR.swift:433-464), fused
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, 0, tilesY,
-                             (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount}), "blend");
+                             (__half*)color, (__half*)depth, TileOut{res.tileHeaders, res.activeTiles, &res.fs->activeTileCount},
+                             r->expTable, &res.fs->ticketBlend, r->numSMs), "blend");
     recordStage(r, s, 7);
     recordStage(r, s, 8);
     if (r->profiling) r->evRecorded = true;
@@ -1199,12 +1213,27 @@ gsm_status gsm_sort_pairs(gsm_renderer* r, void* stream, void* keys, void* paylo
     return gsm::sortPairsStandalone((cudaStream_t)stream, r->numSMs, keys, payload, count, keyBits, numPasses);
 }
 
+size_t gsm_sort_pairs_scratch_bytes(uint32_t count, int keyBits, int numPasses) {
+    if ((keyBits != 16 && keyBits != 32) || numPasses < 1 || numPasses > keyBits / 8 || count == 0) return 0;
+    return gsm::sortScratchBytes(count, keyBits, numPasses);
+}
+
+gsm_status gsm_sort_pairs_with_scratch(gsm_renderer* r, void* stream, void* keys, void* payload, uint32_t count, int keyBits,
+                                       int numPasses, void* scratch) {
+    if (!r || !keys || !payload || !scratch) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if ((keyBits != 16 && keyBits != 32) || numPasses < 1 || numPasses > keyBits / 8) return fail(GSM_ERR_INVALID_ARGUMENT, "bad key width / pass count");
+    if (count == 0) return GSM_OK;
+    if (((uintptr_t)scratch & 255u) != 0) return fail(GSM_ERR_INVALID_ARGUMENT, "scratch must be 256-byte aligned");
+    DeviceGuard guard(r->device);
+    return gsm::sortPairsStandalone((cudaStream_t)stream, r->numSMs, keys, payload, count, keyBits, numPasses, scratch);
+}
+
 gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void* out, uint32_t n) {
     if (!a || !out || n == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
     if (device < 0) cudaGetDevice(&device);
     DeviceGuard guard(device);
-    const size_t inEl = (op == 11) ? 6 : ((op == 5 || op == 7 || op == 8 || op == 12) ? 2 : 4);
-    const size_t outEl = (op == 5 || op == 6 || op == 7 || op == 8 || op == 11 || op == 12) ? 2 : 4;
+    const size_t inEl = (op == 11) ? 6 : ((op == 5 || op == 7 || op == 8 || op == 12 || op == 13) ? 2 : 4);
+    const size_t outEl = (op == 5 || op == 6 || op == 7 || op == 8 || op == 11 || op == 12 || op == 13) ? 2 : 4;
     void *da = nullptr, *db = nullptr, *dout = nullptr;
     gsm_status st = GSM_OK;
     cudaError_t e;
@@ -1216,7 +1245,15 @@ gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void
             if ((e = cudaMalloc(&db, n * inEl)) != cudaSuccess) break;
             if ((e = cudaMemcpy(db, b, n * inEl, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         }
-        if ((e = launchProbe(nullptr, op, da, db, dout, n)) != cudaSuccess) break;
+        if (op == 13) {  // the blend's table form of exp(-0.5h * p): table built exactly as gsm_renderer_create builds it
+            unsigned short* tab = nullptr;
+            if ((e = cudaMalloc((void**)&tab, blendExpTableBytes())) != cudaSuccess) break;
+            e = buildBlendExpTable(nullptr, tab);
+            if (e == cudaSuccess) e = launchBlendExpProbe(nullptr, tab, (const unsigned short*)da, (unsigned short*)dout, n);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+            cudaFree(tab);
+            if (e != cudaSuccess) break;
+        } else if ((e = launchProbe(nullptr, op, da, db, dout, n)) != cudaSuccess) break;
         e = cudaMemcpy(out, dout, n * outEl, cudaMemcpyDeviceToHost);
     } while (false);
     if (e != cudaSuccess) st = fail(GSM_ERR_RENDER_FAILED, "gsm_probe_math", e);

@@ -23,6 +23,21 @@ __device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcon
 bool pdlEnabled();  // capi.cu: GSM_PDL=0 in the environment turns the attribute off (A/B measurement)
 
 template <typename... KArgs, typename... Args>
+inline cudaError_t launchChainedSmem(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, size_t smemBytes, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdlEnabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
 inline cudaError_t launchChained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -56,9 +71,10 @@ struct FrameState {
     uint32_t routeDone;          // group.cu: CTAs of the routing kernel that have issued all their (remote) stores
     uint32_t hist[8][256];       // global digit histograms: depth passes 0-3, tile passes 4-7
     uint32_t routeTotals[8];     // group.cu: records routed to each destination rank this frame
+    uint32_t ticketBlend;        // tiles of the persistent mono blend
     uint32_t ingestDone;         // group.cu: CTAs of the ingest kernel that have read all their records
     uint32_t recordTotal;        // group.cu: records received from all sources this frame (device-side N of the compaction)
-    uint32_t _pad2[6];
+    uint32_t _pad2[5];
 };
 
 // What the blend stage reads per splat: the quantised record pre-expanded once per visible Gaussian

@@ -82,7 +82,13 @@ cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTi
 struct TileOut { GSMGaussianHeader* tileHeaders; uint32_t* activeTiles; uint32_t* activeTileCount; };
 cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,
                             uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY, uint32_t tileRowFirst,
-                            uint32_t tileRowCount, __half* color, __half* depth, TileOut tout);
+                            uint32_t tileRowCount, __half* color, __half* depth, TileOut tout, const unsigned short* expTable,
+                            uint32_t* ticket, int numSMs);
+// exact table of the blend's exp(-0.5h * p) over the non-negative halfs (built once per renderer from the canonical function)
+size_t blendExpTableBytes();
+bool blendUsesExpTable();   // false in the default build: the polynomial is faster (blend.cu, GSM_BLEND_TABLE)
+cudaError_t buildBlendExpTable(cudaStream_t s, unsigned short* table);
+cudaError_t launchBlendExpProbe(cudaStream_t s, const unsigned short* table, const unsigned short* in, unsigned short* out, uint32_t n);
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
                               __half* dstSideBySide, int eyeMask, int flipY, TileOut tout);

@@ -379,6 +379,14 @@ class DepthFirstRenderer:
         _check(self._lib.gsm_sort_pairs(self._h, N.stream_handle(commandBuffer), N.ptr(keys), N.ptr(payload),
                                         int(count), int(keyBits), int(numPasses)))
 
+    def sortPairsScratchBytes(self, count: int, keyBits: int = 32, numPasses: int = 4) -> int:
+        return int(self._lib.gsm_sort_pairs_scratch_bytes(int(count), int(keyBits), int(numPasses)))
+
+    def sortPairsWithScratch(self, commandBuffer, keys, payload, count: int, keyBits: int, numPasses: int, scratch) -> None:
+        """gsm_sort_pairs_with_scratch: no allocation, no host synchronisation."""
+        _check(self._lib.gsm_sort_pairs_with_scratch(self._h, N.stream_handle(commandBuffer), N.ptr(keys), N.ptr(payload),
+                                                     int(count), int(keyBits), int(numPasses), N.ptr(scratch)))
+
     # -- white-box reads (DepthFirstUnitTests.swift:911-1252)
     def _read(self, which: str, dtype, count: int, first: int = 0, stream=None) -> np.ndarray:
         dtype = np.dtype(dtype)
@@ -443,10 +451,10 @@ class DepthFirstRenderer:
 def probe_math(op: int, a, b=None, device: int = -1) -> np.ndarray:
     """gsm_probe_math: device restatement of the canonical math (0 sin, 1 cos, 2 log, 3 atan2, 4 powr 2.4,
     5 half exp, 6 float->half, 7/8 packed half exp forms, 9/10 min/max, 11 fused half fma on (n,3) triples,
-    12 exp(-0.5h * p) with the -0.5 folded in)."""
+    12 exp(-0.5h * p) with the -0.5 folded in, 13 the same through the blend's shared-memory table)."""
     a = np.ascontiguousarray(a)
     n = a.shape[0] if op == 11 else a.size  # op 11 (half fma) takes (n, 3) uint16 triples
-    out = np.empty(n if op == 11 else a.shape, np.uint16 if op in (5, 6, 7, 8, 11, 12) else np.float32)
+    out = np.empty(n if op == 11 else a.shape, np.uint16 if op in (5, 6, 7, 8, 11, 12, 13) else np.float32)
     bp = None if b is None else N.ptr(np.ascontiguousarray(b))
     _check(N.lib().gsm_probe_math(device, op, N.ptr(a), bp, N.ptr(out), n))
     return out

@@ -251,6 +251,13 @@ gsm_status gsm_strip_render(gsm_renderer* r, void* stream, void* color, void* de
                             uint32_t recordCount, uint32_t width, uint32_t height, uint32_t tileRowFirst,
                             uint32_t tileRowCount);
 
+/* The same sort without any allocation or host synchronisation (hosts that sort every frame): `scratch` is a device
+ * buffer of gsm_sort_pairs_scratch_bytes(count, keyBits, numPasses) bytes, 256-byte aligned, that must stay untouched until
+ * the stream has run the sort. */
+size_t gsm_sort_pairs_scratch_bytes(uint32_t count, int keyBits, int numPasses);
+gsm_status gsm_sort_pairs_with_scratch(gsm_renderer* r, void* stream, void* keys, void* payload, uint32_t count,
+                                       int keyBits, int numPasses, void* scratch);
+
 /* ---- gsm_group: one frame split over the GPUs of one node by horizontal strips of whole tile rows (SURVEY.md 8e, config C3;
  * no reference counterpart -- the reference is single-device). One process (or thread) per GPU, one renderer + one group
  * handle per rank. Every rank owns an EXCHANGE WINDOW in its HBM -- a mailbox, one receive region per source rank and an

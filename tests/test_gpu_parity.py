@@ -64,6 +64,13 @@ def test_math_probes_bit_exact(oracle):
     with np.errstate(invalid="ignore"):
         x = (np.float16(-0.5) * bits.view(np.float16)).astype(np.float16)
     assert np.array_equal(probe_math(12, bits)[notnan], oracle.probe_hexp(x.view(np.uint16))[notnan])
+    # the mono blend's shared-memory table form: identical to the polynomial on ALL 65 536 inputs (NaNs included: the table is
+    # built from that very function), hence to the oracle wherever the input is not a NaN
+    tab = probe_math(13, bits)
+    assert np.array_equal(tab, probe_math(12, bits))
+    assert np.array_equal(tab[notnan], oracle.probe_hexp(x.view(np.uint16))[notnan])
+    shuffled = rng.permutation(bits)                          # pairs of unrelated values share a half2 in the probe
+    assert np.array_equal(probe_math(13, shuffled), probe_math(12, shuffled))
     xf = np.concatenate([rng.normal(0, 300, 200_000), [65504, 65520, 1e10, -1e10, 6e-8, 2.9e-8, 0.0]]).astype(np.float32)
     assert np.array_equal(probe_math(6, xf), oracle.probe_f2h(xf))
 
@@ -318,3 +325,48 @@ def test_three_million_gaussians_frame_gpu(oracle, pu):
     cl = syn.synthetic_cloud(3_100_000, 3, seed=9, scale_median=0.006)
     res = pu.run_mono_case(oracle, cl, "float16", 1280, 720)
     assert res["V"] > 1_000_000 and res["I"] > res["V"]
+
+
+def test_sorts_equal_cub_library_bar_gpu():
+    """SURVEY.md 4.1: cub::DeviceRadixSort::SortPairs (stable) output byte-equal to the hand-written onesweep sorts, on the
+    frame's own key distributions and on adversarial ones (all equal, two values, already sorted, reversed)."""
+    import ctypes as C
+    import os
+    import torch
+    from gsm_renderer_b200.renderer import DepthFirstRenderer, RendererConfig
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bin", "libcub_bar.so")
+    if not os.path.exists(path):
+        import __graft_entry__
+        __graft_entry__.build()
+    cub = C.CDLL(path)
+    cub.cub_sort_pairs.restype = C.c_int
+    cub.cub_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int, C.c_void_p]
+    r = DepthFirstRenderer(device=0, config=RendererConfig(maxGaussians=1024, maxWidth=64, maxHeight=64))
+    rng = np.random.default_rng(5)
+    s = torch.cuda.current_stream()
+
+    def check(keys_np, bits, passes):
+        n = keys_np.size
+        keys = torch.from_numpy(keys_np.view(np.int32 if bits == 32 else np.int16)).cuda()
+        vals = torch.arange(n, dtype=torch.int32, device="cuda")
+        ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+        assert cub.cub_sort_pairs(keys.data_ptr(), vals.data_ptr(), ko.data_ptr(), vo.data_ptr(), n, bits, 0, 8 * passes,
+                                  s.cuda_stream, 0, None) == 0
+        k, v = keys.clone(), vals.clone()
+        r.sortPairs(s, k, v, n, bits, passes)
+        torch.cuda.synchronize()
+        assert torch.equal(k, ko) and torch.equal(v, vo), f"n={n} bits={bits} passes={passes}"
+
+    for n in (1, 255, 2049, 70_000, 709_202):
+        depth = rng.uniform(2.0, 20.0, n).astype(np.float32)
+        check(depth.view(np.uint32) | np.uint32(0x80000000), 32, 4)
+        check(rng.integers(0, 8160, n, dtype=np.int64).astype(np.uint16), 16, 2)
+    n = 300_000
+    check(np.full(n, 0x80001234, np.uint32), 32, 4)
+    check(rng.integers(0, 2, n, dtype=np.int64).astype(np.uint32) * np.uint32(0x01000000), 32, 4)
+    check(np.arange(n, dtype=np.uint32), 32, 4)
+    check(np.arange(n, dtype=np.uint32)[::-1].copy(), 32, 4)
+    check((np.arange(n, dtype=np.uint32) % 8160).astype(np.uint16), 16, 2)
+    check(rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32), 32, 2)   # partial sort: 2 passes == bits [0, 16)
+    r.close()
