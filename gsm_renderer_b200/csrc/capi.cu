@@ -118,6 +118,10 @@ struct Resources {
     GSMGaussianHeader* tileHeaders = nullptr;
     uint32_t* activeTiles = nullptr;
     GSMDepthFirstHeader* header = nullptr;
+    // depth sort as bucket scatter + local sort (bucketsort.cu): key range recorded by the projection (cleared by its consumer),
+    // plan written by the compaction's last CTA. Not part of the per-frame zero region.
+    KeyRange* keyRange = nullptr;
+    DepthPlan* depthPlan = nullptr;
     // zeroed every frame
     FrameState* fs = nullptr;
     unsigned long long* projStatus = nullptr;
@@ -210,6 +214,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t oTH = take((size_t)T * 8);
     const size_t oAT = take((size_t)T * 4);
     const size_t oHeader = take(sizeof(GSMDepthFirstHeader));
+    const size_t oKeyRange = take(sizeof(KeyRange));
+    const size_t oDepthPlan = take(sizeof(DepthPlan));
     const size_t oZero = off;
     const size_t oFS = take(sizeof(FrameState));
     const size_t oProjStatus = take(((size_t)(G + 31) / 32 + 8) * 8);  // one prefix word per 32-gid warp tile (strip ingest) / 2048-gid tile (compaction)
@@ -246,6 +252,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     res.tileHeaders = (GSMGaussianHeader*)(a + oTH);
     res.activeTiles = (uint32_t*)(a + oAT);
     res.header = (GSMDepthFirstHeader*)(a + oHeader);
+    res.keyRange = (KeyRange*)(a + oKeyRange);
+    res.depthPlan = (DepthPlan*)(a + oDepthPlan);
     res.fs = (FrameState*)(a + oFS);
     res.projStatus = (unsigned long long*)(a + oProjStatus);
     res.scanStatus = (unsigned long long*)(a + oScanStatus);
@@ -258,6 +266,8 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     res.tileSortGStatus = (uint32_t*)(a + oTileGStatus);
     e = cudaMemset(res.arena, 0, res.bytes);
     if (e != cudaSuccess) return fail(GSM_ERR_RENDER_FAILED, "arena memset", e);
+    e = bucketSortPrepareDevice();
+    if (e != cudaSuccess) return fail(GSM_ERR_FAILED_TO_CREATE_PIPELINE, "depth sort local pass: shared memory opt-in", e);
     return GSM_OK;
 }
 
@@ -267,6 +277,20 @@ void freeResources(Resources& res) {
 }
 
 bool largeSort(uint32_t frameGaussians) { return frameGaussians >= 3000000u; }  // see sort.cu: sortTileSize
+
+// GSM_DEPTH_BUCKETS=0 in the environment keeps the depth sort on the four LSD passes (A/B measurement)
+bool depthBucketsEnabled() {
+    static const bool on = [] { const char* e = getenv("GSM_DEPTH_BUCKETS"); return !(e && e[0] == '0'); }();
+    return on;
+}
+// The bucket path runs when the projection kernel records the key range of exactly the keys the compaction stores -- 32-bit
+// depth keys (16-bit keys are re-encoded inside the compaction) of a frame projected on this GPU -- and the frame is small
+// enough for one wave of scatter tiles (bucketsort.cu).
+void attachDepthPlan(const gsm_renderer* r, Resources& res, ProjectOut& po, uint32_t gaussianCount) {
+    if (depthBucketsEnabled() && r->cfg.depthSortKeyPrecision != GSM_KEY_BITS16 && bucketSortCovers(gaussianCount, r->numSMs)) {
+        po.keyRange = res.keyRange;
+    }
+}
 
 int tileSortPasses(uint32_t tileCount) {  // TileSortEncoder.swift:61-62
     uint32_t v = tileCount > 0 ? (tileCount - 1 > 1 ? tileCount - 1 : 1) : 1;
@@ -284,7 +308,8 @@ void recordStage(gsm_renderer* r, cudaStream_t s, int idx) {
 
 // stages 2-7 shared by the mono and stereo frames (DFR.swift:325-430, :683-787)
 gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s, bool stereo, uint32_t tilesX, uint32_t tilesY,
-                                 bool depthHistReady = true, uint32_t tileRowFirst = 0u, uint32_t tileRowCount = 0xFFFFFFFFu) {  // false: a histogram kernel runs first (no producer filled hist[0..3])
+                                 bool depthHistReady = true, uint32_t tileRowFirst = 0u, uint32_t tileRowCount = 0xFFFFFFFFu,
+                                 bool depthPlanned = false) {  // depthHistReady false: a histogram kernel runs first (no producer filled hist[0..3]); depthPlanned: the compaction wrote res.depthPlan
     const gsm_config& c = r->cfg;
     const bool tile16 = c.tileIdPrecision == GSM_KEY_BITS16;
     const bool key16 = c.depthSortKeyPrecision == GSM_KEY_BITS16;
@@ -298,7 +323,16 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     dp.largeTiles = largeSort(res.frameGaussians);
     dp.tilesCap = res.depthTilesCap; dp.keyBits = 32; dp.numPasses = key16 ? 2 : 4; dp.numSMs = r->numSMs;
     dp.histogramReady = depthHistReady;  // compact_visible_kernel filled hist[0..3]; the status words were cleared with the frame state
-    GSM_CUDA(launchSort(s, dp), "depth sort");
+    if (depthPlanned) {   // one global pass + one shared-memory pass instead of the four LSD passes
+        BucketSortPlan bp;
+        bp.k0 = res.depthKeys[0]; bp.k1 = res.depthKeys[1]; bp.v0 = dp.v0; bp.v1 = dp.v1;
+        bp.countPtr = dp.countPtr; bp.countCap = dp.countCap; bp.plan = res.depthPlan; bp.fineHist = res.fs->fineHist; bp.keyRange = res.keyRange;
+        bp.status = res.depthSortStatus; bp.gstatus = res.depthSortGStatus;
+        bp.gatherSrc = dp.gatherSrc; bp.gatherDst = dp.gatherDst; bp.numSMs = r->numSMs;
+        GSM_CUDA(launchBucketSort(s, bp), "depth sort (buckets)");
+    } else {
+        GSM_CUDA(launchSort(s, dp), "depth sort");
+    }
     recordStage(r, s, 2);
     // stages 3+4
     const int tilePasses = tileSortPasses(tilesX * tilesY);
@@ -521,10 +555,11 @@ gsm_status gsm_render(gsm_renderer* r, void* stream, void* color, void* depth, c
     po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
+    attachDepthPlan(r, res, po, gaussianCount);
     GSM_CUDA(launchProjectMono(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, po), "project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
     recordStage(r, s, 1);
-    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY);
+    st = encodeSortExpandRange(r, res, s, false, tilesX, tilesY, true, 0u, 0xFFFFFFFFu, po.keyRange != nullptr);
     if (st != GSM_OK) return st;
     // step 8: clear + blend (DFR.swift:433-464), fused
     GSM_CUDA(launchBlendMono(s, res.lowerBounds, res.blendSplats, res.instIdx[0], width, height, tilesX, tilesY, 0, tilesY,
@@ -587,10 +622,11 @@ static gsm_status encodeStereoFrame(gsm_renderer* r, void* stream, void* colorSi
     po.depthHist = &res.fs->hist[0][0]; po.depthPasses = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 2u : 4u;
     po.depthKey16 = r->cfg.depthSortKeyPrecision == GSM_KEY_BITS16 ? 1u : 0u; po.gidFirst = 0;
     if (zeroInKernel) { po.zeroBase = (uint4*)res.fs; po.zeroVecs = res.zeroBytes / 16; }
+    attachDepthPlan(r, res, po, gaussianCount);
     GSM_CUDA(launchProjectStereo(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, sc, po), "stereo project+cull");
     GSM_CUDA(launchCompactVisible(s, gaussianCount, po, r->numSMs), "visibility compaction");
     recordStage(r, s, 1);
-    st = encodeSortExpandRange(r, res, s, true, tilesX, tilesY);
+    st = encodeSortExpandRange(r, res, s, true, tilesX, tilesY, true, 0u, 0xFFFFFFFFu, po.keyRange != nullptr);
     if (st != GSM_OK) return st;
     // steps 9+10: clear, blend both eyes, copy into the side-by-side target (DFR.swift:789-830), fused
     GSM_CUDA(launchBlendStereo(s, res.lowerBounds, (const GSMStereoTiledRenderData*)res.renderData, res.instIdx[0], width, height,
@@ -1127,6 +1163,7 @@ size_t gsm_debug_element_size(gsm_renderer* r, int which) {
         case GSM_DBG_TILE_BOUNDS: return 16;
         case GSM_DBG_RENDER_DATA: return r->lastStereo ? 32 : 16;
         case GSM_DBG_TILE_HEADERS: return 8;
+        case GSM_DBG_DEPTH_SORT_PLAN: return 16;
         case GSM_DBG_SORTED_PRIMITIVE_INDICES: case GSM_DBG_INSTANCE_OFFSETS: case GSM_DBG_N_TOUCHED_TILES:
         case GSM_DBG_INSTANCE_GAUSSIAN_INDICES: case GSM_DBG_DEPTH_KEYS: case GSM_DBG_ACTIVE_TILES:
         case GSM_DBG_SCRATCH_DEPTH_KEYS: case GSM_DBG_SCRATCH_PRIMITIVE_INDICES: return 4;
@@ -1157,6 +1194,7 @@ gsm_status gsm_debug_read(gsm_renderer* r, void* stream, int which, void* dst, s
         case GSM_DBG_ACTIVE_TILES: src = (const char*)res.activeTiles; cap = res.maxTiles; break;
         case GSM_DBG_SCRATCH_DEPTH_KEYS: src = (const char*)res.depthKeys[1]; cap = res.maxGaussians; break;
         case GSM_DBG_SCRATCH_PRIMITIVE_INDICES: src = (const char*)res.primIdx[1]; cap = res.maxGaussians; break;
+        case GSM_DBG_DEPTH_SORT_PLAN: src = (const char*)res.depthPlan; cap = 1; break;
         default: return fail(GSM_ERR_INVALID_ARGUMENT, "unknown debug buffer");
     }
     if (first > cap || count > cap - first) return fail(GSM_ERR_INVALID_ARGUMENT, "debug read out of range");

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/gsm/gsm.h"
@@ -74,8 +75,43 @@ struct FrameState {
     uint32_t ticketBlend;        // tiles of the persistent mono blend
     uint32_t ingestDone;         // group.cu: CTAs of the ingest kernel that have read all their records
     uint32_t recordTotal;        // group.cu: records received from all sources this frame (device-side N of the compaction)
-    uint32_t _pad2[5];
+    uint32_t compactDone;        // CTAs of the compaction kernel that have issued all their stores (the last one plans the depth sort)
+    uint32_t ticketBucket;       // sort.cu: tiles of the depth sort's bucket-scatter pass
+    uint32_t ticketLocal;        // sort.cu: buckets of the depth sort's local pass
+    uint32_t _pad2[2];
+    uint32_t fineHist[8192];     // depth keys per fine bin ((key - keyMin) >> shift), counted by the compaction kernel (kDepthFineBins)
 };
+
+// ---- depth sort as ONE global pass + one shared-memory pass (bucketsort.cu: bucket_scatter_kernel, bucket_local_sort_kernel),
+// used for frames of up to kDepthBucketMaxGaussians Gaussians (host-side choice; larger frames run the LSD passes of sort.cu).
+// The projection kernels record the frame's key range (KeyRange: outside the per-frame zero region because the projection
+// kernel itself clears that region; reset by the local-sort kernel). The compaction kernel counts a sample of the keys per fine
+// bin of that range (FrameState::fineHist); the scatter kernel turns the sample into bucket boundaries and sums the exact
+// bucket offsets (DepthPlan).
+constexpr uint32_t kDepthFineBins = 8192;
+constexpr uint32_t kDepthMaxBuckets = 512;
+constexpr uint32_t kDepthBucketTarget = 2048;   // expected keys per bucket
+constexpr uint32_t kDepthBucketCap = 4096;      // what one CTA of the local pass sorts in shared memory (larger buckets stream)
+constexpr uint32_t kDepthSampleStride = 8;
+constexpr uint32_t kDepthBucketMaxGaussians = 1000000;   // => at most 1e6 / 8 / 256 + 1 = 489 buckets, 326 scatter tiles of 3072 keys
+struct KeyRange {
+    uint32_t maxKey[32];      // atomicMax of key        (slot = warp tile & 31: same-address REDs serialise)
+    uint32_t maxInvKey[32];   // atomicMax of ~key  => min key = ~max; all zero = nothing recorded
+};
+struct DepthPlan {            // written by the scatter kernel's first tile, read by the local pass
+    uint32_t numBuckets;      // 0: nothing to sort
+    uint32_t keyMin, shift, _pad;                 // the fine bins' origin and width (diagnostic, gsm_debug_read)
+    uint32_t bucketStart[kDepthMaxBuckets + 4];   // exclusive offsets, [kDepthMaxBuckets] = key count
+};
+__device__ __forceinline__ void recordKeyRange(KeyRange* kr, uint32_t key, bool valid, uint32_t slot) {  // whole warp
+    if (!kr) return;
+    const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, valid ? key : 0u);
+    const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, valid ? ~key : 0u);
+    if ((threadIdx.x & 31u) == 0u && (hi | lo) != 0u) {
+        atomicMax(&kr->maxKey[slot & 31u], hi);
+        atomicMax(&kr->maxInvKey[slot & 31u], lo);
+    }
+}
 
 // What the blend stage reads per splat: the quantised record pre-expanded once per visible Gaussian
 // (conic from conicFromThetaSigmas GaussianShared.h:490-510 rounded to half exactly as

@@ -30,6 +30,9 @@ struct ProjectOut {
     // fused into the compaction kernel: digit histograms of the compacted depth keys
     uint32_t* depthHist;          // [4][256], zeroed with the frame state
     uint32_t depthPasses;
+    // depth sort as bucket scatter + local sort (bucketsort.cu): the projection records the key range and the compaction counts
+    // a sample of the keys per fine bin of that range. Null: the LSD passes run (large frames, strip ingest, 16-bit depth keys).
+    KeyRange* keyRange = nullptr;
 };
 
 int shDegreeFromComponents(uint32_t n);
@@ -65,6 +68,23 @@ struct SortPlan {
 };
 uint32_t sortTileSize(int keyBits, bool large);
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p);
+
+// The frame's depth sort as bucket scatter + local sort (bucketsort.cu), for frames bucketSortCovers() accepts; the compaction
+// kernel must have run with ProjectOut::plan / keyRange set. Result in (k0, v0), like launchSort.
+struct BucketSortPlan {
+    uint32_t* k0; uint32_t* k1; uint32_t* v0; uint32_t* v1;
+    const uint32_t* countPtr; uint32_t countCap;
+    DepthPlan* plan;      // bucket offsets, written by the scatter kernel for the local pass
+    const uint32_t* fineHist;  // FrameState::fineHist, the compaction's sample of the keys per fine bin
+    KeyRange* keyRange;   // cleared for the next frame
+    uint32_t* status;     // >= tiles * 512 zeroed words (the LSD passes' status rows: a frame uses one path or the other)
+    uint32_t* gstatus;    // >= groups * 512 + groups zeroed words
+    const uint32_t* gatherSrc; uint32_t* gatherDst;
+    int numSMs;
+};
+bool bucketSortCovers(uint32_t maxKeys, int numSMs);
+cudaError_t bucketSortPrepareDevice();
+cudaError_t launchBucketSort(cudaStream_t s, const BucketSortPlan& p);
 
 
 // instance expansion (expand.cu)

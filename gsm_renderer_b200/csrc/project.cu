@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_mono_kernel(const v
         }
     }
     if (inRange) o.preDepthKeys[gid] = key;  // compacted by compact_visible_kernel (no inter-warp wait in this kernel)
+    recordKeyRange(o.keyRange, key, touched > 0u, warpTile);  // the depth sort's bucket plan needs the frame's key range
 }
 
 // ---------------------------------------------------------------- stereo
@@ -691,6 +692,7 @@ __global__ void __launch_bounds__(kProjThreads) project_cull_stereo_kernel(const
         if (touched == 0) writeCulled(o, gid);
     }
     if (inRange) o.preDepthKeys[gid] = key;  // compacted by compact_visible_kernel (no inter-warp wait in this kernel)
+    recordKeyRange(o.keyRange, key, touched > 0u, warpTile);
 }
 
 // ---------------------------------------------------------------- stage 1.25: visibility compaction
@@ -719,6 +721,7 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
     __shared__ uint32_t s_touched[8];
     __shared__ uint32_t s_tile, s_baseVisible;
     __shared__ uint32_t s_hist[4][256];
+    __shared__ uint32_t s_keyMin, s_fineShift;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     pdlLaunchDependents();
     for (int i = tid; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
@@ -733,7 +736,22 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
         }
         return;
     }
+    // the frame's key range (recorded by the projection kernel) fixes the fine bins a sample of the keys is counted into; the
+    // depth sort's scatter kernel derives its bucket boundaries from that sample (bucketsort.cu)
+    if (o.keyRange && warp == 0) {
+        uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, o.keyRange->maxKey[lane]);
+        uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, o.keyRange->maxInvKey[lane]);
+        if (lane == 0) {
+            const bool valid = (hi | lo) != 0u && ~lo <= hi;
+            s_keyMin = valid ? ~lo : 0u;
+            const uint32_t span = valid ? hi - ~lo : 0xFFFFFFFFu;
+            const int bits = 32 - __clz(span);  // 0 for span 0
+            s_fineShift = bits > 13 ? (uint32_t)(bits - 13) : 0u;   // (span >> shift) < kDepthFineBins
+        }
+    }
     __syncthreads();
+    const bool planning = o.keyRange != nullptr;
+    const uint32_t keyMin = planning ? s_keyMin : 0u, fineShift = planning ? s_fineShift : 0u;
     while (true) {
         if (tid == 0) s_tile = atomicAdd(&o.fs->ticketProject, 1u);
         __syncthreads();
@@ -789,6 +807,8 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
                     o.depthKeys[dst] = key;
                     o.primitiveIndices[dst] = (int32_t)gid;
                     for (uint32_t p = 0; p < o.depthPasses; ++p) atomicAdd(&s_hist[p][(key >> (8u * p)) & 0xFFu], 1u);  // the sort's digit histograms
+                    if (planning && (dst % kDepthSampleStride) == 0u)   // a sample fixes the bucket boundaries (RED; one per key was 24 us)
+                        atomicAdd(&o.fs->fineHist[min((key - keyMin) >> fineShift, kDepthFineBins - 1u)], 1u);
                 }
                 dst++;
             }

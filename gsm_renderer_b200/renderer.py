@@ -228,7 +228,7 @@ class StereoRenderTarget:
 # debugRead* ids (include/gsm/gsm.h gsm_debug_buffer)
 _DBG = dict(header=0, activeTileCount=1, sortedTileIds=2, tileBounds=3, sortedPrimitiveIndices=4,
             instanceOffsets=5, nTouchedTiles=6, instanceGaussianIndices=7, depthKeys=8, renderData=9,
-            tileHeaders=10, activeTiles=11, scratchDepthKeys=12, scratchPrimitiveIndices=13)
+            tileHeaders=10, activeTiles=11, scratchDepthKeys=12, scratchPrimitiveIndices=13, depthSortPlan=14)
 
 RENDER_DATA_DTYPE = np.dtype(
     [("meanX", "<f2"), ("meanY", "<f2"), ("theta", "<u2"), ("sigma1", "<f2"), ("sigma2", "<f2"),
@@ -399,6 +399,11 @@ class DepthFirstRenderer:
         h = N.DepthFirstHeader()
         _check(self._lib.gsm_debug_read(self._h, None, _DBG["header"], C.addressof(h), 0, 1))
         return h
+
+    def debugReadDepthSortPlan(self) -> dict:
+        """No reference counterpart: the bucket plan of the last frame's depth sort (bucketCount 0 = nothing was planned)."""
+        w = self._read("depthSortPlan", np.dtype((np.uint32, 4)), 1)[0]
+        return dict(bucketCount=int(w[0]), keyMin=int(w[1]), fineShift=int(w[2]))
 
     def debugReadActiveTileCount(self) -> int:
         return int(self._read("activeTileCount", np.uint32, 1)[0])

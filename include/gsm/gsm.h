@@ -214,6 +214,8 @@ typedef enum {
     GSM_DBG_ACTIVE_TILES = 11,        /* activeTiles list (atomic append order, nondeterministic as in the reference) */
     GSM_DBG_SCRATCH_DEPTH_KEYS = 12,  /* debugReadScratchDepthKeys: ping-pong buffer, content unspecified */
     GSM_DBG_SCRATCH_PRIMITIVE_INDICES = 13, /* debugReadScratchPrimitiveIndices: same */
+    GSM_DBG_DEPTH_SORT_PLAN = 14,     /* no reference counterpart: u32 x4 {bucketCount, keyMin, fineShift, 0}: the bucket plan of
+                                         the last frame's depth sort (csrc/bucketsort.cu; stale when the LSD passes ran) */
     GSM_DBG_COUNT_
 } gsm_debug_buffer;
 
