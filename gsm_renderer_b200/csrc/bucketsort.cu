@@ -81,43 +81,61 @@ struct ScatterShared {
 };
 
 // Every CTA builds the same table: bucket(bin) = exclusive sample prefix / (T / stride), so a bucket expects ~T keys.
-__device__ __forceinline__ void buildBucketTable(const uint32_t* __restrict__ fineHist, const KeyRange* keyRange, ScatterShared& sh) {
+// The sample counts (< 65536 per bin: at most 1e6 / 8 samples in all) are loaded coalesced into the table's own storage as
+// 16-bit words, then every thread scans its 32 consecutive bins in place.
+__device__ __forceinline__ void loadSampleCounts(const uint32_t* __restrict__ fineHist, const KeyRange* keyRange, ScatterShared& sh) {
+    constexpr uint32_t PER = kDepthFineBins / kBkThreads;   // 32 bins per thread
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    {
+        uint4 v[PER / 4];
+#pragma unroll
+        for (uint32_t i = 0; i < PER / 4; ++i) v[i] = __ldcg(reinterpret_cast<const uint4*>(fineHist) + i * kBkThreads + tid);
+        uint32_t hi = 0u, lo = 0u;
+        if (tid < 32u) { hi = __ldcg(&keyRange->maxKey[lane]); lo = __ldcg(&keyRange->maxInvKey[lane]); }
+#pragma unroll
+        for (uint32_t i = 0; i < PER / 4; ++i)
+            *reinterpret_cast<uint2*>(sh.u.bucketOf + 4u * (i * kBkThreads + tid)) = make_uint2(v[i].x | (v[i].y << 16), v[i].z | (v[i].w << 16));
+        if (tid < 32u) {   // the frame's key range, as the compaction kernel derived it
+            hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+            lo = __reduce_max_sync(0xFFFFFFFFu, lo);
+            if (lane == 0) {
+                const bool valid = (hi | lo) != 0u && ~lo <= hi;
+                const uint32_t span = valid ? hi - ~lo : 0xFFFFFFFFu;
+                const int bits = 32 - __clz(span);
+                sh.keyMin = valid ? ~lo : 0u;
+                sh.fineShift = bits > 13 ? (uint32_t)(bits - 13) : 0u;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void scanSampleCounts(ScatterShared& sh) {   // after loadSampleCounts
     constexpr uint32_t PER = kDepthFineBins / kBkThreads;   // 32 consecutive bins per thread
     constexpr uint32_t TS = kDepthBucketTarget / kDepthSampleStride;
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
-    uint32_t cnt[PER];
+    const unsigned tid = threadIdx.x;
+    __syncthreads();
+    uint32_t pk[PER / 2];
+    uint4* mine = reinterpret_cast<uint4*>(sh.u.bucketOf + tid * PER);
 #pragma unroll
-    for (uint32_t i = 0; i < PER; i += 4) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(fineHist + tid * PER + i));
-        cnt[i] = v.x; cnt[i + 1] = v.y; cnt[i + 2] = v.z; cnt[i + 3] = v.w;
-    }
-    if (tid < 32u) {   // the frame's key range, as the compaction kernel derived it
-        const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, __ldcg(&keyRange->maxKey[lane]));
-        const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, __ldcg(&keyRange->maxInvKey[lane]));
-        if (lane == 0) {
-            const bool valid = (hi | lo) != 0u && ~lo <= hi;
-            const uint32_t span = valid ? hi - ~lo : 0xFFFFFFFFu;
-            const int bits = 32 - __clz(span);
-            sh.keyMin = valid ? ~lo : 0u;
-            sh.fineShift = bits > 13 ? (uint32_t)(bits - 13) : 0u;
-        }
+    for (uint32_t i = 0; i < PER / 8; ++i) {
+        const uint4 v = mine[i];
+        pk[4 * i] = v.x; pk[4 * i + 1] = v.y; pk[4 * i + 2] = v.z; pk[4 * i + 3] = v.w;
     }
     uint32_t sum = 0u;
 #pragma unroll
-    for (uint32_t i = 0; i < PER; ++i) sum += cnt[i];
+    for (uint32_t i = 0; i < PER / 2; ++i) sum += (pk[i] & 0xFFFFu) + (pk[i] >> 16);
     uint32_t total;
     uint32_t excl = blockExclusive(sum, sh.scan, total);
     if (tid == 0) sh.numBuckets = total > 0u ? min((total - 1u) / TS + 1u, kDepthMaxBuckets) : 0u;
-    uint32_t packed[PER / 2];
 #pragma unroll
-    for (uint32_t i = 0; i < PER; ++i) {
-        const uint32_t b = min(excl / TS, kDepthMaxBuckets - 1u);
-        if (i & 1u) packed[i / 2] |= b << 16; else packed[i / 2] = b;
-        excl += cnt[i];
+    for (uint32_t i = 0; i < PER / 2; ++i) {
+        const uint32_t c0 = pk[i] & 0xFFFFu, c1 = pk[i] >> 16;
+        const uint32_t b0 = min(excl / TS, kDepthMaxBuckets - 1u);
+        const uint32_t b1 = min((excl + c0) / TS, kDepthMaxBuckets - 1u);
+        pk[i] = b0 | (b1 << 16);
+        excl += c0 + c1;
     }
-    uint4* dst = reinterpret_cast<uint4*>(sh.u.bucketOf + tid * PER);
 #pragma unroll
-    for (uint32_t i = 0; i < PER / 2; i += 4) dst[i / 4] = make_uint4(packed[i], packed[i + 1], packed[i + 2], packed[i + 3]);
+    for (uint32_t i = 0; i < PER / 8; ++i) mine[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     __syncthreads();
 }
 
@@ -137,6 +155,7 @@ __device__ __forceinline__ void bucketScatterTile(const uint32_t* __restrict__ k
     const uint32_t base = tile * TILE;
     const uint32_t tileValid = min(TILE, count - base);
 
+    loadSampleCounts(fineHist, keyRange, sh);
     // warp-striped: element (warp, item, lane) has index base + warp*ITEMS*32 + item*32 + lane
     uint32_t key[ITEMS], val[ITEMS], br[ITEMS];   // br: bucket in the high half, rank inside the bucket in the low half
     const uint32_t warpBase = warp * ITEMS * 32u + lane;
@@ -150,7 +169,7 @@ __device__ __forceinline__ void bucketScatterTile(const uint32_t* __restrict__ k
         const uint32_t j = warpBase + i * 32u;
         val[i] = (j < tileValid) ? valsIn[base + j] : 0u;
     }
-    buildBucketTable(fineHist, keyRange, sh);   // under the loads just issued
+    scanSampleCounts(sh);   // under the loads just issued
     const uint32_t keyMin = sh.keyMin, fineShift = sh.fineShift;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(kBkThreads, 3) bucket_scatter_kernel(const uin
     pdlLaunchDependents();
     for (int i = tid; i < kBkWarps * kBkBins; i += kBkThreads) (&sh.warpHist[0][0])[i] = 0;
     pdlWait();
-    const uint32_t count = min(*countPtr, countCap);
+    const uint32_t count = min(ldAfterWait(countPtr), countCap);
     if (count == 0u) {
         if (blockIdx.x == 0 && tid == 0) plan->numBuckets = 0u;
         return;
@@ -283,15 +302,20 @@ constexpr uint32_t kLocalMaxBin = 32;                        // fast path: no bi
 constexpr int kLocalDB = 8;                                  // skewed path: digit bits per ballot-ranked pass
 constexpr int kLocalBins = 1 << kLocalDB;
 struct LocalShared {
-    uint32_t keysA[kDepthBucketCap];
-    uint32_t keysB[kDepthBucketCap];
-    unsigned short idxA[kDepthBucketCap];
-    unsigned short idxB[kDepthBucketCap];
-    unsigned short rank[kDepthBucketCap];
+    uint32_t keysA[kDepthBucketCap];   // raw keys in bucket order (both paths)
     union {
-        struct { uint32_t count[kLocalFastBins]; uint32_t start[kLocalFastBins]; } fast;
-        uint32_t rows[kLocalWarps][kLocalBins];
-    } h;
+        struct {   // fast path
+            uint32_t packedB[kDepthBucketCap];   // bin-ordered ((key - lo) & lowMask) << 12 | position
+            uint32_t vals[kDepthBucketCap];      // payloads in bucket order
+            uint32_t count[kLocalFastBins], start[kLocalFastBins];
+        } f;
+        struct {   // skewed path
+            uint32_t keysB[kDepthBucketCap];
+            unsigned short idxA[kDepthBucketCap], idxB[kDepthBucketCap];
+            uint32_t rows[kLocalWarps][kLocalBins];
+        } s;
+    } u;
+    unsigned short rank[kDepthBucketCap];
     uint32_t scan[9];
     uint32_t red[2][kLocalWarps];
 };
@@ -329,9 +353,9 @@ __device__ __noinline__ bool skewedBucketSort(LocalShared& sh, uint32_t n, uint3
     const uint32_t chunks = (n + kLocalThreads - 1u) / kLocalThreads;   // per warp
     const uint32_t segBase = warp * chunks * 32u + lane;
     const int passes = (bits + kLocalDB - 1) / kLocalDB;
-    uint32_t* src = sh.keysA; uint32_t* dst = sh.keysB;
-    unsigned short* srcIdx = sh.idxA; unsigned short* dstIdx = sh.idxB;
-    uint32_t* warpRow = sh.h.rows[warp];
+    uint32_t* src = sh.keysA; uint32_t* dst = sh.u.s.keysB;
+    unsigned short* srcIdx = sh.u.s.idxA; unsigned short* dstIdx = sh.u.s.idxB;
+    uint32_t* warpRow = sh.u.s.rows[warp];
     __syncthreads();   // the fast path's bin arrays share the rows
     for (int pass = 0; pass < passes; ++pass) {
         const uint32_t shift = (uint32_t)(pass * kLocalDB);
@@ -343,14 +367,14 @@ __device__ __noinline__ bool skewedBucketSort(LocalShared& sh, uint32_t n, uint3
             uint32_t run = 0u;
 #pragma unroll
             for (int w = 0; w < kLocalWarps; ++w) {
-                const uint32_t c = sh.h.rows[w][tid];
-                sh.h.rows[w][tid] = run;
+                const uint32_t c = sh.u.s.rows[w][tid];
+                sh.u.s.rows[w][tid] = run;
                 run += c;
             }
             uint32_t total;
             const uint32_t excl = blockExclusive(run, sh.scan, total);
 #pragma unroll
-            for (int w = 0; w < kLocalWarps; ++w) sh.h.rows[w][tid] += excl;
+            for (int w = 0; w < kLocalWarps; ++w) sh.u.s.rows[w][tid] += excl;
         }
         __syncthreads();
         for (uint32_t c = 0; c < chunks; ++c) {   // every warp moves its own segment
@@ -384,36 +408,36 @@ __device__ __noinline__ void streamingBucketSort(uint32_t* bufK0, uint32_t* bufV
         const uint32_t shift = 8u * (uint32_t)pass;
         s_digitBase[tid] = 0u;
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += kLocalThreads) atomicAdd(&s_digitBase[((srcK[i] - lo) >> shift) & 0xFFu], 1u);
+        for (uint32_t i = tid; i < n; i += kLocalThreads) atomicAdd(&s_digitBase[((__ldcg(srcK + i) - lo) >> shift) & 0xFFu], 1u);
         __syncthreads();
         uint32_t total;
         const uint32_t digitExcl = blockExclusive(s_digitBase[tid], sh.scan, total);
         s_digitBase[tid] = digitExcl;
         __syncthreads();
         for (uint32_t c0 = 0; c0 < n; c0 += CH) {
-            for (int i = lane; i < 256; i += 32) sh.h.rows[warp][i] = 0u;
+            for (int i = lane; i < 256; i += 32) sh.u.s.rows[warp][i] = 0u;
             __syncwarp();
             uint32_t key[8], val[8], rank[8];
             const uint32_t wb = c0 + warp * 256u + lane;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint32_t j = wb + i * 32u;
-                key[i] = j < n ? srcK[j] : 0xFFFFFFFFu;
-                val[i] = j < n ? srcV[j] : 0u;
+                key[i] = j < n ? __ldcg(srcK + j) : 0xFFFFFFFFu;
+                val[i] = j < n ? __ldcg(srcV + j) : 0u;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint32_t j = wb + i * 32u;
                 const uint32_t d = j < n ? ((key[i] - lo) >> shift) & 0xFFu : 0xFFu;   // padding: last digit, last in index order
-                rank[i] = warpRankDigit<8>(d, sh.h.rows[warp], lane);
+                rank[i] = warpRankDigit<8>(d, sh.u.s.rows[warp], lane);
             }
             __syncthreads();
             {   // thread d: exclusive prefix over warps on top of the running digit offset, which advances by the chunk's count
                 uint32_t run = s_digitBase[tid];
 #pragma unroll
                 for (int w = 0; w < kLocalWarps; ++w) {
-                    const uint32_t c = sh.h.rows[w][tid];
-                    sh.h.rows[w][tid] = run;
+                    const uint32_t c = sh.u.s.rows[w][tid];
+                    sh.u.s.rows[w][tid] = run;
                     run += c;
                 }
                 s_digitBase[tid] = run;   // padding inflates only digit 0xFF of the LAST chunk: never read again
@@ -423,7 +447,7 @@ __device__ __noinline__ void streamingBucketSort(uint32_t* bufK0, uint32_t* bufV
             for (int i = 0; i < 8; ++i) {
                 const uint32_t j = wb + i * 32u;
                 if (j < n) {
-                    const uint32_t p = sh.h.rows[warp][((key[i] - lo) >> shift) & 0xFFu] + rank[i];
+                    const uint32_t p = sh.u.s.rows[warp][((key[i] - lo) >> shift) & 0xFFu] + rank[i];
                     dstK[p] = key[i];
                     dstV[p] = val[i];
                 }
@@ -434,7 +458,7 @@ __device__ __noinline__ void streamingBucketSort(uint32_t* bufK0, uint32_t* bufV
         t = srcV; srcV = dstV; dstV = t;
     }
     if (srcK != bufK0) {   // zero or an even number of passes: the result sits in the input pair
-        for (uint32_t i = tid; i < n; i += kLocalThreads) { bufK0[i] = srcK[i]; bufV0[i] = srcV[i]; }
+        for (uint32_t i = tid; i < n; i += kLocalThreads) { bufK0[i] = __ldcg(srcK + i); bufV0[i] = __ldcg(srcV + i); }
         __syncthreads();
     }
 }
@@ -451,10 +475,10 @@ __global__ void __launch_bounds__(kLocalThreads, 3) bucket_local_sort_kernel(uin
     pdlWait();
     // the key range was consumed by the compaction and scatter kernels (complete now); clear it for the next frame's projection
     if (blockIdx.x == gridDim.x - 1 && tid < 64) (&keyRange->maxKey[0])[tid] = 0u;
-    const uint32_t numBuckets = plan->numBuckets;
+    const uint32_t numBuckets = ldAfterWait(&plan->numBuckets);
     for (uint32_t bucket = blockIdx.x; bucket < numBuckets; bucket += gridDim.x) {
-        const uint32_t start = plan->bucketStart[bucket];
-        const uint32_t n = plan->bucketStart[bucket + 1] - start;
+        const uint32_t start = ldAfterWait(plan->bucketStart + bucket);
+        const uint32_t n = ldAfterWait(plan->bucketStart + bucket + 1) - start;
         if (n == 0u) continue;
         // key range of the bucket: the passes sort key - lo, which has `bits` significant bits
         const bool fits = n <= kDepthBucketCap;
@@ -462,10 +486,10 @@ __global__ void __launch_bounds__(kLocalThreads, 3) bucket_local_sort_kernel(uin
 #pragma unroll 4
         for (uint32_t i = tid; i < n; i += kLocalThreads) {
             const uint32_t k = keysIn[start + i];
-            if (fits) sh.keysA[i] = k;
+            if (fits) { sh.keysA[i] = k; sh.u.f.vals[i] = valsIn[start + i]; }
             lo = min(lo, k); hi = max(hi, k);
         }
-        for (int i = tid; i < kLocalFastBins; i += kLocalThreads) sh.h.fast.count[i] = 0u;
+        for (int i = tid; i < kLocalFastBins; i += kLocalThreads) sh.u.f.count[i] = 0u;
         lo = __reduce_min_sync(0xFFFFFFFFu, lo);
         hi = __reduce_max_sync(0xFFFFFFFFu, hi);
         if (lane == 0) { sh.red[0][warp] = lo; sh.red[1][warp] = hi; }
@@ -478,56 +502,58 @@ __global__ void __launch_bounds__(kLocalThreads, 3) bucket_local_sort_kernel(uin
             streamingBucketSort(keysOut + start, valsOut + start, keysIn + start, valsIn + start, n, lo, bits, sh);
             __syncthreads();
             if (gatherDst)
-                for (uint32_t i = tid; i < n; i += kLocalThreads) gatherDst[start + i] = __ldg(gatherSrc + valsOut[start + i]);
+                for (uint32_t i = tid; i < n; i += kLocalThreads) gatherDst[start + i] = __ldg(gatherSrc + __ldcg(valsOut + start + i));
             __syncthreads();
             continue;
         }
-        // ---- fast path: bins by the top bits of key - lo, one shared-memory atomic per element (order inside a bin arbitrary)
+        // ---- fast path: bins by the top 10 bits of key - lo, one shared-memory atomic per element (order inside a bin arbitrary)
         const uint32_t binShift = bits > 10 ? (uint32_t)(bits - 10) : 0u;
+        const uint32_t lowMask = (1u << binShift) - 1u;
 #pragma unroll 4
         for (uint32_t i = tid; i < n; i += kLocalThreads)
-            sh.rank[i] = (unsigned short)atomicAdd(&sh.h.fast.count[(sh.keysA[i] - lo) >> binShift], 1u);
+            sh.rank[i] = (unsigned short)atomicAdd(&sh.u.f.count[(sh.keysA[i] - lo) >> binShift], 1u);
         __syncthreads();
         bool skewed;
         {
-            const uint4 c = *reinterpret_cast<const uint4*>(&sh.h.fast.count[4u * tid]);
+            const uint4 c = *reinterpret_cast<const uint4*>(&sh.u.f.count[4u * tid]);
             uint32_t total;
             const uint32_t excl = blockExclusive(c.x + c.y + c.z + c.w, sh.scan, total);
-            *reinterpret_cast<uint4*>(&sh.h.fast.start[4u * tid]) = make_uint4(excl, excl + c.x, excl + c.x + c.y, excl + c.x + c.y + c.z);
-            skewed = __syncthreads_or(max(max(c.x, c.y), max(c.z, c.w)) > kLocalMaxBin) != 0;
+            *reinterpret_cast<uint4*>(&sh.u.f.start[4u * tid]) = make_uint4(excl, excl + c.x, excl + c.x + c.y, excl + c.x + c.y + c.z);
+            // the packed word keeps 20 bits of the key below the bin bits
+            skewed = __syncthreads_or(max(max(c.x, c.y), max(c.z, c.w)) > kLocalMaxBin || binShift > 20u) != 0;
         }
-        bool inA = true;
         if (!skewed) {
 #pragma unroll 4
             for (uint32_t i = tid; i < n; i += kLocalThreads) {
                 const uint32_t rel = sh.keysA[i] - lo;
-                const uint32_t p = sh.h.fast.start[rel >> binShift] + sh.rank[i];
-                sh.keysB[p] = rel;
-                sh.idxB[p] = (unsigned short)i;
+                sh.u.f.packedB[sh.u.f.start[rel >> binShift] + sh.rank[i]] = ((rel & lowMask) << 12) | i;
             }
             __syncthreads();
-            // place every element by counting the smaller (key, position) pairs of its bin
+            // An element's place = its bin's offset + the number of smaller (key, position) words in the bin. The pair goes
+            // straight to its final place in global memory, with the tile count fetched through the payload.
 #pragma unroll 2
             for (uint32_t p = tid; p < n; p += kLocalThreads) {
-                const uint32_t rel = sh.keysB[p];
-                const uint32_t id = sh.idxB[p];
-                const uint32_t bin = rel >> binShift;
-                const uint32_t b = sh.h.fast.start[bin], e = b + sh.h.fast.count[bin];
+                const uint32_t pk = sh.u.f.packedB[p];
+                const uint32_t i = pk & 0xFFFu;
+                const uint32_t key = sh.keysA[i];
+                const uint32_t val = sh.u.f.vals[i];
+                const uint32_t bin = (key - lo) >> binShift;
+                const uint32_t b = sh.u.f.start[bin], e = b + sh.u.f.count[bin];
+                uint32_t touched = 0u;
+                if (gatherDst) touched = __ldg(gatherSrc + val);
                 uint32_t smaller = 0u;
-                for (uint32_t q = b; q < e; ++q) {
-                    const uint32_t r2 = sh.keysB[q];
-                    const uint32_t i2 = sh.idxB[q];
-                    smaller += (uint32_t)(r2 < rel) | ((uint32_t)(r2 == rel) & (uint32_t)(i2 < id));
-                }
-                sh.keysA[b + smaller] = rel + lo;   // nobody reads the raw keys any more
-                sh.idxA[b + smaller] = (unsigned short)id;
+                for (uint32_t q = b; q < e; ++q) smaller += sh.u.f.packedB[q] < pk ? 1u : 0u;
+                const uint32_t dst = start + b + smaller;
+                keysOut[dst] = key;
+                valsOut[dst] = val;
+                if (gatherDst) gatherDst[dst] = touched;
             }
             __syncthreads();
-        } else {
-            inA = skewedBucketSort(sh, n, lo, bits);
+            continue;
         }
-        const uint32_t* sorted = inA ? sh.keysA : sh.keysB;
-        const unsigned short* sortedIdx = inA ? sh.idxA : sh.idxB;
+        const bool inA = skewedBucketSort(sh, n, lo, bits);
+        const uint32_t* sorted = inA ? sh.keysA : sh.u.s.keysB;
+        const unsigned short* sortedIdx = inA ? sh.u.s.idxA : sh.u.s.idxB;
         // positions [0, n) hold (key, original position inside the bucket); the payload is fetched through that position and
         // the tile count through the payload -- four elements per trip, every load of a stage issued before any is used
         for (uint32_t j0 = tid; j0 < n; j0 += 4u * kLocalThreads) {

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
     __shared__ int32_t s_idx[8][32];
     __shared__ uint32_t s_scan[9];
     __shared__ uint32_t s_tile, s_tileBase;
-    const uint32_t visibleCount = header->visibleCount;
+    const uint32_t visibleCount = ldAfterWait(&header->visibleCount);
     const unsigned warp = threadIdx.x >> 5;
     const uint32_t numTiles = (visibleCount + 255u) / 256u;
 

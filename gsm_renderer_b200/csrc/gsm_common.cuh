@@ -20,6 +20,15 @@ namespace gsm {
 // implies "its predecessor completed" down the chain.
 __device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// A scalar the predecessor kernel produced (a device-side count, a header field): read it with this after pdlWait(), never
+// through a `const T* __restrict__` pointer -- nvcc treats such loads as invariant and may hoist them ABOVE the inline-asm wait
+// (SASS: LDG.E.CONSTANT before ACQBULK; found when the depth sort's local pass read a bucket count of zero). A volatile asm
+// load cannot move across the volatile asm wait. tools/check_pdl_hoist.py and tests/test_abi.py scan the built library for it.
+__device__ __forceinline__ uint32_t ldAfterWait(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 bool pdlEnabled();  // capi.cu: GSM_PDL=0 in the environment turns the attribute off (A/B measurement)
 

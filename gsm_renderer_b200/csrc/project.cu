@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
     pdlLaunchDependents();
     for (int i = tid; i < 4 * 256; i += 256) (&s_hist[0][0])[i] = 0u;
     pdlWait();
-    if (o.countPtr) N = min(*o.countPtr, N);  // routed records: the count exists only on the device
+    if (o.countPtr) N = min(ldAfterWait(o.countPtr), N);  // routed records: the count exists only on the device
     const uint32_t numTiles = (N + 256u * kCompactItems - 1u) / (256u * kCompactItems);
     if (numTiles == 0u) {  // nothing arrived: no last tile will write the header
         if (blockIdx.x == 0 && tid == 0) {

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) tile_lower_bounds_kernel(const TileT* __r
     constexpr uint32_t PER = 16u / sizeof(TileT);
     pdlLaunchDependents();
     pdlWait();
-    const uint32_t total = header->totalInstances;
+    const uint32_t total = ldAfterWait(&header->totalInstances);
     const uint32_t first = (blockIdx.x * 256u + threadIdx.x) * PER;
     if (first > total) return;  // first == total still closes the last run
     TileT ids[PER];

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const KeyT* __rest
     for (int i = threadIdx.x; i < NPASS * 256; i += 256) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     pdlWait();
-    const uint32_t count = min(*countPtr, countCap);
+    const uint32_t count = min(ldAfterWait(countPtr), countCap);
     {   // reset the look-back words this frame's passes will use (sized by the device-side count, not the capacity)
         constexpr uint32_t TILE = kSortThreads * ITEMS;
         const uint32_t words = ((count + TILE - 1) / TILE) * 256u;
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(kSortThreads, ((sizeof(KeyT) == 4 && ITEMS == 
     pdlWait();
     uint32_t firstTicket = 0;
     if (tid == 0) firstTicket = atomicAdd(ticket, 1u);
-    const uint32_t digitTotal = digitHist[tid];
-    const uint32_t count = min(*countPtr, countCap);
+    const uint32_t digitTotal = ldAfterWait(digitHist + tid);
+    const uint32_t count = min(ldAfterWait(countPtr), countCap);
     const uint32_t numTiles = (count + TILE - 1) / TILE;
 #ifdef GSM_SORT_TRACE
     const size_t traceBase = (size_t)(shift >> 3) * numTiles;

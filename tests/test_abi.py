@@ -105,3 +105,18 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("CPU oracle", "").replace("the oracle", "").lower() or \
                     not re.search(r"(import\s+oracle|from\s+oracle|#include\s+[\"<].*oracle|gsm_oracle|gsmo_)", txt), f
+
+
+def test_no_global_access_before_dependent_launch_wait(native):
+    """Every kernel of the chain reads its predecessor's output only after griddepcontrol.wait. nvcc may hoist a load through a
+    `const T* __restrict__` pointer (an invariant load) above the inline-asm wait: tools/check_pdl_hoist.py scans the SASS of
+    the built library for global loads / atomics scheduled before the first ACQBULK of a kernel (round 2: the depth sort's local
+    pass read its bucket count before the scatter kernel had written it; create_instances read the frame header early)."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_pdl_hoist.py"),
+                          os.path.join(root, "gsm_renderer_b200", "lib", "libgsm_b200.so")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:]
