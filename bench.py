@@ -30,6 +30,16 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: native libraries that print to fd 1 (NCCL's version banner under NCCL_DEBUG=VERSION)
+# are sent to stderr for the whole run; emit_line() writes the result to the real stdout
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_line(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -200,7 +210,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -541,7 +551,7 @@ def main():
         "clocks": clocks,
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

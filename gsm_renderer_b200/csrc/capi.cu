@@ -224,7 +224,7 @@ gsm_status ensureResources(gsm_renderer* r, Resources& res, bool stereo) {
     const size_t oScanGroups = take(((size_t)(G + 255) / 256 / 32 + 8) * 8);
     // the sorts' per-tile status words are part of the per-frame memset too (a few MB: cheaper than a reset kernel's launch)
     const size_t oDepthStatus = take((size_t)4 * res.depthTilesCap * 256 * 4);
-    const size_t oTileStatus = take((size_t)(tile16 ? 2 : 4) * res.tileTilesCap * 256 * 4);
+    const size_t oTileStatus = take(((size_t)(tile16 ? 2 : 4) * res.tileTilesCap + 258) * 256 * 4);  // + 256 rows: the MSD tile sort numbers its chunks per bucket (tilesort.cu)
     const size_t oDepthGStatus = take((size_t)4 * sortGroupRows(res.depthTilesCap) * 256 * 4);
     const size_t oTileGStatus = take((size_t)(tile16 ? 2 : 4) * sortGroupRows(res.tileTilesCap) * 256 * 4);
     const size_t zeroEnd = off;
@@ -278,6 +278,11 @@ void freeResources(Resources& res) {
 
 bool largeSort(uint32_t frameGaussians) { return frameGaussians >= 3000000u; }  // see sort.cu: sortTileSize
 
+// GSM_TILE_MSD=0 in the environment keeps the tile sort on the LSD passes + the range kernel (A/B measurement)
+bool tileSortMsdEnabled() {
+    static const bool on = [] { const char* e = getenv("GSM_TILE_MSD"); return !(e && e[0] == '0'); }();
+    return on;
+}
 // GSM_DEPTH_BUCKETS=0 in the environment keeps the depth sort on the four LSD passes (A/B measurement)
 bool depthBucketsEnabled() {
     static const bool on = [] { const char* e = getenv("GSM_DEPTH_BUCKETS"); return !(e && e[0] == '0'); }();
@@ -337,10 +342,14 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     // stages 3+4
     const int tilePasses = tileSortPasses(tilesX * tilesY);
     recordStage(r, s, 3);
+    // 16-bit ids of 9..16 bits on frames small enough for the direct-summation prefix: one pass on the high byte + a local
+    // pass per bucket that also writes the tile ranges (tilesort.cu); else the LSD passes + the range kernel
+    const uint32_t lowBits = tileSortLowBits(tilesX * tilesY);
+    const bool msdTiles = tileSortMsdEnabled() && tile16 && tilePasses == 2 && lowBits > 0u && !largeSort(res.frameGaussians);
     // stage 5
     GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.offsets, res.hitMask, res.offsets, res.scanStatus, res.scanGroups, &res.fs->ticketScan, res.bounds, res.renderData, res.tileIds[0],
                                    res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians, &res.fs->hist[4][0],
-                                   (uint32_t)tilePasses, r->numSMs), "create instances");
+                                   (uint32_t)tilePasses, r->numSMs, msdTiles ? lowBits : 0xFFFFFFFFu), "create instances");
     recordStage(r, s, 4);
     // stage 6
     SortPlan tp;
@@ -351,12 +360,20 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     tp.largeTiles = largeSort(res.frameGaussians);
     tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tilePasses;
     tp.numSMs = r->numSMs; tp.histogramReady = true;  // create_instances_kernel filled hist[4..7]; the status words were cleared with the frame state
+    if (msdTiles) { tp.numPasses = 1; tp.shift0 = (int)lowBits; tp.leaveInScratch = true; }
     GSM_CUDA(launchSort(s, tp), "tile sort");
+    if (msdTiles)
+        GSM_CUDA(launchTileLocalSort(s, res.tileIds[1], (const uint32_t*)res.instIdx[1], res.tileIds[0], (uint32_t*)res.instIdx[0],
+                                     &res.fs->hist[4][0], res.header, res.maxInstances, lowBits, tilesX * tilesY, res.lowerBounds,
+                                     res.tileSortStatus + (size_t)res.tileTilesCap * 256u),
+                 "tile sort (local pass)");
     recordStage(r, s, 5);
     // stage 7
-    const uint32_t rowEnd = tileRowCount > tilesY - tileRowFirst ? tilesY : tileRowFirst + tileRowCount;
-    GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.maxInstances,
-                              tileRowFirst * tilesX, rowEnd * tilesX), "tile ranges");
+    if (!msdTiles) {
+        const uint32_t rowEnd = tileRowCount > tilesY - tileRowFirst ? tilesY : tileRowFirst + tileRowCount;
+        GSM_CUDA(launchTileRanges(s, tile16, res.tileIds[0], res.header, tilesX * tilesY, res.lowerBounds, res.maxInstances,
+                                  tileRowFirst * tilesX, rowEnd * tilesX), "tile ranges");
+    }
     recordStage(r, s, 6);
     return GSM_OK;
 }

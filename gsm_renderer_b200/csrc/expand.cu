@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
                                                                TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx,
                                                                const GSMDepthFirstHeader* __restrict__ header, uint32_t tilesX,
                                                                uint32_t maxAssignments, uint32_t* __restrict__ tileHist,
-                                                               uint32_t tilePasses) {
+                                                               uint32_t tilePasses, uint32_t msdShift) {
     // the mask replay and the tile-test walk run one after the other: one buffer serves both
     union WarpWork { WarpTileWork test; WarpMaskWork replay; };
     __shared__ WarpWork s_warpWork[8];
@@ -144,14 +144,14 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
         GSM_XTRACE(tile, 4);
         if (!STEREO)
             warpEmitMasked<TileT>(s_warpWork[warp].replay, mask, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
-                                  tileIds, instanceIdx, &s_hist[0][0], tilePasses);
+                                  tileIds, instanceIdx, &s_hist[0][0], tilePasses, msdShift);
         if (STEREO) {
             // every tile of the union AABB is an instance, no ellipse test (DFS.metal:816-825)
             warpEmitBox<TileT>(s_warpWork[warp].replay, n, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
-                               tileIds, instanceIdx, &s_hist[0][0], tilePasses);
+                               tileIds, instanceIdx, &s_hist[0][0], tilePasses, msdShift);
         } else {
             warpEmitTiles<TileT>(s_warpWork[warp].test, n, q, minTX, minTY, maxTX - minTX + 1, writeOffset, originalIdx, tilesX, maxAssignments,
-                                 tileIds, instanceIdx, s_base[warp], s_idx[warp], &s_hist[0][0], tilePasses);
+                                 tileIds, instanceIdx, s_base[warp], s_idx[warp], &s_hist[0][0], tilePasses, msdShift);
         }
 #ifdef GSM_EXPAND_TRACE
         GSM_XTRACE(tile, 5);
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
 #endif
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < tilePasses * 256u; i += 256u) {
+    for (uint32_t i = threadIdx.x; i < (msdShift != kNoMsdShift ? 256u : tilePasses * 256u); i += 256u) {
         const uint32_t v = (&s_hist[0][0])[i];
         if (v) atomicAdd(&tileHist[i], v);
     }
@@ -169,12 +169,12 @@ __global__ void __launch_bounds__(256) create_instances_kernel(const int32_t* __
 cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* sortedTouched,
                                   const uint2* hitMask, uint32_t* offsets, unsigned long long* scanStatus, unsigned long long* scanGroups, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
-                                  uint32_t* tileHist, uint32_t tilePasses, int numSMs) {
+                                  uint32_t* tileHist, uint32_t tilePasses, int numSMs, uint32_t msdShift) {
     uint32_t grid = (capVisible + 255u) / 256u;
     // persistent, 6 CTAs per SM: 3 left the kernel 25 % slower, 8 changed nothing (profiles/README.md); few CTAs flush the histograms
     if (grid > (uint32_t)numSMs * 6u) grid = (uint32_t)numSMs * 6u;
     if (grid == 0) grid = 1;
-#define GSM_LAUNCH(T, ST) launchChained(create_instances_kernel<T, ST>, grid, 256, s, sortedIdx, sortedTouched, hitMask, offsets, scanStatus, scanGroups, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses)
+#define GSM_LAUNCH(T, ST) launchChained(create_instances_kernel<T, ST>, grid, 256, s, sortedIdx, sortedTouched, hitMask, offsets, scanStatus, scanGroups, ticket, bounds, renderData, (T*)tileIds, instanceIdx, header, tilesX, maxAssignments, tileHist, tilePasses, msdShift)
     if (tileId16) { if (stereo) GSM_LAUNCH(uint16_t, true); else GSM_LAUNCH(uint16_t, false); }
     else { if (stereo) GSM_LAUNCH(uint32_t, true); else GSM_LAUNCH(uint32_t, false); }
 #undef GSM_LAUNCH

@@ -65,6 +65,8 @@ struct SortPlan {
     const uint32_t* gatherSrc = nullptr;  // optional: the last pass also writes gatherDst[i] = gatherSrc[sorted payload i]
     uint32_t* gatherDst = nullptr;
     bool histogramReady; // hist filled and status/gstatus zeroed by earlier kernels of the frame (fused); else a histogram kernel runs
+    int shift0 = 0;      // digit of pass p = (key >> (shift0 + 8p)) & 0xFF
+    bool leaveInScratch = false;  // odd pass counts: do not copy the result back from (k1, v1) (the MSD tile sort's local pass reads it there)
 };
 uint32_t sortTileSize(int keyBits, bool large);
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p);
@@ -91,7 +93,16 @@ cudaError_t launchBucketSort(cudaStream_t s, const BucketSortPlan& p);
 cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, const int32_t* sortedIdx, const uint32_t* sortedTouched,
                                   const uint2* hitMask, uint32_t* offsets, unsigned long long* scanStatus, unsigned long long* scanGroups, uint32_t* ticket, const int32_t* bounds, const void* renderData, void* tileIds, int32_t* instanceIdx,
                                   const GSMDepthFirstHeader* header, uint32_t tilesX, uint32_t maxAssignments, uint32_t capVisible,
-                                  uint32_t* tileHist, uint32_t tilePasses, int numSMs);
+                                  uint32_t* tileHist, uint32_t tilePasses, int numSMs,
+                                  uint32_t msdShift = 0xFFFFFFFFu);  // != ~0: histogram of (tileId >> msdShift) & 0xFF instead (tilesort.cu)
+
+// MSD tile sort, second half (tilesort.cu): after ONE onesweep pass with shift0 = lowBits on the ids' high byte, one CTA per
+// bucket finishes the stable sort on the low bits into (keysOut, valsOut) and writes the tile ranges (no range kernel).
+uint32_t tileSortLowBits(uint32_t tileCount);
+cudaError_t launchTileLocalSort(cudaStream_t s, const void* keysIn, const uint32_t* valsIn, void* keysOut, uint32_t* valsOut,
+                                const uint32_t* bucketHist, const GSMDepthFirstHeader* header, uint32_t capInstances, uint32_t lowBits,
+                                uint32_t tileCount, uint32_t* lowerBounds, uint32_t* chunkCounts);
+// chunkCounts: (capInstances / 4096 + 257) rows of 2^lowBits words of scratch
 
 // tile ranges (ranges.cu)
 cudaError_t launchTileRanges(cudaStream_t s, bool tileId16, const void* sortedTileIds, const GSMDepthFirstHeader* header,

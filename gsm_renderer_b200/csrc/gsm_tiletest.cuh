@@ -193,12 +193,16 @@ struct WarpMaskWork {
 // Every lane passes its splat's hit mask (0 if it has none or takes the tile-test path), AABB origin and width, the
 // scan offset and the original index. Instance r of a splat is its r-th set bit; lanes take instances, not splats, so
 // the stores are coalesced and the work is balanced. Emission order and the maxAssignments bound are those of
+// msdShift of the emit functions: the tile sort runs as one pass on the id's high byte + a local pass (tilesort.cu) and wants the
+// histogram of (tileId >> msdShift) & 0xFF instead of the LSD passes' digit histograms.
+constexpr uint32_t kNoMsdShift = 0xFFFFFFFFu;
+
 // DFS.metal:692-715. The tile sort's digit histograms are accumulated for the stored instances.
 template <typename TileT>
 __device__ __forceinline__ void warpEmitMasked(WarpMaskWork& s, uint2 mask, int minTX, int minTY, int w, uint32_t writeBase,
                                                int32_t originalIdx, uint32_t tilesX, uint32_t maxAssignments,
                                                TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx, uint32_t* sHist,
-                                               uint32_t histPasses) {
+                                               uint32_t histPasses, uint32_t msdShift) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n = (uint32_t)__popc(mask.x) + (uint32_t)__popc(mask.y);
     uint32_t total;
@@ -240,15 +244,18 @@ __device__ __forceinline__ void warpEmitMasked(WarpMaskWork& s, uint2 mask, int 
             if (dst < maxAssignments) {  // DFS.metal:707
                 tileIds[dst] = (TileT)tileId;
                 instanceIdx[dst] = s.idx[o];
-                atomicAdd(&sHist[tileId & 0xFFu], 1u);
+                if (msdShift == kNoMsdShift) atomicAdd(&sHist[tileId & 0xFFu], 1u);
                 stored = true;
             }
         }
-        if (histPasses > 1) {  // upper digits are shared by most lanes: one shared-memory atomic per distinct value
-            const uint32_t hi = stored ? (tileId >> 8) : 0xFFFFFFFFu;
+        if (histPasses > 1 || msdShift != kNoMsdShift) {  // upper digits are shared by most lanes: one shared-memory atomic per distinct value
+            const bool msd = msdShift != kNoMsdShift;
+            const uint32_t hi = stored ? (tileId >> (msd ? msdShift : 8u)) : 0xFFFFFFFFu;
             const unsigned peers = __match_any_sync(0xFFFFFFFFu, hi);
-            if (stored && (peers & ((1u << lane) - 1u)) == 0u)
-                for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], (uint32_t)__popc(peers));
+            if (stored && (peers & ((1u << lane) - 1u)) == 0u) {
+                if (msd) atomicAdd(&sHist[hi & 0xFFu], (uint32_t)__popc(peers));   // the bucket histogram of the MSD tile sort
+                else for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], (uint32_t)__popc(peers));
+            }
         }
     }
     __syncwarp();
@@ -261,7 +268,7 @@ template <typename TileT>
 __device__ __forceinline__ void warpEmitBox(WarpMaskWork& s, uint32_t n, int minTX, int minTY, int w, uint32_t writeBase,
                                             int32_t originalIdx, uint32_t tilesX, uint32_t maxAssignments,
                                             TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx, uint32_t* sHist,
-                                            uint32_t histPasses) {
+                                            uint32_t histPasses, uint32_t msdShift) {
     const unsigned lane = threadIdx.x & 31u;
     uint32_t total;
     const uint32_t excl = warpExclusiveScan(n, total);
@@ -289,15 +296,18 @@ __device__ __forceinline__ void warpEmitBox(WarpMaskWork& s, uint32_t n, int min
             if (dst < maxAssignments) {  // DFS.metal:832
                 tileIds[dst] = (TileT)tileId;
                 instanceIdx[dst] = s.idx[o];
-                atomicAdd(&sHist[tileId & 0xFFu], 1u);
+                if (msdShift == kNoMsdShift) atomicAdd(&sHist[tileId & 0xFFu], 1u);
                 stored = true;
             }
         }
-        if (histPasses > 1) {  // upper digits are shared by most lanes: one shared-memory atomic per distinct value
-            const uint32_t hi = stored ? (tileId >> 8) : 0xFFFFFFFFu;
+        if (histPasses > 1 || msdShift != kNoMsdShift) {  // upper digits are shared by most lanes: one shared-memory atomic per distinct value
+            const bool msd = msdShift != kNoMsdShift;
+            const uint32_t hi = stored ? (tileId >> (msd ? msdShift : 8u)) : 0xFFFFFFFFu;
             const unsigned peers = __match_any_sync(0xFFFFFFFFu, hi);
-            if (stored && (peers & ((1u << lane) - 1u)) == 0u)
-                for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], (uint32_t)__popc(peers));
+            if (stored && (peers & ((1u << lane) - 1u)) == 0u) {
+                if (msd) atomicAdd(&sHist[hi & 0xFFu], (uint32_t)__popc(peers));   // the bucket histogram of the MSD tile sort
+                else for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], (uint32_t)__popc(peers));
+            }
         }
     }
     __syncwarp();
@@ -309,7 +319,7 @@ template <typename TileT>
 __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const QuantSplat& q, int minTX, int minTY, int w,
                                               uint32_t writeBase, int32_t originalIdx, uint32_t tilesX, uint32_t maxAssignments,
                                               TileT* __restrict__ tileIds, int32_t* __restrict__ instanceIdx, uint32_t* sBase,
-                                              int32_t* sIdx, uint32_t* sHist, uint32_t histPasses) {
+                                              int32_t* sIdx, uint32_t* sHist, uint32_t histPasses, uint32_t msdShift) {
     const unsigned lane = threadIdx.x & 31u;
     uint32_t total;
     const uint32_t excl = warpExclusiveScan(n, total);
@@ -339,11 +349,12 @@ __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const
         __syncwarp();
         if (active && (peers & ((1u << lane) - 1u)) == 0u) s.counter[o] = before + __popc(hits);
         __syncwarp();
-        if (histPasses > 1) {
+        if (histPasses > 1 || msdShift != kNoMsdShift) {
             // higher digits are equal along a tile row, so one shared-memory atomic per lane would serialise; lanes
             // that hit and share the upper bits with their left neighbour form a run and only its head adds the run length
             const bool counted = hit && (sBase[o] + before + __popc(hits & ((1u << lane) - 1u)) < maxAssignments);
-            const uint32_t hi = tileId >> 8;
+            const bool msd = msdShift != kNoMsdShift;
+            const uint32_t hi = tileId >> (msd ? msdShift : 8u);
             const uint32_t hiPrev = __shfl_up_sync(0xFFFFFFFFu, hi, 1);
             const unsigned cmask = __ballot_sync(0xFFFFFFFFu, counted);
             const bool head = counted && (lane == 0 || !((cmask >> (lane - 1)) & 1u) || hiPrev != hi);
@@ -354,7 +365,8 @@ __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const
                 const unsigned stop = after | breaks;
                 const uint32_t endLane = stop ? (uint32_t)(__ffs(stop) - 1) : 32u;
                 const uint32_t runLen = endLane - lane;
-                for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], runLen);
+                if (msd) atomicAdd(&sHist[hi & 0xFFu], runLen);
+                else for (uint32_t p = 1; p < histPasses; ++p) atomicAdd(&sHist[p * 256u + ((tileId >> (8u * p)) & 0xFFu)], runLen);
             }
         }
         if (hit) {
@@ -362,7 +374,7 @@ __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const
             if (pos < maxAssignments) {  // DFS.metal:707
                 tileIds[pos] = (TileT)tileId;
                 instanceIdx[pos] = sIdx[o];
-                atomicAdd(&sHist[tileId & 0xFFu], 1u);  // low digit: neighbouring lanes hold consecutive tiles, no conflict
+                if (msdShift == kNoMsdShift) atomicAdd(&sHist[tileId & 0xFFu], 1u);  // low digit: neighbouring lanes hold consecutive tiles, no conflict
             }
         }
     }

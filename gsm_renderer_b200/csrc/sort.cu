@@ -397,12 +397,12 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
         launchChained(kernel, grid, kSortThreads, s,
                       even ? k0 : k1, even ? p.v0 : p.v1, even ? k1 : k0, even ? p.v1 : p.v0, p.countPtr, p.countCap,
                       p.hist + 256 * pass, p.status + (size_t)pass * p.tilesCap * 256u,
-                      p.gstatus + (size_t)pass * sortGroupRows(p.tilesCap) * 256u, p.tickets + pass, 8 * pass,
+                      p.gstatus + (size_t)pass * sortGroupRows(p.tilesCap) * 256u, p.tickets + pass, p.shift0 + 8 * pass,
                       p.gatherSrc, p.gatherDst);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (p.numPasses & 1) {  // odd pass count: result is in the scratch pair, copy back (TileSortEncoder.swift:170-177)
+    if ((p.numPasses & 1) && !p.leaveInScratch) {  // odd pass count: result is in the scratch pair, copy back (TileSortEncoder.swift:170-177)
         e = cudaMemcpyAsync(p.k0, p.k1, (size_t)p.countCap * sizeof(KeyT), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
         e = cudaMemcpyAsync(p.v0, p.v1, (size_t)p.countCap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
