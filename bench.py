@@ -187,6 +187,42 @@ def cpu_baseline_dict(fps, cores, sample, fr):
                     "stage is that emulation's cost, so this is a parity definition timed, not a tuned CPU renderer"}
 
 
+def library_sort_bar(torch, V, I, T, stage_ms):
+    """cub::DeviceRadixSort::SortPairs (tools/cub_bar.cu, built by __graft_entry__.build) on arrays of the frame's own sizes and
+    key distributions, timed with CUDA events beside the frame's sort stages: V (depth key u32, gid) pairs over all 32 bits,
+    I (tile id u16, instance) pairs over the id's bits. Measurement infrastructure only -- the product never loads it."""
+    import ctypes as C
+    lib = os.path.join(ROOT, "tools", "bin", "libcub_bar.so")
+    if not os.path.exists(lib):
+        return {"unavailable": "tools/bin/libcub_bar.so not built"}
+    try:
+        cub = C.CDLL(lib)
+        cub.cub_sort_pairs.restype = C.c_int
+        cub.cub_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_int, C.POINTER(C.c_float)]
+        rng = np.random.default_rng(0)
+        out = {}
+        depth = rng.uniform(2.0, 20.0, V).astype(np.float32)
+        k32 = torch.from_numpy((depth.view(np.uint32) | np.uint32(0x80000000)).view(np.int32)).cuda()
+        k16 = torch.from_numpy(rng.integers(0, T, I, dtype=np.int64).astype(np.int16)).cuda()
+        tile_bits = max(1, int(T - 1).bit_length())
+        for name, keys, bits, end_bit, ours in (("depthSort", k32, 32, 32, stage_ms.get("depthSort")),
+                                                ("tileSort", k16, 16, tile_bits, stage_ms.get("tileSort", 0.0) + stage_ms.get("ranges", 0.0))):
+            vals = torch.arange(keys.numel(), dtype=torch.int32, device="cuda")
+            ko, vo, ms = torch.empty_like(keys), torch.empty_like(vals), C.c_float(0)
+            rc = cub.cub_sort_pairs(keys.data_ptr(), vals.data_ptr(), ko.data_ptr(), vo.data_ptr(), keys.numel(), bits, 0, end_bit,
+                                    torch.cuda.current_stream().cuda_stream, 20, C.byref(ms))
+            if rc != 0:
+                return {"unavailable": f"cub_sort_pairs rc {rc}"}
+            out[name] = {"pairs": int(keys.numel()), "cub_us": ms.value * 1e3, "ours_us": None if ours is None else ours * 1e3,
+                         "end_bit": end_bit}
+        out["note"] = ("cub::DeviceRadixSort::SortPairs alone on resident arrays (L2 warm, 20 repetitions) vs this frame's stage times "
+                       "(tileSort includes the tile ranges, which the MSD tile sort writes itself); cub sorts only the id's significant bits")
+        return out
+    except Exception as e:  # measurement extra: never fail the bench line
+        return {"unavailable": repr(e)}
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host cores (CPU port; Metal cannot run here)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -510,6 +546,7 @@ def main():
                     "pipes": pipes, "pipes_source": pipes_src}
     roofline["sort_stages_hbm_frac"] = {x["stage"]: x["frac"] for x in stage_roofline if x["stage"] in ("depthSort", "tileSort")}
     sort_blend_ms = stage_ms.get("tileSort", 0) + stage_ms.get("ranges", 0) + stage_ms.get("blend", 0)
+    library_bar = library_sort_bar(torch, V, I, T, stage_ms)
 
     # ---- CPU baseline (bounded sample: whole frames of the same workload on this box's cores)
     cpu_baseline = None
@@ -540,6 +577,7 @@ def main():
         "stage_ms": stage_ms,
         "roofline": roofline,
         "stage_roofline": stage_roofline,
+        "library_bar": library_bar,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h * world,
                 "steps": e2e_steps, "matches_device_path": same, "frames_in_flight": 2,

@@ -365,7 +365,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     if (msdTiles)
         GSM_CUDA(launchTileLocalSort(s, res.tileIds[1], (const uint32_t*)res.instIdx[1], res.tileIds[0], (uint32_t*)res.instIdx[0],
                                      &res.fs->hist[4][0], res.header, res.maxInstances, lowBits, tilesX * tilesY, res.lowerBounds,
-                                     res.tileSortStatus + (size_t)res.tileTilesCap * 256u),
+                                     res.tileSortStatus + (size_t)res.tileTilesCap * 256u, r->numSMs),
                  "tile sort (local pass)");
     recordStage(r, s, 5);
     // stage 7

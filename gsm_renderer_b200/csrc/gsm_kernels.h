@@ -101,7 +101,7 @@ cudaError_t launchCreateInstances(cudaStream_t s, bool stereo, bool tileId16, co
 uint32_t tileSortLowBits(uint32_t tileCount);
 cudaError_t launchTileLocalSort(cudaStream_t s, const void* keysIn, const uint32_t* valsIn, void* keysOut, uint32_t* valsOut,
                                 const uint32_t* bucketHist, const GSMDepthFirstHeader* header, uint32_t capInstances, uint32_t lowBits,
-                                uint32_t tileCount, uint32_t* lowerBounds, uint32_t* chunkCounts);
+                                uint32_t tileCount, uint32_t* lowerBounds, uint32_t* chunkCounts, int numSMs);
 // chunkCounts: (capInstances / 4096 + 257) rows of 2^lowBits words of scratch
 
 // tile ranges (ranges.cu)

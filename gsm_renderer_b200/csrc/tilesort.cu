@@ -195,10 +195,9 @@ __global__ void __launch_bounds__(kTlThreads, 4) tile_chunk_count_kernel(const u
     pdlLaunchDependents();
     for (uint32_t i = tid; i < kTlWarps * bins; i += kTlThreads) sh.rows[i >> lowBits][i & (bins - 1u)] = 0u;
     pdlWait();
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= min(ldAfterWait(&header->totalInstances), capInstances) / kTlChunk + 257u) return;   // bound on the chunk count
+    if (blockIdx.x >= min(ldAfterWait(&header->totalInstances), capInstances) / kTlChunk + 257u) return;   // bound on the chunk count
     const uint32_t totalChunks = numberChunks(bucketHist, sh);
-    if (chunk >= totalChunks) return;
+    for (uint32_t chunk = blockIdx.x; chunk < totalChunks; chunk += gridDim.x) {
     const uint32_t b = bucketOfChunk(chunk, sh);
     const uint32_t c = chunk - sh.chunkBase[b];
     const uint32_t bucketBase = sh.bucketStart[b], bucketN = sh.bucketStart[b + 1] - bucketBase;
@@ -220,6 +219,12 @@ __global__ void __launch_bounds__(kTlThreads, 4) tile_chunk_count_kernel(const u
         for (int w = 0; w < kTlWarps; ++w) cnt += sh.rows[w][tid];
         chunkCounts[(size_t)chunk * bins + tid] = cnt;
     }
+    if (chunk + gridDim.x < totalChunks) {   // frames beyond one chunk per CTA
+        __syncthreads();
+        for (uint32_t i = tid; i < kTlWarps * bins; i += kTlThreads) sh.rows[i >> lowBits][i & (bins - 1u)] = 0u;
+        __syncthreads();
+    }
+    }
 }
 
 // PLACE: one CTA per chunk -- per tile of the bucket, ids in all its chunks (-> tile offsets, the tile ranges) and in the chunks
@@ -235,17 +240,16 @@ __global__ void __launch_bounds__(kTlThreads, 2) tile_chunk_place_kernel(const u
     pdlLaunchDependents();
     for (uint32_t i = tid; i < kTlWarps * bins; i += kTlThreads) sh.rows[i >> lowBits][i & (bins - 1u)] = 0u;
     pdlWait();
-    const uint32_t chunk = blockIdx.x;
     const uint32_t total = min(ldAfterWait(&header->totalInstances), capInstances);
-    if (chunk >= total / kTlChunk + 257u && chunk >= 256u) return;   // bound on the chunk count; CTAs 0..255 also own a bucket's empty case
+    if (blockIdx.x >= total / kTlChunk + 257u && blockIdx.x >= 256u) return;   // bound on the chunk count; CTAs 0..255 also own a bucket's empty case
     const uint32_t totalChunks = numberChunks(bucketHist, sh);
-    // tiles of EMPTY buckets have no chunk to write their (empty) range: CTA b < 256 does it for bucket b
-    if (chunk < 256u && sh.bucketStart[chunk + 1] == sh.bucketStart[chunk]) {
-        const uint32_t t = (chunk << lowBits) + tid;
-        if (tid < bins && t < tileCount) lowerBounds[t] = sh.bucketStart[chunk];
+    // tiles of EMPTY buckets have no chunk to write their (empty) range: CTA b < 256 does it for bucket b (the grid has >= 256 CTAs)
+    if (blockIdx.x < 256u && sh.bucketStart[blockIdx.x + 1] == sh.bucketStart[blockIdx.x]) {
+        const uint32_t t = (blockIdx.x << lowBits) + tid;
+        if (tid < bins && t < tileCount) lowerBounds[t] = sh.bucketStart[blockIdx.x];
     }
-    if (chunk == 0u && tid == 0) lowerBounds[tileCount] = total;
-    if (chunk >= totalChunks) return;
+    if (blockIdx.x == 0u && tid == 0) lowerBounds[tileCount] = total;
+    for (uint32_t chunk = blockIdx.x; chunk < totalChunks; chunk += gridDim.x) {
     const uint32_t b = bucketOfChunk(chunk, sh);
     const uint32_t c = chunk - sh.chunkBase[b];
     const uint32_t bucketBase = sh.bucketStart[b], bucketN = sh.bucketStart[b + 1] - bucketBase;
@@ -283,6 +287,12 @@ __global__ void __launch_bounds__(kTlThreads, 2) tile_chunk_place_kernel(const u
         case 7: placeChunk<7>(keysIn, valsIn, keysOut, valsOut, base, n, running, sh); break;
         default: placeChunk<8>(keysIn, valsIn, keysOut, valsOut, base, n, running, sh); break;
     }
+    if (chunk + gridDim.x < totalChunks) {   // frames beyond one chunk per CTA
+        __syncthreads();
+        for (uint32_t i = tid; i < kTlWarps * bins; i += kTlThreads) sh.rows[i >> lowBits][i & (bins - 1u)] = 0u;
+        __syncthreads();
+    }
+    }
 }
 
 // lowBits of the MSD tile sort for a frame of tileCount tiles: 0 = the id has at most 8 bits, the LSD pass alone sorts it
@@ -294,9 +304,11 @@ uint32_t tileSortLowBits(uint32_t tileCount) {
 
 cudaError_t launchTileLocalSort(cudaStream_t s, const void* keysIn, const uint32_t* valsIn, void* keysOut, uint32_t* valsOut,
                                 const uint32_t* bucketHist, const GSMDepthFirstHeader* header, uint32_t capInstances, uint32_t lowBits,
-                                uint32_t tileCount, uint32_t* lowerBounds, uint32_t* chunkCounts) {
+                                uint32_t tileCount, uint32_t* lowerBounds, uint32_t* chunkCounts, int numSMs) {
     // one CTA per chunk; the chunk count lives on the device, the grid covers its bound and the surplus CTAs return at once
-    const uint32_t grid = capInstances / kTlChunk + 257u;
+    uint32_t grid = capInstances / kTlChunk + 257u;
+    const uint32_t persistent = (uint32_t)numSMs * 8u;   // larger frames: every CTA loops over chunks (>= 256 CTAs: the empty-bucket ranges)
+    if (grid > persistent) grid = persistent;
     launchChained(tile_chunk_count_kernel, (int)grid, kTlThreads, s, (const unsigned short*)keysIn, bucketHist, header, capInstances, lowBits,
                   chunkCounts);
     launchChained(tile_chunk_place_kernel, (int)grid, kTlThreads, s, (const unsigned short*)keysIn, valsIn, (unsigned short*)keysOut,
