@@ -52,7 +52,7 @@ WORKLOADS = {
     "C5v": (3_000_000, 3, "float16", 1280, 720, 0.012, "C5 (one view): 3M Gaussians SH3 float16, 1280x720"),
 }
 NEAR, FAR = 0.1, 100.0  # PLYBenchmarkTests.swift:60-62
-KERNELS_PER_FRAME = 11  # project, compaction (+header), 4 depth + 2 tile onesweep passes, scan+expand, ranges, blend
+KERNELS_PER_FRAME = 9   # project, compaction (+header), depth bucket scatter + local sort, scan+expand, one tile onesweep pass + chunk count + chunk place (writes the ranges), blend
 
 
 def measured_peaks():
@@ -518,8 +518,13 @@ def main():
     Vp = V  # Gaussians reaching the SH fetch >= V; the (9) exit after the fetch is rare. Lower bound used.
     sb = stage_bytes(N, V, Vp, I, T, W * H, 32 if prec == "float16" else 48, 3 * K * (2 if prec == "float16" else 4))
     stage_roofline = []
-    for k in ("project", "depthSort", "expand", "tileSort", "ranges", "blend"):
-        ms = stage_ms.get(k, 0.0) + (stage_ms.get("applyScan", 0.0) if k == "expand" else 0.0)  # the scan runs inside the expansion kernel
+    # stage intervals with no kernel of their own are folded into the stage that does their work, bytes and time alike: the scan
+    # runs inside the expansion kernel, the tile ranges are written by the tile sort's place kernel
+    fold = {"expand": "applyScan", "tileSort": "ranges"}
+    sb = dict(sb)
+    sb["tileSort"] += sb.pop("ranges")
+    for k in ("project", "depthSort", "expand", "tileSort", "blend"):
+        ms = stage_ms.get(k, 0.0) + stage_ms.get(fold.get(k, ""), 0.0)
         gbs = sb[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stage_roofline.append({"stage": k, "ms": ms, "bytes": int(sb[k]), "GBps": gbs, "frac": gbs / peak})
     dom = max(stage_roofline, key=lambda s: s["ms"])

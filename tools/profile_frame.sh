@@ -4,12 +4,14 @@
 set -u
 TAG=${1:-rX}
 OUT=gpurun_out
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-modes"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_ncu_launch.log 2>&1
-# a warm frame: skip the first 3 frames (11 kernels each: 5 stage kernels + 4 depth + 2 tile sort passes)
-SKIP=33
+# a warm frame: skip the first 3 frames (9 kernels each since round 2: project, compaction, depth bucket scatter + local sort,
+# expansion, one tile-sort pass, tile chunk count + place, blend)
+KPF=${KPF:-9}
+SKIP=$((3 * KPF))
 N=$(grep -c "project_cull_mono_kernel" $OUT/${TAG}_launches.csv)
-ncu --set full --import-source on --clock-control none -k regex:"project_cull|compact_visible|onesweep_pass|create_instances|tile_lower_bounds|blend_mono" \
-    --launch-skip $SKIP -c 11 -o $OUT/${TAG}_frame $BENCH > $OUT/${TAG}_ncu_full.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"project_cull|compact_visible|onesweep_pass|bucket_scatter|bucket_local_sort|create_instances|tile_chunk|tile_lower_bounds|blend_mono" \
+    --launch-skip $SKIP -c $KPF -o $OUT/${TAG}_frame $BENCH > $OUT/${TAG}_ncu_full.log 2>&1
 echo "launch list rows: $N, skipped $SKIP"
 ls -la $OUT/${TAG}_frame.ncu-rep
