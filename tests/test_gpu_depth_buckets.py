@@ -1,4 +1,4 @@
-"""The depth sort's bucket path (csrc/bucketsort.cu) on the key distributions that leave its fast path: every white-box buffer
+"""The round-2 sorts on the inputs that leave their fast paths. Depth sort's bucket path (csrc/bucketsort.cu): every white-box buffer
 and every pixel against the oracle, whose depth sort is the reference's four 8-bit LSD passes (DFS.metal:1387-1696).
 
  * thousands of Gaussians inside ONE fine bin of the key histogram (a thin slab, with two outliers stretching the key range):
@@ -105,4 +105,43 @@ def test_bucket_path_equals_lsd_path_gpu(tmp_path):
         out[mode] = np.load(f)
     assert int(out["1"]["plan"][0]) > 50 and int(out["0"]["plan"][0]) == 0   # the two runs really took different paths
     for k in ("c", "d", "keys", "idx", "off", "inst"):
+        assert np.array_equal(out["1"][k], out["0"][k]), k
+
+
+# ---- tile sort, most-significant digit first (csrc/tilesort.cu): every low-bit width L = bits(tileCount - 1) - 8
+@pytest.mark.parametrize("W,H", [(320, 400),      # 20 x 25 = 500 tiles, L = 1
+                                 (512, 512),      # 1024 tiles, L = 2 (ids use exactly 10 bits)
+                                 (720, 720),      # 2025 tiles, L = 3
+                                 (1280, 720),     # 3600 tiles, L = 4
+                                 (2560, 1440),    # 14400 tiles, L = 6
+                                 (3840, 2160),    # 32400 tiles, L = 7
+                                 (4096, 4080),    # 65280 tiles, L = 8 (the largest count 16-bit ids allow is 65535)
+                                 (257 * 16, 16),  # 257 tiles in one row, L = 1: a bucket of one tile at the end
+                                 (4110, 17)])     # 257 x 2 tiles through the odd-size path
+def test_tile_sort_low_bit_widths_gpu(oracle, pu, W, H):
+    cl = syn.synthetic_cloud(30_000, 1, seed=W + H, scale_median=0.02)
+    res = pu.run_mono_case(oracle, cl, "float16", W, H)
+    assert res["I"] >= res["V"] > 0
+
+
+def test_tile_msd_equals_lsd_path_gpu(tmp_path):
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "import tests.parity_util as pu\n"
+        "from gsm_renderer_b200 import synthetic as syn\n"
+        "cl = syn.synthetic_cloud(400_000, 2, seed=13, scale_median=0.02)\n"
+        "g, h = pu.make_scene_inputs(cl, 'float16')\n"
+        "cam = pu.default_camera(1920, 1080)\n"
+        "r, c, d = pu.gpu_mono(g, h, 'float16', cam, 1920, 1080, cl.sh_components, cl.count, False)\n"
+        "hd = r.debugReadHeader()\n"
+        "np.savez(sys.argv[1], c=c, d=d, ids=r.debugReadSortedTileIds(hd.totalInstances), inst=r.debugReadInstanceGaussianIndices(hd.totalInstances),\n"
+        "         th=r.debugReadTileHeaders(120 * 68))\n"
+        "r.close()\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = {}
+    for mode in ("1", "0"):
+        f = str(tmp_path / f"frame{mode}.npz")
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, GSM_TILE_MSD=mode), timeout=300)
+        out[mode] = np.load(f)
+    for k in ("c", "d", "ids", "inst", "th"):
         assert np.array_equal(out["1"][k], out["0"][k]), k
