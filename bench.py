@@ -52,7 +52,7 @@ WORKLOADS = {
     "C5v": (3_000_000, 3, "float16", 1280, 720, 0.012, "C5 (one view): 3M Gaussians SH3 float16, 1280x720"),
 }
 NEAR, FAR = 0.1, 100.0  # PLYBenchmarkTests.swift:60-62
-KERNELS_PER_FRAME = 9   # project, compaction (+header), depth bucket scatter + local sort, scan+expand, one tile onesweep pass + chunk count + chunk place (writes the ranges), blend
+KERNELS_PER_FRAME = 10  # project, compaction (+header), depth bucket rank + scatter + local sort, scan+expand, one tile onesweep pass + chunk count + chunk place (writes the ranges), blend
 
 
 def measured_peaks():

@@ -4,14 +4,16 @@
 // (depthSort* DFS.metal:1387-1696, DepthRadixSortEncoder.swift:139-217). Any stable ascending sort yields the same
 // arrays bit for bit, so at frame size -- where an LSD pass costs ~14 us of fixed latency however few keys it moves
 // (profiles/README.md, sort_trace) -- frames of up to kDepthBucketMaxGaussians Gaussians replace the four passes by:
-//   1. bucket_scatter_kernel: a stable scatter of (key, gid) into up to 512 BUCKETS of consecutive key ranges holding ~2048
-//      keys each. The bucket boundaries adapt to the depth distribution: the projection kernel recorded the frame's key
-//      range, the compaction kernel counted every 8th stored key into an 8192-bin histogram over that range, and every CTA
-//      here turns that sample into the same bin -> bucket table (in shared memory, under its key loads).
-//      Mechanically this is an Onesweep pass whose "digit" is the bucket id: ranking in index order with 9 ballots per key,
-//      per-tile counts published once; every tile is in flight at once (one tile per CTA), waits for all of them and sums
-//      both its predecessors' counts and the bucket totals, i.e. the exact bucket offsets (nothing depends on the sample
-//      being representative).
+//   1. bucket_rank_kernel + bucket_scatter_kernel: a stable scatter of (key, gid) into up to 512 BUCKETS of consecutive key
+//      ranges holding ~2048 keys each. The bucket boundaries adapt to the depth distribution: the projection kernel recorded the
+//      frame's key range, the compaction kernel counted every 8th stored key into an 8192-bin histogram over that range, and
+//      every CTA of the rank kernel turns that sample into the same bin -> bucket table (in shared memory, under its key loads).
+//      Mechanically this is an Onesweep pass whose "digit" is the bucket id, cut in two at its only global dependency: the rank
+//      kernel ranks a tile in index order (9 ballots per key), stores every key's bucket and tile-local position and publishes
+//      the tile's bucket counts; the scatter kernel, one kernel boundary later, sums its predecessors' counts AND the bucket
+//      totals -- the exact offsets, nothing depends on the sample being representative -- stages the tile in bucket order
+//      and writes it out. (As ONE kernel every tile had to wait for every other tile's counts: that needs all tiles' CTAs
+//      resident together, which two frames in flight on two streams can deny each other forever.)
 //   2. bucket_local_sort_kernel: one CTA per bucket, in shared memory. (key, position) pairs are unique, so ANY sort of the
 //      pairs is the stable sort of the keys: the bucket is split into 1024 bins by the top bits of key - bucketMin with one
 //      shared-memory atomic per element, then every element is placed by counting the smaller pairs of its own bin (two or
@@ -139,35 +141,28 @@ __device__ __forceinline__ void scanSampleCounts(ScatterShared& sh) {   // after
     __syncthreads();
 }
 
+// Kernel 1a: bucket and final tile-local position of every key of the tile, the tile's bucket counts published.
 template <int ITEMS>
-__device__ __forceinline__ void bucketScatterTile(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
-                                                  uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t count,
-                                                  const uint32_t* __restrict__ fineHist, const KeyRange* keyRange,
-                                                  DepthPlan* __restrict__ plan, uint32_t* status, uint32_t* gstatus, ScatterShared& sh) {
+__device__ __forceinline__ void bucketRankTile(const uint32_t* __restrict__ keysIn, uint32_t count, const uint32_t* __restrict__ fineHist,
+                                               const KeyRange* keyRange, DepthPlan* __restrict__ plan, uint32_t* status, uint32_t* gstatus,
+                                               uint32_t* __restrict__ place, ScatterShared& sh) {
     constexpr uint32_t TILE = kBkThreads * ITEMS;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t numTiles = (count + TILE - 1u) / TILE;
     const uint32_t tile = blockIdx.x;
     if (tile >= numTiles) return;
-    const uint32_t numGroups = (numTiles + kBkGroup - 1u) / kBkGroup;   // <= 32: one arrival mask per lane
-    uint32_t* arriveMask = gstatus + (size_t)numGroups * kBkBins;
     const uint32_t bin0 = 2u * tid;
     const uint32_t base = tile * TILE;
     const uint32_t tileValid = min(TILE, count - base);
 
     loadSampleCounts(fineHist, keyRange, sh);
     // warp-striped: element (warp, item, lane) has index base + warp*ITEMS*32 + item*32 + lane
-    uint32_t key[ITEMS], val[ITEMS], br[ITEMS];   // br: bucket in the high half, rank inside the bucket in the low half
+    uint32_t key[ITEMS], br[ITEMS];   // br: bucket in the high half, rank inside the bucket in the low half
     const uint32_t warpBase = warp * ITEMS * 32u + lane;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const uint32_t j = warpBase + i * 32u;
         key[i] = (j < tileValid) ? keysIn[base + j] : 0xFFFFFFFFu;
-    }
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const uint32_t j = warpBase + i * 32u;
-        val[i] = (j < tileValid) ? valsIn[base + j] : 0u;
     }
     scanSampleCounts(sh);   // under the loads just issued
     const uint32_t keyMin = sh.keyMin, fineShift = sh.fineShift;
@@ -192,32 +187,58 @@ __device__ __forceinline__ void bucketScatterTile(const uint32_t* __restrict__ k
     }
     uint2 validCount = binCount;
     if (tid == kBkThreads - 1) validCount.y -= TILE - tileValid;
-
-    // publish the counts once (a word per bin and a RED into the group's sums), set the arrival bit, wait for EVERY tile
-    const uint32_t group = tile / kBkGroup;
+    // publish the counts: a word per bin and a RED into the group's sums. Nobody waits inside this kernel: the scatter kernel
+    // reads them after the kernel boundary (an in-kernel "wait for every tile" needs every tile's CTA resident at once, which two
+    // frames on two streams can deny each other forever)
     {
+        const uint32_t group = tile / kBkGroup;
         uint32_t* myStatus = status + (size_t)tile * kBkBins + bin0;
         uint32_t* myGroup = gstatus + (size_t)group * kBkBins + bin0;
-        st_u64_relaxed(reinterpret_cast<unsigned long long*>(myStatus), ((unsigned long long)validCount.y << 32) | validCount.x);
+        *reinterpret_cast<uint2*>(myStatus) = validCount;
         if (validCount.x) atomicAdd(myGroup, validCount.x);   // RED
         if (validCount.y) atomicAdd(myGroup + 1, validCount.y);
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) atomicOr(arriveMask + group, 1u << (tile % kBkGroup));
-        if (tid < 32u) {
-            uint32_t need = 0u;
-            if (lane < numGroups) need = (lane + 1u) * kBkGroup <= numTiles ? 0xFFFFu : (1u << (numTiles - lane * kBkGroup)) - 1u;
-            bool ok;
-            do {
-                const uint32_t m = lane < numGroups ? ld_status32(arriveMask + lane) : 0u;
-                ok = (m & need) == need;
-            } while (!__all_sync(0xFFFFFFFFu, ok));
-            __threadfence();
-        }
-        __syncthreads();
+    }
+    uint32_t scanTotal;
+    const uint32_t pairExcl = blockExclusive(binCount.x + binCount.y, sh.scan, scanTotal);
+    sh.binExcl[bin0] = pairExcl;
+    sh.binExcl[bin0 + 1] = pairExcl + binCount.x;
+    if (tile == 0u && tid == 0) { plan->numBuckets = sh.numBuckets; plan->keyMin = keyMin; plan->shift = fineShift; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t j = warpBase + i * 32u;
+        const uint32_t b = br[i] >> 16;
+        const uint32_t p = (br[i] & 0xFFFFu) + sh.binExcl[b] + sh.warpHist[warp][b];  // position inside the tile
+        if (j < tileValid) place[base + j] = (b << 16) | p;
+    }
+}
+
+// Kernel 1b: every count is published (kernel boundary): sum the predecessors' counts and the bucket totals, stage the tile in
+// bucket order, write it out. No ballots, no waiting.
+template <int ITEMS>
+__device__ __forceinline__ void bucketScatterTile(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                  uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, uint32_t count,
+                                                  DepthPlan* __restrict__ plan, const uint32_t* status, const uint32_t* gstatus,
+                                                  const uint32_t* __restrict__ place, ScatterShared& sh) {
+    constexpr uint32_t TILE = kBkThreads * ITEMS;
+    const unsigned tid = threadIdx.x;
+    const uint32_t numTiles = (count + TILE - 1u) / TILE;
+    const uint32_t tile = blockIdx.x;
+    if (tile >= numTiles) return;
+    const uint32_t numGroups = (numTiles + kBkGroup - 1u) / kBkGroup;
+    const uint32_t bin0 = 2u * tid;
+    const uint32_t base = tile * TILE;
+    const uint32_t tileValid = min(TILE, count - base);
+    const uint32_t group = tile / kBkGroup;
+    uint32_t key[ITEMS], val[ITEMS], bp[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t j = tid + i * kBkThreads;
+        if (j < tileValid) { key[i] = keysIn[base + j]; val[i] = valsIn[base + j]; bp[i] = place[base + j]; }
     }
     uint2 exclusive = make_uint2(0u, 0u), totals = make_uint2(0u, 0u);
-    {   // all rows are published: issue every load of a batch before using any (15 tile rows + 16 + 12 group rows at most)
+    const uint2 mine = ld_status32x2(status + (size_t)tile * kBkBins + bin0);   // this tile's counts (padding not included)
+    {   // issue every load of a batch before using any (15 tile rows + 16 + 12 group rows at most)
         const uint32_t groupStart = group * kBkGroup, nPred = tile - groupStart;
         uint2 pv[kBkGroup];
 #pragma unroll
@@ -239,26 +260,24 @@ __device__ __forceinline__ void bucketScatterTile(const uint32_t* __restrict__ k
     }
     // one scan for both prefixes: bucket offsets over the frame (high 20 bits), bin offsets inside the tile (low 12 bits)
     uint32_t scanTotal;
-    const uint32_t packedExcl = blockExclusive(((totals.x + totals.y) << 12) | (binCount.x + binCount.y), sh.scan, scanTotal);
+    const uint32_t packedExcl = blockExclusive(((totals.x + totals.y) << 12) | (mine.x + mine.y), sh.scan, scanTotal);
     const uint32_t bucketStart = packedExcl >> 12, pairExcl = packedExcl & 0xFFFu;
     if (tile == 0u) {   // the local pass reads the bucket offsets from the plan
         plan->bucketStart[bin0] = bucketStart;
         plan->bucketStart[bin0 + 1] = bucketStart + totals.x;
-        if (tid == kBkThreads - 1) { plan->bucketStart[kBkBins] = count; plan->numBuckets = sh.numBuckets; plan->keyMin = keyMin; plan->shift = fineShift; }
+        if (tid == kBkThreads - 1) plan->bucketStart[kBkBins] = count;
     }
-    sh.binExcl[bin0] = pairExcl;
-    sh.binExcl[bin0 + 1] = pairExcl + binCount.x;
     sh.globalBase[bin0] = bucketStart + exclusive.x - pairExcl;
-    sh.globalBase[bin0 + 1] = bucketStart + totals.x + exclusive.y - (pairExcl + binCount.x);
-    __syncthreads();
-
+    sh.globalBase[bin0 + 1] = bucketStart + totals.x + exclusive.y - (pairExcl + mine.x);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const uint32_t b = br[i] >> 16;
-        const uint32_t p = (br[i] & 0xFFFFu) + sh.binExcl[b] + sh.warpHist[warp][b];  // position inside the tile
-        sh.u.stage.keys[p] = key[i];
-        sh.u.stage.vals[p] = val[i];
-        sh.bucket[p] = (unsigned short)b;
+        const uint32_t j = tid + i * kBkThreads;
+        if (j < tileValid) {
+            const uint32_t p = bp[i] & 0xFFFFu;
+            sh.u.stage.keys[p] = key[i];
+            sh.u.stage.vals[p] = val[i];
+            sh.bucket[p] = (unsigned short)(bp[i] >> 16);
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -272,11 +291,10 @@ __device__ __forceinline__ void bucketScatterTile(const uint32_t* __restrict__ k
     }
 }
 
-__global__ void __launch_bounds__(kBkThreads, 3) bucket_scatter_kernel(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
-                                                                       uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
-                                                                       const uint32_t* __restrict__ countPtr, uint32_t countCap,
-                                                                       const uint32_t* __restrict__ fineHist, const KeyRange* keyRange,
-                                                                       DepthPlan* __restrict__ plan, uint32_t* status, uint32_t* gstatus) {
+__global__ void __launch_bounds__(kBkThreads, 3) bucket_rank_kernel(const uint32_t* __restrict__ keysIn, const uint32_t* countPtr, uint32_t countCap,
+                                                                    const uint32_t* __restrict__ fineHist, const KeyRange* keyRange,
+                                                                    DepthPlan* __restrict__ plan, uint32_t* status, uint32_t* gstatus,
+                                                                    uint32_t* __restrict__ place) {
     __shared__ __align__(16) ScatterShared sh;
     const unsigned tid = threadIdx.x;
     pdlLaunchDependents();
@@ -289,9 +307,25 @@ __global__ void __launch_bounds__(kBkThreads, 3) bucket_scatter_kernel(const uin
     }
     __syncthreads();
     if (count <= gridDim.x * (uint32_t)kBkThreads * 8u)
-        bucketScatterTile<8>(keysIn, valsIn, keysOut, valsOut, count, fineHist, keyRange, plan, status, gstatus, sh);
+        bucketRankTile<8>(keysIn, count, fineHist, keyRange, plan, status, gstatus, place, sh);
     else   // the host routes frames here only while count <= gridDim.x * 2816 (bucketSortCovers)
-        bucketScatterTile<kScatterItemsMax>(keysIn, valsIn, keysOut, valsOut, count, fineHist, keyRange, plan, status, gstatus, sh);
+        bucketRankTile<kScatterItemsMax>(keysIn, count, fineHist, keyRange, plan, status, gstatus, place, sh);
+}
+
+__global__ void __launch_bounds__(kBkThreads, 3) bucket_scatter_kernel(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                                       uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
+                                                                       const uint32_t* countPtr, uint32_t countCap,
+                                                                       DepthPlan* __restrict__ plan, const uint32_t* status, const uint32_t* gstatus,
+                                                                       const uint32_t* __restrict__ place) {
+    __shared__ __align__(16) ScatterShared sh;
+    pdlLaunchDependents();
+    pdlWait();
+    const uint32_t count = min(ldAfterWait(countPtr), countCap);
+    if (count == 0u) return;
+    if (count <= gridDim.x * (uint32_t)kBkThreads * 8u)
+        bucketScatterTile<8>(keysIn, valsIn, keysOut, valsOut, count, plan, status, gstatus, place, sh);
+    else
+        bucketScatterTile<kScatterItemsMax>(keysIn, valsIn, keysOut, valsOut, count, plan, status, gstatus, place, sh);
 }
 
 // ---------------------------------------------------------------- pass 2: one CTA sorts one bucket
@@ -587,7 +621,7 @@ __global__ void __launch_bounds__(kLocalThreads, 3) bucket_local_sort_kernel(uin
 uint32_t bucketScatterGrid(int numSMs) {
     static int blocksPerSM = 0;
     if (blocksPerSM == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, bucket_scatter_kernel, kBkThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, bucket_rank_kernel, kBkThreads, 0);
         if (blocksPerSM < 1) blocksPerSM = 1;
         if (blocksPerSM > 3) blocksPerSM = 3;
     }
@@ -606,8 +640,10 @@ cudaError_t bucketSortPrepareDevice() {
 }
 
 cudaError_t launchBucketSort(cudaStream_t s, const BucketSortPlan& p) {
+    launchChained(bucket_rank_kernel, bucketScatterGrid(p.numSMs), kBkThreads, s, (const uint32_t*)p.k0, p.countPtr, p.countCap, p.fineHist,
+                  (const KeyRange*)p.keyRange, p.plan, p.status, p.gstatus, p.place);
     launchChained(bucket_scatter_kernel, bucketScatterGrid(p.numSMs), kBkThreads, s, (const uint32_t*)p.k0, (const uint32_t*)p.v0, p.k1, p.v1,
-                  p.countPtr, p.countCap, p.fineHist, (const KeyRange*)p.keyRange, p.plan, p.status, p.gstatus);
+                  p.countPtr, p.countCap, p.plan, (const uint32_t*)p.status, (const uint32_t*)p.gstatus, (const uint32_t*)p.place);
     launchChainedSmem(bucket_local_sort_kernel, (int)kDepthMaxBuckets, kLocalThreads, s, kLocalSmemBytes, p.k1, p.v1, p.k0, p.v0,
                       (const DepthPlan*)p.plan, p.keyRange, p.gatherSrc, p.gatherDst);
     return cudaGetLastError();

@@ -334,6 +334,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
         bp.countPtr = dp.countPtr; bp.countCap = dp.countCap; bp.plan = res.depthPlan; bp.fineHist = res.fs->fineHist; bp.keyRange = res.keyRange;
         bp.status = res.depthSortStatus; bp.gstatus = res.depthSortGStatus;
         bp.gatherSrc = dp.gatherSrc; bp.gatherDst = dp.gatherDst; bp.numSMs = r->numSMs;
+        bp.place = res.offsets;   // free until the local pass writes the depth-ordered tile counts into it
         GSM_CUDA(launchBucketSort(s, bp), "depth sort (buckets)");
     } else {
         GSM_CUDA(launchSort(s, dp), "depth sort");

@@ -81,6 +81,7 @@ struct BucketSortPlan {
     KeyRange* keyRange;   // cleared for the next frame
     uint32_t* status;     // >= tiles * 512 zeroed words (the LSD passes' status rows: a frame uses one path or the other)
     uint32_t* gstatus;    // >= groups * 512 + groups zeroed words
+    uint32_t* place;      // countCap words of scratch: bucket and tile-local position per key, between the rank and the scatter kernel
     const uint32_t* gatherSrc; uint32_t* gatherDst;
     int numSMs;
 };

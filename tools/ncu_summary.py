@@ -52,7 +52,7 @@ with open(f"profiles/{tag}_ncu_full_summary.csv", "w", newline="") as f:
 def stage_of(name):
     if "project_cull" in name or "compact_visible" in name:
         return "project"
-    if "onesweep_pass_kernel<unsigned int" in name or "bucket_scatter" in name or "bucket_local_sort" in name:
+    if "onesweep_pass_kernel<unsigned int" in name or "bucket_rank" in name or "bucket_scatter" in name or "bucket_local_sort" in name:
         return "depthSort"
     if "tile_chunk_count" in name or "tile_chunk_place" in name:
         return "tileSort"
