@@ -1279,3 +1279,257 @@ void gsmo_render_stereo(gsmo_frame* f, const void* gaussians, const void* harmon
     for (int i = 0; i < 9; ++i) f->stageSeconds[i] = t[i + 1] - t[i];
     f->stageSeconds[9] = t[9] - t[0];
 }
+
+/* ================================================================================================================
+ * GlobalRenderer: Sources/Renderer/GlobalRenderer/GlobalShaders.metal = "GS.metal",
+ * GlobalRenderer.swift = "GR.swift". Same shared helpers as the DepthFirst path (GShared.h); what differs:
+ *   - projection: ndcToScreenCentered, no far-plane exit, no tile count (GS.metal:19-125); 32 x 16 tiles;
+ *   - visibility = valid bounds (GS.metal:169-208); tiles by gaussianIntersectsTile on the quantised record with
+ *     opacity passed as the BYTE value (GS.metal:589-590: `float(g.opacity)` of a uchar, literal) -- two passes
+ *     (count, prefix sum, scatter: GS.metal:563-680);
+ *   - ONE sort of 32-bit keys [tile:16][half depth ^ 0x8000:16] (GS.metal:267-295; 3 or 4 stable LSD passes,
+ *     RadixSortEncoder.swift:52-63 == a stable sort by the whole key); headers by binary search (GS.metal:304-363);
+ *   - render: 8 x 8 threads of 4 x 2 pixels per 32 x 16 tile, early exit over the thread's eight pixels
+ *     (GS.metal:1036-1187); clear = (0,0,0,1), depth 0 (GS.metal:140-154).
+ * Tiles come from the renderer's LIMITS (maxWidth / maxHeight: GR.swift:26-49, RenderParams.width/height too), the
+ * camera from the frame's width / height. PARITY UNPINNED by the reference beyond the sort KATs
+ * (GlobalUnitTests.swift:23-176): its tests hold no other value and the Metal path cannot run here.
+ * ================================================================================================================ */
+static float gsmo_log2f_canonical(float x) { return gsmo_log(x) * 1.44269504088896341f; }
+
+/* GShared.h:595-597 */
+static float gaussianComputePower(float opacity) {
+    const float LN2 = 0.693147180559945f;
+    return LN2 * 8.0f + LN2 * gsmo_log2f_canonical(gsmo_fmax(opacity, 1e-6f));
+}
+/* GShared.h:599-604 */
+static int gaussianSegmentIntersectEllipse(float a, float b, float c, float d, float l, float r) {
+    float delta = b * b - 4.0f * a * c;
+    float t1 = (l - d) * (2.0f * a) + b;
+    float t2 = (r - d) * (2.0f * a) + b;
+    return delta >= 0.0f && (t1 <= 0.0f || t1 * t1 <= delta) && (t2 >= 0.0f || t2 * t2 <= delta);
+}
+/* GShared.h:606-645 */
+static int gaussianIntersectsTile(int minX, int minY, int maxX, int maxY, float cx, float cy, float conicX, float conicY,
+                                  float conicZ, float power) {
+    if (cx >= (float)minX && cx <= (float)maxX && cy >= (float)minY && cy <= (float)maxY) return 1;
+    float w = 2.0f * power;
+    float dx, dy, a, b, c;
+    if (cx * 2.0f < (float)(minX + maxX)) dx = cx - (float)minX; else dx = cx - (float)maxX;
+    a = conicZ;
+    b = -2.0f * conicY * dx;
+    c = conicX * dx * dx - w;
+    if (gaussianSegmentIntersectEllipse(a, b, c, cy, (float)minY, (float)maxY)) return 1;
+    if (cy * 2.0f < (float)(minY + maxY)) dy = cy - (float)minY; else dy = cy - (float)maxY;
+    a = conicX;
+    b = -2.0f * conicY * dy;
+    c = conicZ * dy * dy - w;
+    if (gaussianSegmentIntersectEllipse(a, b, c, cx, (float)minX, (float)maxX)) return 1;
+    return 0;
+}
+
+/* GS.metal:563-680: count (emit == 0) or scatter the tiles of one visible Gaussian */
+static uint32_t globalWalkTiles(const gsmo_render_data* g, const int32_t* rect, uint32_t tileW, uint32_t tileH, uint32_t tilesX,
+                                int emit, int32_t* tileIds, int32_t* tileIndices, uint32_t writePos, uint32_t maxAssignments,
+                                int32_t gaussianIdx) {
+    const int minTX = rect[0], maxTX = rect[1], minTY = rect[2], maxTY = rect[3];
+    if (minTX > maxTX || minTY > maxTY) return 0;
+    const float alpha = (float)g->opacity;   /* the byte value, literal (GS.metal:589) */
+    if (alpha < 1e-4f) return 0;
+    const float cx = gsmo_h2f(g->meanX), cy = gsmo_h2f(g->meanY);
+    const float theta = unpackThetaPi(g->theta);
+    float A, B, C;
+    conicFromThetaSigmas(theta, gsmo_h2f(g->sigma1), gsmo_h2f(g->sigma2), &A, &B, &C);
+    const float power = gaussianComputePower(alpha);
+    uint32_t n = 0;
+    for (int ty = minTY; ty <= maxTY; ++ty)
+        for (int tx = minTX; tx <= maxTX; ++tx) {
+            const int px0 = tx * (int)tileW, py0 = ty * (int)tileH;
+            if (gaussianIntersectsTile(px0, py0, px0 + (int)tileW - 1, py0 + (int)tileH - 1, cx, cy, A, B, C, power)) {
+                if (!emit) n++;
+                else if (writePos < maxAssignments) {
+                    tileIds[writePos] = ty * (int)tilesX + tx;
+                    tileIndices[writePos] = gaussianIdx;
+                    writePos++;
+                    n++;
+                }
+            }
+        }
+    return n;
+}
+
+void gsmo_render_global(const void* gaussians, const void* harmonics, int precision, const gsmo_camera* cam,
+                        uint32_t maxWidth, uint32_t maxHeight, uint32_t maxGaussians, uint32_t width, uint32_t height,
+                        gsmo_half* color, gsmo_half* depthOut, gsmo_render_data* renderData, int32_t* bounds, uint8_t* mask,
+                        uint32_t* visibleIndices, uint32_t* sortedKeys, int32_t* sortedIndices, gsmo_tile_header* headers,
+                        gsmo_global_info* info) {
+    const uint32_t tileW = 32, tileH = 16;
+    const uint32_t tilesX = (maxWidth + tileW - 1) / tileW, tilesY = (maxHeight + tileH - 1) / tileH;
+    const uint32_t tileCount = tilesX * tilesY > 0 ? tilesX * tilesY : 1;
+    const uint32_t maxAssignments = 4u * maxGaussians;   /* GlobalResources.swift:79-81 */
+    const float alphaThreshold = 0.005f, totalInkThreshold = 2.0f;   /* GR.swift:45-46 */
+    const uint32_t N = cam->gaussianCount;
+    memset(info, 0, sizeof *info);
+
+    /* GS.metal:19-125 */
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (uint32_t gid = 0; gid < N; ++gid) {
+        int32_t* rect = bounds + 4 * (size_t)gid;
+        mask[gid] = 0; rect[0] = 0; rect[1] = -1; rect[2] = 0; rect[3] = -1;
+        v3 position, scale; v4 rot; float opacity;
+        loadGaussian(gaussians, precision, gid, &position, &scale, &rot, &opacity);
+        float maxScale = gsmo_fmax(scale.x, gsmo_fmax(scale.y, scale.z));
+        if (maxScale < 0.0005f) continue;
+        v4 p4 = {position.x, position.y, position.z, 1.0f};
+        v4 viewPos4 = mul44(cam->view, p4);
+        v4 clip = mul44(cam->proj, viewPos4);
+        float depth = clip.w;
+        if (!(clip.w > cam->nearPlane)) continue;
+        float ndcX = clip.x / clip.w, ndcY = clip.y / clip.w;
+        float screenX = ((ndcX + 1.0f) * cam->width - 1.0f) * 0.5f;    /* ndcToScreenCentered, GShared.h:184-189 */
+        float screenY = ((ndcY + 1.0f) * cam->height - 1.0f) * 0.5f;
+        if (opacity < alphaThreshold) continue;
+        v4 quat = normalizeQuaternion(rot);
+        m3 cov3d = buildCovariance3D(scale, quat);
+        v3 viewPos = {viewPos4.x, viewPos4.y, viewPos4.z};
+        m2 cov2d = projectCovariance2D(cov3d, viewPos, cam->view, cam->proj, cam->width, cam->height);
+        cov2d = stabilizeCovariance2D(cov2d, cam->width, cam->height);
+        float theta, sigma1, sigma2;
+        if (!covarianceToThetaSigmas(cov2d, &theta, &sigma1, &sigma2)) continue;
+        float radius = 3.0f * gsmo_fmax(sigma1, sigma2);
+        if (radius < 0.5f) continue;
+        if (cullByTotalInkFromCov(opacity, cov2d, depth, cam->nearPlane, cam->farPlane, totalInkThreshold)) continue;
+        float obbX, obbY;
+        computeOBBExtents(cov2d, 3.0f, &obbX, &obbY);
+        if (screenX + obbX < 0.0f || screenX - obbX > cam->width || screenY + obbY < 0.0f || screenY - obbY > cam->height) continue;
+        v3 col = computeSHColor(harmonics, precision, gid, position, *(const v3*)cam->center, cam->shComponents);
+        col.x = gsmo_fmax(col.x + 0.5f, 0.0f); col.y = gsmo_fmax(col.y + 0.5f, 0.0f); col.z = gsmo_fmax(col.z + 0.5f, 0.0f);
+        if (cam->inputIsSRGB > 0.5f) { col.x = srgbToLinearChannel(col.x); col.y = srgbToLinearChannel(col.y); col.z = srgbToLinearChannel(col.z); }
+        gsmo_render_data rd;
+        rd.meanX = gsmo_f2h(screenX); rd.meanY = gsmo_f2h(screenY);
+        rd.theta = packThetaPi(theta);
+        rd.sigma1 = gsmo_f2h(sigma1); rd.sigma2 = gsmo_f2h(sigma2);
+        rd.depth = gsmo_f2h(depth);
+        rd.colorR = quantU8(col.x); rd.colorG = quantU8(col.y); rd.colorB = quantU8(col.z); rd.opacity = quantU8(opacity);
+        renderData[gid] = rd;
+        tile_bounds tb = computeTileBounds(screenX, screenY, obbX, obbY, cam->width, cam->height, (int)tileW, (int)tileH,
+                                           (int)tilesX, (int)tilesY);
+        rect[0] = tb.minTX; rect[1] = tb.maxTX; rect[2] = tb.minTY; rect[3] = tb.maxTY;
+        mask[gid] = 1;
+    }
+    /* GS.metal:169-208: visible = valid bounds, compacted in gid order */
+    uint32_t V = 0;
+    for (uint32_t gid = 0; gid < N; ++gid) {
+        const int32_t* r = bounds + 4 * (size_t)gid;
+        if (r[0] <= r[1] && r[2] <= r[3]) visibleIndices[V++] = gid;
+    }
+    info->visibleCount = V;
+    /* GS.metal:563-621 + prefix sum: offsets of the UNCLAMPED counts */
+    uint32_t* offsets = (uint32_t*)malloc(((size_t)V + 1) * sizeof(uint32_t));
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (uint32_t i = 0; i < V; ++i) {
+        const uint32_t g = visibleIndices[i];
+        offsets[i] = globalWalkTiles(&renderData[g], bounds + 4 * (size_t)g, tileW, tileH, tilesX, 0, NULL, NULL, 0, 0, 0);
+    }
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < V; ++i) { const uint32_t c = offsets[i]; offsets[i] = total; total += c; }
+    /* GS.metal:623-678: scatter, bounded by maxAssignments per store */
+    int32_t* tileIds = (int32_t*)malloc(((size_t)maxAssignments + 1) * sizeof(int32_t));
+    int32_t* tileIndices = (int32_t*)malloc(((size_t)maxAssignments + 1) * sizeof(int32_t));
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (uint32_t i = 0; i < V; ++i) {
+        const uint32_t g = visibleIndices[i];
+        globalWalkTiles(&renderData[g], bounds + 4 * (size_t)g, tileW, tileH, tilesX, 1, tileIds, tileIndices, offsets[i], maxAssignments,
+                        (int32_t)g);
+    }
+    free(offsets);
+    /* GS.metal:685-703: clamp, overflow flag, padded count */
+    if (total > maxAssignments) { total = maxAssignments; info->overflow = 1; }
+    info->totalAssignments = total;
+    info->paddedCount = ((total + 1023u) / 1024u) * 1024u;
+    /* GS.metal:267-295 */
+#pragma omp parallel for schedule(static)
+    for (uint32_t i = 0; i < total; ++i) {
+        const int32_t g = tileIndices[i];
+        const uint32_t depthBits = (uint32_t)gsmo_f2h(gsmo_h2f(renderData[g].depth)) ^ 0x8000u;
+        sortedKeys[i] = ((uint32_t)tileIds[i] << 16) | (depthBits & 0xFFFFu);
+        sortedIndices[i] = g;
+    }
+    free(tileIds); free(tileIndices);
+    gsmo_sort_pairs_u32(sortedKeys, sortedIndices, total, 4);
+    /* GS.metal:304-363 (the active list's order is the atomic's: here ascending tile) */
+    uint32_t* activeTiles = (uint32_t*)malloc((size_t)tileCount * sizeof(uint32_t));
+    uint32_t activeCount = 0, cursor = 0;
+    for (uint32_t t = 0; t < tileCount; ++t) {
+        while (cursor < total && (sortedKeys[cursor] >> 16) < t) cursor++;
+        uint32_t end = cursor;
+        while (end < total && (sortedKeys[end] >> 16) == t) end++;
+        headers[t].offset = total ? cursor : 0; headers[t].count = end - cursor;
+        if (end > cursor) activeTiles[activeCount++] = t;
+        cursor = end;
+    }
+    info->activeTileCount = activeCount;
+    /* GS.metal:140-154 */
+    gsmo_clear(color, depthOut, width, height);
+    /* GS.metal:1036-1187 */
+    const gsmo_half h255 = gsmo_f2h(255.0f);
+    const gsmo_half thr = gsmo_hdiv(H_ONE, h255);
+    const gsmo_half h099 = gsmo_f2h(0.99f);
+    const uint32_t W = maxWidth, Hh = maxHeight;   /* RenderParams.width / height are the limits (GR.swift:26-28) */
+#pragma omp parallel for schedule(dynamic, 2)
+    for (uint32_t ti = 0; ti < activeCount; ++ti) {
+        const uint32_t tile = activeTiles[ti];
+        const gsmo_tile_header hdr = headers[tile];
+        const uint32_t tileX = tile % tilesX, tileY = tile / tilesX;
+        for (uint32_t ly = 0; ly < 8; ++ly)
+            for (uint32_t lx = 0; lx < 8; ++lx) {
+                const uint32_t baseX = tileX * 32 + lx * 4, baseY = tileY * 16 + ly * 2;
+                /* pixel k = x + 4 * y of the thread's 4 x 2 block */
+                gsmo_half px[8], py[8], trans[8], col[8][3], dep[8];
+                for (int k = 0; k < 8; ++k) {
+                    px[k] = h_from_uint(baseX + (uint32_t)(k & 3));
+                    py[k] = h_from_uint(baseY + (uint32_t)(k >> 2));
+                    trans[k] = H_ONE; col[k][0] = col[k][1] = col[k][2] = H_ZERO; dep[k] = H_ZERO;
+                }
+                for (uint32_t i = 0; i < hdr.count; ++i) {
+                    gsmo_half m0 = gsmo_hmax(gsmo_hmax(trans[0], trans[1]), gsmo_hmax(trans[2], trans[3]));
+                    gsmo_half m1 = gsmo_hmax(gsmo_hmax(trans[4], trans[5]), gsmo_hmax(trans[6], trans[7]));
+                    if (h_lt(gsmo_hmax(m0, m1), thr)) break;
+                    const int32_t gi = sortedIndices[hdr.offset + i];
+                    if (gi < 0) continue;
+                    const gsmo_render_data g = renderData[gi];
+                    float A, B, C;
+                    conicFromThetaSigmas(unpackThetaPi(g.theta), gsmo_h2f(g.sigma1), gsmo_h2f(g.sigma2), &A, &B, &C);
+                    const gsmo_half cxx = gsmo_f2h(A), cyy = gsmo_f2h(C), cxy2 = gsmo_f2h(2.0f * B);
+                    const gsmo_half opacity = gsmo_hdiv(gsmo_f2h((float)g.opacity), h255);
+                    const gsmo_half gc[3] = {gsmo_hdiv(gsmo_f2h((float)g.colorR), h255), gsmo_hdiv(gsmo_f2h((float)g.colorG), h255),
+                                             gsmo_hdiv(gsmo_f2h((float)g.colorB), h255)};
+                    gsmo_half a[8];
+                    int allZero = 1;
+                    for (int k = 0; k < 8; ++k) {
+                        const gsmo_half dx = gsmo_hsub(px[k], g.meanX), dy = gsmo_hsub(py[k], g.meanY);
+                        const gsmo_half p = h_power(dx, dy, cxx, cyy, cxy2);
+                        a[k] = gsmo_hmin(gsmo_hmul(opacity, gsmo_hexp(gsmo_hmul(H_NEG_HALF, p))), h099);
+                        if (!h_eq0(a[k])) allZero = 0;
+                    }
+                    if (allZero) continue;
+                    for (int k = 0; k < 8; ++k) {
+                        const gsmo_half w = gsmo_hmul(a[k], trans[k]);
+                        for (int c = 0; c < 3; ++c) col[k][c] = h_mad(gc[c], w, col[k][c]);
+                        dep[k] = h_mad(g.depth, w, dep[k]);
+                    }
+                    for (int k = 0; k < 8; ++k) trans[k] = gsmo_hmul(trans[k], gsmo_hsub(H_ONE, a[k]));
+                }
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t x = baseX + (uint32_t)(k & 3), y = baseY + (uint32_t)(k >> 2);
+                    if (x < W && y < Hh && x < width && y < height) {   /* texture writes outside the target are dropped */
+                        const size_t o = (size_t)y * width + x;
+                        color[4 * o + 0] = col[k][0]; color[4 * o + 1] = col[k][1]; color[4 * o + 2] = col[k][2];
+                        color[4 * o + 3] = gsmo_hsub(H_ONE, trans[k]);
+                        if (depthOut) depthOut[o] = dep[k];
+                    }
+                }
+            }
+    }
+    free(activeTiles);
+}

@@ -245,6 +245,16 @@ void gsmo_render_stereo(gsmo_frame* f, const void* gaussians, const void* harmon
 void gsmo_set_blend_contraction(int on);
 int gsmo_get_blend_contraction(void);
 
+/* --- GlobalRenderer (GlobalShaders.metal, GlobalRenderer.swift): one whole frame with its white-box buffers.
+ * renderData / bounds / mask: per Gaussian (entries of culled Gaussians: mask 0, bounds (0,-1,0,-1), renderData untouched);
+ * visibleIndices: N; sortedKeys / sortedIndices: 4 * maxGaussians; headers: tiles of the LIMITS (32 x 16 px). */
+typedef struct { uint32_t totalAssignments, paddedCount, overflow, visibleCount, activeTileCount; } gsmo_global_info;
+void gsmo_render_global(const void* gaussians, const void* harmonics, int precision, const gsmo_camera* cam,
+                        uint32_t maxWidth, uint32_t maxHeight, uint32_t maxGaussians, uint32_t width, uint32_t height,
+                        gsmo_half* color, gsmo_half* depthOut, gsmo_render_data* renderData, int32_t* bounds, uint8_t* mask,
+                        uint32_t* visibleIndices, uint32_t* sortedKeys, int32_t* sortedIndices, gsmo_tile_header* headers,
+                        gsmo_global_info* info);
+
 #ifdef __cplusplus
 }
 #endif
