@@ -101,6 +101,9 @@ EXPORTS = {
     "gsm_get_stage_times_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gsm_stage_name": (C.c_char_p, [C.c_int]),
     "gsm_debug_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "gsm_render_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_uint32, C.c_uint32, C.POINTER(gsm_camera), C.c_uint32, C.c_uint32]),
+    "gsm_global_debug_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]),
     "gsm_debug_element_size": (C.c_size_t, [C.c_void_p, C.c_int]),
     "gsm_buffer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
     "gsm_buffer_free": (C.c_int, [C.c_void_p]),

@@ -499,6 +499,126 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
     if (tid == 0) publishTile(tout, tile, start, count);
 }
 
+// ---------------------------------------------------------------- GlobalRenderer: globalRender (GlobalShaders.metal:1036-1187)
+// One CTA per 32 x 16 tile of the LIMITS, 8 x 8 threads of 4 x 2 pixels; the clear (GlobalShaders.metal:140-154: colour
+// (0,0,0,1), depth 0) is fused: tiles without a list write it themselves. Same half arithmetic as the DepthFirst blend
+// (power / dhexp2_neghalf_packed / contracted accumulate); the early exit looks at the thread's eight pixels.
+struct GlobalStaged {
+    __half2 mean;            // meanX, meanY
+    __half2 cxx, cyy, cxy2;  // each broadcast to both halves
+    __half2 op, r, g, b, d;
+    uint32_t valid;
+};
+
+__global__ void __launch_bounds__(64) global_render_kernel(GlobalFrame f, uint32_t width, uint32_t height, uint32_t maxWidth,
+                                                           uint32_t maxHeight, __half* __restrict__ color, __half* __restrict__ depth) {
+    __shared__ GlobalStaged s_sp[64];
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+    const GSMGaussianHeader hdr = f.tileHeaders[tile];
+    const uint32_t tileX = tile % f.tilesX, tileY = tile / f.tilesX;
+    const uint32_t baseX = tileX * 32u + (tid & 7u) * 4u, baseY = tileY * 16u + (tid >> 3) * 2u;
+    const __half2 one = h2(1.0f), zero = h2(0.0f), h099 = h2(0.99f);
+    const __half thr = __float2half_rn(1.0f / 255.0f);
+    const __half2 pxA = __halves2half2(__uint2half_rn(baseX), __uint2half_rn(baseX + 1u));
+    const __half2 pxB = __halves2half2(__uint2half_rn(baseX + 2u), __uint2half_rn(baseX + 3u));
+    const __half2 py0 = __half2half2(__uint2half_rn(baseY)), py1 = __half2half2(__uint2half_rn(baseY + 1u));
+    // pair k: 0 = row 0 (x0,x1), 1 = row 0 (x2,x3), 2 = row 1 (x0,x1), 3 = row 1 (x2,x3)
+    __half2 T[4] = {one, one, one, one}, R[4] = {zero, zero, zero, zero}, G[4] = {zero, zero, zero, zero},
+            B[4] = {zero, zero, zero, zero}, D[4] = {zero, zero, zero, zero};
+    bool done = false;
+    for (uint32_t c0 = 0; c0 < hdr.count; c0 += 64u) {
+        __syncthreads();
+        {
+            GlobalStaged sp;
+            sp.valid = 0u;
+            if (c0 + tid < hdr.count) {
+                const int32_t gi = f.sortedIndices[hdr.offset + c0 + tid];
+                if (gi >= 0) {
+                    const uint4 rd = f.renderData[gi];
+                    const float theta = (float)(rd.y & 0xFFFFu) * GSM_THETA_UNPACK;
+                    float sn, cs;
+                    dsincos(theta, sn, cs);
+                    const float sig1 = dmax(__half2float(__ushort_as_half((unsigned short)(rd.y >> 16))), 1e-4f);
+                    const float sig2 = dmax(__half2float(__ushort_as_half((unsigned short)(rd.z & 0xFFFFu))), 1e-4f);
+                    const float invVar1 = 1.0f / (sig1 * sig1), invVar2 = 1.0f / (sig2 * sig2);
+                    const float cc = cs * cs, ss = sn * sn, csn = cs * sn;
+                    const float A = cc * invVar1 + ss * invVar2, Bq = csn * (invVar1 - invVar2), C = ss * invVar1 + cc * invVar2;
+                    sp.mean = *reinterpret_cast<const __half2*>(&rd.x);
+                    sp.cxx = __half2half2(__float2half_rn(A));
+                    sp.cyy = __half2half2(__float2half_rn(C));
+                    sp.cxy2 = __half2half2(__float2half_rn(2.0f * Bq));
+                    sp.op = __half2half2(__float2half_rn((float)(rd.w >> 24) / 255.0f));
+                    sp.r = __half2half2(__float2half_rn((float)(rd.w & 0xFFu) / 255.0f));
+                    sp.g = __half2half2(__float2half_rn((float)((rd.w >> 8) & 0xFFu) / 255.0f));
+                    sp.b = __half2half2(__float2half_rn((float)((rd.w >> 16) & 0xFFu) / 255.0f));
+                    sp.d = __half2half2(__ushort_as_half((unsigned short)(rd.z >> 16)));
+                    sp.valid = 1u;
+                }
+            }
+            s_sp[tid] = sp;
+        }
+        __syncthreads();
+        if (!done) {
+            const uint32_t m = min(64u, hdr.count - c0);
+            for (uint32_t j = 0; j < m; ++j) {
+                {   // GlobalShaders.metal:1081-1084, before every list entry
+                    const __half2 mm = __hmax2(__hmax2(T[0], T[1]), __hmax2(T[2], T[3]));
+                    if (__hlt(__hmax(__low2half(mm), __high2half(mm)), thr)) { done = true; break; }
+                }
+                const GlobalStaged& sp = s_sp[j];
+                if (!sp.valid) continue;
+                const __half2 mx = __low2half2(sp.mean), my = __high2half2(sp.mean);
+                const __half2 dxA = __hsub2_rn(pxA, mx), dxB = __hsub2_rn(pxB, mx);
+                const __half2 dy0 = __hsub2_rn(py0, my), dy1 = __hsub2_rn(py1, my);
+                __half2 a[4];
+                a[0] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxA, dy0, sp.cxx, sp.cyy, sp.cxy2))), h099);
+                a[1] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxB, dy0, sp.cxx, sp.cyy, sp.cxy2))), h099);
+                a[2] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxA, dy1, sp.cxx, sp.cyy, sp.cxy2))), h099);
+                a[3] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxB, dy1, sp.cxx, sp.cyy, sp.cxy2))), h099);
+                if (((h2bits(a[0]) | h2bits(a[1]) | h2bits(a[2]) | h2bits(a[3])) & 0x7FFF7FFFu) == 0u) continue;   // all eight alphas are (+-)0
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __half2 w = __hmul2_rn(a[k], T[k]);
+                    R[k] = __hfma2(sp.r, w, R[k]);
+                    G[k] = __hfma2(sp.g, w, G[k]);
+                    B[k] = __hfma2(sp.b, w, B[k]);
+                    D[k] = __hfma2(sp.d, w, D[k]);
+                    T[k] = __hmul2_rn(T[k], __hsub2_rn(one, a[k]));
+                }
+            }
+        }
+        if (__syncthreads_and(done ? 1 : 0)) break;
+    }
+    const uint32_t W = min(width, maxWidth), H = min(height, maxHeight);   // texture writes outside the target are dropped
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = baseX + (uint32_t)(k & 1) * 2u, y = baseY + (uint32_t)(k >> 1);
+        if (y >= H) continue;
+        const __half2 al = hdr.count > 0u ? __hsub2_rn(one, T[k]) : one;
+        const size_t o = (size_t)y * width + x;
+        if (x < W) {
+            uint2 v;
+            v.x = h2bits(__halves2half2(__low2half(R[k]), __low2half(G[k])));
+            v.y = h2bits(__halves2half2(__low2half(B[k]), __low2half(al)));
+            *reinterpret_cast<uint2*>(color + 4 * o) = v;
+            if (depth) depth[o] = __low2half(D[k]);
+        }
+        if (x + 1u < W) {
+            uint2 v;
+            v.x = h2bits(__halves2half2(__high2half(R[k]), __high2half(G[k])));
+            v.y = h2bits(__halves2half2(__high2half(B[k]), __high2half(al)));
+            *reinterpret_cast<uint2*>(color + 4 * o + 4) = v;
+            if (depth) depth[o + 1] = __high2half(D[k]);
+        }
+    }
+}
+
+cudaError_t launchGlobalRender(cudaStream_t s, const GlobalFrame& f, uint32_t width, uint32_t height, uint32_t maxWidth, uint32_t maxHeight,
+                               __half* color, __half* depth) {
+    global_render_kernel<<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
+    return cudaGetLastError();
+}
+
 cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const BlendSplat* splats, const int32_t* instanceIdx,
                             uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY, uint32_t tileRowFirst,
                             uint32_t tileRowCount, __half* color, __half* depth, TileOut tout, const unsigned short* expTable,

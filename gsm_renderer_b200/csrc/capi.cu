@@ -162,6 +162,11 @@ struct gsm_renderer {
     float* rateTables = nullptr; size_t rateTableFloats = 0;
     uint8_t* srgbLut = nullptr;
     unsigned short* expTable = nullptr;  // exact exp(-0.5h * p) over the non-negative halfs, staged into shared memory by the mono blend
+    // GlobalRenderer path (gsm_render_global): its own arena, allocated on the first global frame
+    char* globalArena = nullptr;
+    gsm::GlobalFrame globalFrame = {};
+    char* globalSortScratch = nullptr;   // sort state + ping-pong buffers (sortScratchLayout over 4 * maxGaussians pairs)
+    bool lastGlobal = false;
 };
 
 namespace gsm {
@@ -541,6 +546,7 @@ void gsm_renderer_destroy(gsm_renderer* r) {
     if (r->rateTables) cudaFree(r->rateTables);
     if (r->srgbLut) cudaFree(r->srgbLut);
     if (r->expTable) cudaFree(r->expTable);
+    if (r->globalArena) cudaFree(r->globalArena);
     delete r;
 }
 
@@ -1219,6 +1225,106 @@ gsm_status gsm_debug_read(gsm_renderer* r, void* stream, int which, void* dst, s
     cudaStream_t s = (cudaStream_t)stream;
     GSM_CUDA(cudaMemcpyAsync(dst, src + first * es, count * es, cudaMemcpyDeviceToHost, s), "debug read");
     GSM_CUDA(cudaStreamSynchronize(s), "debug read sync");
+    return GSM_OK;
+}
+
+// ---- GlobalRenderer (GlobalRenderer.swift:72-372): the same handle, limits and precision; 32 x 16 tiles of the LIMITS
+static gsm_status ensureGlobalResources(gsm_renderer* r) {
+    if (r->globalArena) return GSM_OK;
+    const gsm_config& c = r->cfg;
+    const uint32_t G = c.maxGaussians < 1 ? 1 : c.maxGaussians;
+    const uint32_t A = 4u * G;   // GlobalResources.swift:79-81
+    const uint32_t tileW = 32, tileH = 16;   // GlobalRenderer.swift:74-75
+    const uint32_t tilesX = (c.maxWidth + tileW - 1) / tileW, tilesY = (c.maxHeight + tileH - 1) / tileH;
+    const uint32_t T = tilesX * tilesY < 1 ? 1 : tilesX * tilesY;
+    if (T > 65536u) return fail(GSM_ERR_INVALID_TILE_COUNT, "GlobalRenderer sort keys hold 16 bits of tile id");
+    const SortScratchLayout L = sortScratchLayout(A, 32, 4);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = alignUp(off + bytes, 256); return o; };
+    const size_t oRender = take((size_t)G * 16), oBounds = take((size_t)G * 16), oFlags = take((size_t)G * 4), oFlagOff = take((size_t)G * 4);
+    const size_t oVisible = take((size_t)G * 4), oCounts = take((size_t)G * 4), oOffsets = take((size_t)G * 4);
+    const size_t oBlockSums = take(((size_t)G / 1024 + 8) * 4);
+    const size_t oKeys = take((size_t)A * 4), oIdx = take((size_t)A * 4);
+    const size_t oHeaders = take((size_t)T * 8), oActive = take((size_t)T * 4), oHeader = take(sizeof(GlobalHeader));
+    const size_t oSort = take(L.total);
+    cudaError_t e = cudaMalloc((void**)&r->globalArena, off);
+    if (e != cudaSuccess) { r->globalArena = nullptr; return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "GlobalRenderer arena", e); }
+    e = cudaMemset(r->globalArena, 0, off);
+    if (e != cudaSuccess) return fail(GSM_ERR_RENDER_FAILED, "GlobalRenderer arena memset", e);
+    char* a = r->globalArena;
+    GlobalFrame& f = r->globalFrame;
+    f.renderData = (uint4*)(a + oRender); f.bounds = (int4*)(a + oBounds); f.flags = (uint32_t*)(a + oFlags);
+    f.flagOffsets = (uint32_t*)(a + oFlagOff); f.visibleIndices = (uint32_t*)(a + oVisible); f.counts = (uint32_t*)(a + oCounts);
+    f.offsets = (uint32_t*)(a + oOffsets); f.blockSums = (uint32_t*)(a + oBlockSums); f.sortKeys = (uint32_t*)(a + oKeys);
+    f.sortedIndices = (int32_t*)(a + oIdx); f.tileHeaders = (GSMGaussianHeader*)(a + oHeaders); f.activeTiles = (uint32_t*)(a + oActive);
+    f.header = (GlobalHeader*)(a + oHeader);
+    f.capGaussians = G; f.maxAssignments = A; f.tileW = tileW; f.tileH = tileH; f.tilesX = tilesX; f.tilesY = tilesY;
+    r->globalSortScratch = a + oSort;
+    return GSM_OK;
+}
+
+gsm_status gsm_render_global(gsm_renderer* r, void* stream, void* color, void* depth, const void* gaussians, const void* harmonics,
+                             uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height) {
+    if (!r || !camera) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (gaussianCount > r->cfg.maxGaussians) return GSM_OK;   // validateLimits fails: the frame is not encoded (GlobalRenderer.swift:293-297)
+    gsm_status st = validateFrame(r, width, height, gaussians, harmonics, color);
+    if (st != GSM_OK) return st;
+    if (gaussianCount == 0) return GSM_OK;
+    DeviceGuard guard(r->device);
+    st = ensureGlobalResources(r);
+    if (st != GSM_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    const GlobalFrame& f = r->globalFrame;
+    r->lastGlobal = true;
+    MonoCam mc;
+    fillMonoCam(mc, camera, gaussianCount, shComponents, width, height, r->cfg.gaussianColorSpace == GSM_COLORSPACE_SRGB);
+    // 1. project + cull (+ visibility flags)  2. compaction in gid order  3. tiles per visible Gaussian  4. offsets + totals
+    // 5. scatter keys and indices  6. one stable sort of the 32-bit keys  7. tile headers + active list  8. clear + render
+    GSM_CUDA(launchGlobalProject(s, r->cfg.precision == GSM_PRECISION_FLOAT16, gaussians, harmonics, mc, f), "global project+cull");
+    GSM_CUDA(launchGlobalCompact(s, f, gaussianCount), "global visibility compaction");
+    GSM_CUDA(launchGlobalTileCount(s, f, gaussianCount), "global tile count");
+    GSM_CUDA(launchGlobalAssignOffsets(s, f, gaussianCount), "global assignment offsets");
+    GSM_CUDA(launchGlobalTileScatter(s, f, gaussianCount), "global tile scatter");
+    {
+        const SortScratchLayout L = sortScratchLayout(f.maxAssignments, 32, 4);
+        char* scratch = r->globalSortScratch;
+        GSM_CUDA(cudaMemsetAsync(scratch, 0, L.oK1, s), "global sort state memset");
+        SortPlan p;
+        p.k0 = f.sortKeys; p.k1 = scratch + L.oK1; p.v0 = (uint32_t*)f.sortedIndices; p.v1 = (uint32_t*)(scratch + L.oV1);
+        p.countPtr = &f.header->totalAssignments; p.countCap = f.maxAssignments;
+        p.hist = (uint32_t*)(scratch + L.oHist); p.status = (uint32_t*)(scratch + L.oStatus); p.gstatus = (uint32_t*)(scratch + L.oGStatus);
+        p.tickets = (uint32_t*)(scratch + L.oTickets);
+        p.tilesCap = L.tiles; p.keyBits = 32; p.numPasses = 4; p.numSMs = r->numSMs; p.histogramReady = false; p.largeTiles = L.large;
+        GSM_CUDA(launchSort(s, p), "global sort");   // RadixSortEncoder.swift:52-63 sorts 3 or 4 bytes: the same order
+    }
+    GSM_CUDA(launchGlobalHeaders(s, f), "global tile headers");
+    GSM_CUDA(launchGlobalRender(s, f, width, height, r->cfg.maxWidth, r->cfg.maxHeight, (__half*)color, (__half*)depth), "global render");
+    return GSM_OK;
+}
+
+gsm_status gsm_global_debug_read(gsm_renderer* r, void* stream, int which, void* dst, size_t first, size_t count) {
+    if (!r || !dst) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!r->globalArena) return fail(GSM_ERR_INVALID_ARGUMENT, "no global frame has been rendered");
+    DeviceGuard guard(r->device);
+    const GlobalFrame& f = r->globalFrame;
+    const char* src = nullptr;
+    size_t es = 0, cap = 0;
+    const size_t T = (size_t)f.tilesX * f.tilesY;
+    switch (which) {
+        case GSM_GDBG_HEADER: src = (const char*)f.header; es = sizeof(GlobalHeader); cap = 1; break;
+        case GSM_GDBG_SORTED_KEYS: src = (const char*)f.sortKeys; es = 4; cap = f.maxAssignments; break;
+        case GSM_GDBG_SORTED_INDICES: src = (const char*)f.sortedIndices; es = 4; cap = f.maxAssignments; break;
+        case GSM_GDBG_TILE_HEADERS: src = (const char*)f.tileHeaders; es = 8; cap = T; break;
+        case GSM_GDBG_BOUNDS: src = (const char*)f.bounds; es = 16; cap = f.capGaussians; break;
+        case GSM_GDBG_RENDER_DATA: src = (const char*)f.renderData; es = 16; cap = f.capGaussians; break;
+        case GSM_GDBG_VISIBLE_INDICES: src = (const char*)f.visibleIndices; es = 4; cap = f.capGaussians; break;
+        case GSM_GDBG_ACTIVE_TILES: src = (const char*)f.activeTiles; es = 4; cap = T; break;
+        default: return fail(GSM_ERR_INVALID_ARGUMENT, "unknown global debug buffer");
+    }
+    if (first > cap || count > cap - first) return fail(GSM_ERR_INVALID_ARGUMENT, "debug read out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    GSM_CUDA(cudaMemcpyAsync(dst, src + first * es, count * es, cudaMemcpyDeviceToHost, s), "global debug read");
+    GSM_CUDA(cudaStreamSynchronize(s), "global debug read sync");
     return GSM_OK;
 }
 

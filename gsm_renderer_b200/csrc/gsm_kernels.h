@@ -190,6 +190,36 @@ cudaError_t launchIngestRouted(cudaStream_t s, const IngestParams& P, const Proj
 cudaError_t launchGroupSignal(cudaStream_t s, GroupMailbox* to, uint32_t rank, uint32_t seq);
 cudaError_t launchGroupWait(cudaStream_t s, const GroupMailbox* mine, uint32_t mask, uint32_t seq);
 
+// ---- GlobalRenderer (global.cu + kernels next to the helpers they share in project.cu / blend.cu): GlobalShaders.metal on the
+// DepthFirst path's primitives. One arena per renderer; every count stays on the device.
+struct GlobalHeader {               // TileAssignmentHeader (BridgingTypes.h) + the frame's other device-side counts
+    uint32_t totalAssignments, paddedCount, overflow, visibleCount, activeTileCount, totalRaw, _pad[2];
+};
+struct GlobalFrame {
+    uint4* renderData;              // GSMGaussianRenderData per Gaussian
+    int4* bounds;
+    uint32_t* flags;                // 1 = valid bounds (markVisibilityKernel)
+    uint32_t* flagOffsets;          // exclusive prefix of flags
+    uint32_t* visibleIndices;
+    uint32_t* counts;               // tiles per visible Gaussian
+    uint32_t* offsets;              // exclusive prefix of counts (unclamped)
+    uint32_t* blockSums;            // scan scratch
+    uint32_t* sortKeys;             // [tile:16][half depth ^ 0x8000:16]
+    int32_t* sortedIndices;
+    GSMGaussianHeader* tileHeaders;
+    uint32_t* activeTiles;
+    GlobalHeader* header;
+    uint32_t capGaussians, maxAssignments, tileW, tileH, tilesX, tilesY;
+};
+cudaError_t launchGlobalProject(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam, const GlobalFrame& f);
+cudaError_t launchGlobalCompact(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);        // flags -> visibleIndices, visibleCount
+cudaError_t launchGlobalTileCount(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);
+cudaError_t launchGlobalAssignOffsets(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);  // counts -> offsets, header totals
+cudaError_t launchGlobalTileScatter(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);
+cudaError_t launchGlobalHeaders(cudaStream_t s, const GlobalFrame& f);
+cudaError_t launchGlobalRender(cudaStream_t s, const GlobalFrame& f, uint32_t width, uint32_t height, uint32_t maxWidth, uint32_t maxHeight,
+                               __half* color, __half* depth);
+
 // math probes (probe.cu)
 cudaError_t launchProbe(cudaStream_t s, int op, const void* a, const void* b, void* out, uint32_t n);
 

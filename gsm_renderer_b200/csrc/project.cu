@@ -831,6 +831,159 @@ cudaError_t launchCompactVisible(cudaStream_t s, uint32_t N, const ProjectOut& o
 
 const void* kernel_image_probe() { return (const void*)compact_visible_kernel; }
 
+// ---------------------------------------------------------------- GlobalRenderer
+// globalProjectCull (GlobalShaders.metal:19-125): the same shared helpers as the DepthFirst projection, but
+// ndcToScreenCentered, no far-plane exit, no tile count; 32 x 16-pixel tiles of the renderer's LIMITS.
+__device__ __forceinline__ TileBounds computeTileBoundsWH(float sx, float sy, float ex, float ey, float width, float height, int tileW,
+                                                          int tileH, int tilesX, int tilesY) {
+    TileBounds r;
+    float xmin = sx - ex, xmax = sx + ex, ymin = sy - ey, ymax = sy + ey;
+    float maxW = width - 1.0f, maxH = height - 1.0f;
+    xmin = dclamp(xmin, 0.0f, maxW);
+    xmax = dclamp(xmax, 0.0f, maxW);
+    ymin = dclamp(ymin, 0.0f, maxH);
+    ymax = dclamp(ymax, 0.0f, maxH);
+    r.minTX = (int)floorf(xmin / (float)tileW);
+    r.maxTX = (int)ceilf(xmax / (float)tileW) - 1;
+    r.minTY = (int)floorf(ymin / (float)tileH);
+    r.maxTY = (int)ceilf(ymax / (float)tileH) - 1;
+    r.minTX = max(r.minTX, 0);
+    r.minTY = max(r.minTY, 0);
+    r.maxTX = min(r.maxTX, tilesX - 1);
+    r.maxTY = min(r.maxTY, tilesY - 1);
+    r.valid = (r.minTX <= r.maxTX && r.minTY <= r.maxTY);
+    return r;
+}
+
+template <bool HALF, int DEG>
+__global__ void __launch_bounds__(kProjThreads) global_project_cull_kernel(const void* __restrict__ gaussians, const void* __restrict__ harmonics,
+                                                                           const __grid_constant__ MonoCam cam, GlobalFrame f) {
+    const uint32_t gid = blockIdx.x * kProjThreads + threadIdx.x;
+    if (gid >= cam.gaussianCount) return;
+    int4 rect = make_int4(0, -1, 0, -1);
+    do {
+        GaussianIn g = loadGaussian<HALF>(gaussians, gid);
+        float maxScale = dmax(g.scale.x, dmax(g.scale.y, g.scale.z));
+        if (maxScale < 0.0005f) break;
+        V4 viewPos4 = mul44(cam.view, V4{g.pos.x, g.pos.y, g.pos.z, 1.0f});
+        V4 clip = mul44(cam.proj, viewPos4);
+        float depth = clip.w;
+        if (!(clip.w > cam.nearPlane)) break;
+        float ndcX = clip.x / clip.w, ndcY = clip.y / clip.w;
+        float screenX = ((ndcX + 1.0f) * cam.width - 1.0f) * 0.5f;    // ndcToScreenCentered, GaussianShared.h:184-189
+        float screenY = ((ndcY + 1.0f) * cam.height - 1.0f) * 0.5f;
+        if (g.opacity < kAlphaThreshold) break;
+        V4 quat = normalizeQuaternion(g.rot);
+        M3 cov3d = buildCovariance3D(g.scale, quat);
+        M2 cov2d = projectCovariance2D(cov3d, V3{viewPos4.x, viewPos4.y, viewPos4.z}, cam.view, cam.proj, cam.width, cam.height);
+        cov2d = stabilizeCovariance2D(cov2d, cam.width, cam.height);
+        float theta, sigma1, sigma2;
+        if (!covarianceToThetaSigmas(cov2d, theta, sigma1, sigma2)) break;
+        if (3.0f * dmax(sigma1, sigma2) < 0.5f) break;
+        {
+            float a = cov2d.m00, b = 0.5f * (cov2d.m01 + cov2d.m10), d = cov2d.m11;
+            float detCov = a * d - b * b;
+            if (cullByTotalInk(g.opacity, detCov, depth, cam.nearPlane, cam.farPlane, kTotalInkThreshold)) break;
+        }
+        float obbX, obbY;
+        computeOBBExtents(cov2d, 3.0f, obbX, obbY);
+        if (screenX + obbX < 0.0f || screenX - obbX > cam.width || screenY + obbY < 0.0f || screenY - obbY > cam.height) break;
+        V3 color = computeSHColor<HALF, DEG>(harmonics, gid, g.pos, V3{cam.center[0], cam.center[1], cam.center[2]}, cam.shComponents);
+        color.x = dmax(color.x + 0.5f, 0.0f);
+        color.y = dmax(color.y + 0.5f, 0.0f);
+        color.z = dmax(color.z + 0.5f, 0.0f);
+        if (cam.inputIsSRGB > 0.5f) {
+            color.x = srgbToLinearChannel(color.x);
+            color.y = srgbToLinearChannel(color.y);
+            color.z = srgbToLinearChannel(color.z);
+        }
+        __half hMeanX = __float2half_rn(screenX), hMeanY = __float2half_rn(screenY);
+        uint16_t thetaP = packThetaPi(theta);
+        __half hS1 = __float2half_rn(sigma1), hS2 = __float2half_rn(sigma2), hDepth = __float2half_rn(depth);
+        uint4 rd;
+        rd.x = (uint32_t)__half_as_ushort(hMeanX) | ((uint32_t)__half_as_ushort(hMeanY) << 16);
+        rd.y = (uint32_t)thetaP | ((uint32_t)__half_as_ushort(hS1) << 16);
+        rd.z = (uint32_t)__half_as_ushort(hS2) | ((uint32_t)__half_as_ushort(hDepth) << 16);
+        rd.w = (uint32_t)quantU8(color.x) | ((uint32_t)quantU8(color.y) << 8) | ((uint32_t)quantU8(color.z) << 16) |
+               ((uint32_t)quantU8(g.opacity) << 24);
+        f.renderData[gid] = rd;
+        TileBounds tb = computeTileBoundsWH(screenX, screenY, obbX, obbY, cam.width, cam.height, (int)f.tileW, (int)f.tileH,
+                                            (int)f.tilesX, (int)f.tilesY);
+        rect = make_int4(tb.minTX, tb.maxTX, tb.minTY, tb.maxTY);
+    } while (false);
+    f.bounds[gid] = rect;
+    f.flags[gid] = (rect.x <= rect.y && rect.z <= rect.w) ? 1u : 0u;   // markVisibilityKernel, GlobalShaders.metal:169-181
+}
+
+// GaussianShared.h:595-645 -- gaussianComputePower / gaussianIntersectsTile, opacity passed as the BYTE value (GlobalShaders.metal:589)
+__device__ __forceinline__ bool globalSegmentHitsEllipse(float a, float b, float c, float d, float l, float r) {
+    float delta = b * b - 4.0f * a * c;
+    float t1 = (l - d) * (2.0f * a) + b;
+    float t2 = (r - d) * (2.0f * a) + b;
+    return delta >= 0.0f && (t1 <= 0.0f || t1 * t1 <= delta) && (t2 >= 0.0f || t2 * t2 <= delta);
+}
+__device__ __forceinline__ bool globalIntersectsTile(int minX, int minY, int maxX, int maxY, float cx, float cy, float conicX, float conicY,
+                                                     float conicZ, float power) {
+    if (cx >= (float)minX && cx <= (float)maxX && cy >= (float)minY && cy <= (float)maxY) return true;
+    float w = 2.0f * power;
+    float dx, dy, a, b, c;
+    if (cx * 2.0f < (float)(minX + maxX)) dx = cx - (float)minX; else dx = cx - (float)maxX;
+    a = conicZ;
+    b = -2.0f * conicY * dx;
+    c = conicX * dx * dx - w;
+    if (globalSegmentHitsEllipse(a, b, c, cy, (float)minY, (float)maxY)) return true;
+    if (cy * 2.0f < (float)(minY + maxY)) dy = cy - (float)minY; else dy = cy - (float)maxY;
+    a = conicX;
+    b = -2.0f * conicY * dy;
+    c = conicZ * dy * dy - w;
+    return globalSegmentHitsEllipse(a, b, c, cx, (float)minX, (float)maxX);
+}
+
+// tileCountIndirectKernel / tileScatterIndirectKernel + computeSortKeysKernel (GlobalShaders.metal:563-680, :267-295): EMIT false
+// counts the tiles of visible Gaussian i, EMIT true stores key [tile:16][half depth ^ 0x8000:16] and the Gaussian's index from
+// `writePos` on, bounded by maxAssignments per store. Returns the count.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t globalWalkTiles(const GlobalFrame& f, uint32_t g, uint32_t writePos) {
+    const int4 rect = f.bounds[g];
+    if (rect.x > rect.y || rect.z > rect.w) return 0u;
+    const uint4 rd = f.renderData[g];
+    const float alpha = (float)(rd.w >> 24);
+    if (alpha < 1e-4f) return 0u;
+    const float cx = __half2float(__ushort_as_half((unsigned short)(rd.x & 0xFFFFu)));
+    const float cy = __half2float(__ushort_as_half((unsigned short)(rd.x >> 16)));
+    const float theta = (float)(rd.y & 0xFFFFu) * GSM_THETA_UNPACK;
+    float A, B, C;
+    conicFromThetaSigmasF(theta, __half2float(__ushort_as_half((unsigned short)(rd.y >> 16))),
+                          __half2float(__ushort_as_half((unsigned short)(rd.z & 0xFFFFu))), A, B, C);
+    const float LN2 = 0.693147180559945f;
+    const float power = LN2 * 8.0f + LN2 * (dlog(dmax(alpha, 1e-6f)) * 1.44269504088896341f);
+    const uint32_t depthBits = ((rd.z >> 16) ^ 0x8000u) & 0xFFFFu;
+    uint32_t n = 0u;
+    for (int ty = rect.z; ty <= rect.w; ++ty)
+        for (int tx = rect.x; tx <= rect.y; ++tx) {
+            const int px0 = tx * (int)f.tileW, py0 = ty * (int)f.tileH;
+            if (globalIntersectsTile(px0, py0, px0 + (int)f.tileW - 1, py0 + (int)f.tileH - 1, cx, cy, A, B, C, power)) {
+                if (!EMIT) n++;
+                else if (writePos < f.maxAssignments) {
+                    f.sortKeys[writePos] = ((uint32_t)(ty * (int)f.tilesX + tx) << 16) | depthBits;
+                    f.sortedIndices[writePos] = (int32_t)g;
+                    writePos++;
+                    n++;
+                }
+            }
+        }
+    return n;
+}
+
+__global__ void __launch_bounds__(256) global_tile_count_kernel(GlobalFrame f) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < f.capGaussians) f.counts[i] = i < f.header->visibleCount ? globalWalkTiles<false>(f, f.visibleIndices[i], 0u) : 0u;
+}
+__global__ void __launch_bounds__(256) global_tile_scatter_kernel(GlobalFrame f) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < f.header->visibleCount) globalWalkTiles<true>(f, f.visibleIndices[i], f.offsets[i]);
+}
+
 // ---------------------------------------------------------------- launchers
 template <bool HALF>
 static cudaError_t launchMono(int deg, dim3 grid, cudaStream_t s, const void* g, const void* h, const MonoCam& cam,
@@ -869,5 +1022,23 @@ cudaError_t launchProjectStereo(cudaStream_t s, bool halfInput, const void* g, c
     dim3 grid((cam.gaussianCount + kProjThreads - 1) / kProjThreads);
     int deg = shDegreeFromComponents(cam.shComponents);
     return halfInput ? launchStereo<true>(deg, grid, s, g, h, cam, o) : launchStereo<false>(deg, grid, s, g, h, cam, o);
+}
+
+cudaError_t launchGlobalProject(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam, const GlobalFrame& f) {
+    const dim3 grid((cam.gaussianCount + kProjThreads - 1) / kProjThreads);
+    const int deg = shDegreeFromComponents(cam.shComponents);
+#define GSM_GP(H, D) global_project_cull_kernel<H, D><<<grid, kProjThreads, 0, s>>>(g, h, cam, f)
+    if (halfInput) { switch (deg) { case 0: GSM_GP(true, 0); break; case 1: GSM_GP(true, 1); break; case 2: GSM_GP(true, 2); break; default: GSM_GP(true, 3); } }
+    else { switch (deg) { case 0: GSM_GP(false, 0); break; case 1: GSM_GP(false, 1); break; case 2: GSM_GP(false, 2); break; default: GSM_GP(false, 3); } }
+#undef GSM_GP
+    return cudaGetLastError();
+}
+cudaError_t launchGlobalTileCount(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount) {
+    global_tile_count_kernel<<<(gaussianCount + 255u) / 256u, 256, 0, s>>>(f);
+    return cudaGetLastError();
+}
+cudaError_t launchGlobalTileScatter(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount) {
+    global_tile_scatter_kernel<<<(gaussianCount + 255u) / 256u, 256, 0, s>>>(f);
+    return cudaGetLastError();
 }
 }  // namespace gsm

@@ -463,3 +463,68 @@ def probe_math(op: int, a, b=None, device: int = -1) -> np.ndarray:
     bp = None if b is None else N.ptr(np.ascontiguousarray(b))
     _check(N.lib().gsm_probe_math(device, op, N.ptr(a), bp, N.ptr(out), n))
     return out
+
+
+class GlobalRenderer:
+    """GlobalRenderer (GlobalRenderer.swift:72): the reference's second renderer behind the same GaussianRenderer protocol --
+    32 x 16 tiles of the configured limits, one sort of 32-bit [tile:16][half depth:16] keys, 4 x 2 pixels per thread."""
+
+    maxSupportedGaussians = 30_000_000
+    tileWidth = 32
+    tileHeight = 16
+    _GDBG = dict(header=0, sortedKeys=1, sortedIndices=2, tileHeaders=3, bounds=4, renderData=5, visibleIndices=6, activeTiles=7)
+    HEADER_DTYPE = np.dtype([("totalAssignments", "<u4"), ("paddedCount", "<u4"), ("overflow", "<u4"), ("visibleCount", "<u4"),
+                             ("activeTileCount", "<u4"), ("totalRaw", "<u4"), ("_pad", "<u4", 2)])
+
+    def __init__(self, device: Optional[int] = None, config: RendererConfig = None):
+        self._r = DepthFirstRenderer(device=device, config=config)   # the handle carries limits, precision, colour space
+        self.config = self._r.config
+        self.lastGPUTime: Optional[float] = None
+        self._lib, self._h = self._r._lib, self._r._h
+
+    def close(self) -> None:
+        self._r.close()
+
+    def render(self, commandBuffer, colorTexture, depthTexture, input: GaussianInput, camera: CameraParams,
+               width: int, height: int) -> None:
+        cam = camera.to_native()
+        _check(self._lib.gsm_render_global(self._r._h, N.stream_handle(commandBuffer), N.ptr(colorTexture), N.ptr(depthTexture),
+                                           N.ptr(input.gaussians), N.ptr(input.harmonics), int(input.gaussianCount),
+                                           int(input.shComponents), C.byref(cam), int(width), int(height)))
+
+    def renderStereo(self, commandBuffer, target, input, camera, width: int, height: int) -> None:
+        # GlobalRenderer.swift:249-265: fatalError in the reference
+        raise NotImplementedError("GlobalRenderer does not support stereo rendering. Use DepthFirstRenderer instead.")
+
+    def _read(self, which: str, dtype, count: int, first: int = 0) -> np.ndarray:
+        out = np.empty(count, np.dtype(dtype))
+        if count:
+            _check(self._lib.gsm_global_debug_read(self._r._h, None, self._GDBG[which], N.ptr(out), first, count))
+        return out
+
+    def debugReadHeader(self) -> np.void:
+        return self._read("header", self.HEADER_DTYPE, 1)[0]
+
+    def debugReadTotalAssignments(self) -> int:   # GlobalRenderer.swift:200-203
+        return int(self.debugReadHeader()["totalAssignments"])
+
+    def debugReadSortedKeys(self, count: int) -> np.ndarray:
+        return self._read("sortedKeys", np.uint32, count)
+
+    def debugReadSortedIndices(self, count: int) -> np.ndarray:
+        return self._read("sortedIndices", np.int32, count)
+
+    def debugReadTileHeaders(self, count: int) -> np.ndarray:
+        return self._read("tileHeaders", np.dtype((np.uint32, 2)), count)
+
+    def debugReadBounds(self, count: int) -> np.ndarray:
+        return self._read("bounds", np.dtype((np.int32, 4)), count)
+
+    def debugReadRenderData(self, count: int) -> np.ndarray:
+        return self._read("renderData", RENDER_DATA_DTYPE, count)
+
+    def debugReadVisibleIndices(self, count: int) -> np.ndarray:
+        return self._read("visibleIndices", np.uint32, count)
+
+    def debugReadActiveTiles(self, count: int) -> np.ndarray:
+        return self._read("activeTiles", np.uint32, count)

@@ -220,6 +220,31 @@ typedef enum {
 } gsm_debug_buffer;
 
 gsm_status gsm_debug_read(gsm_renderer* r, void* stream, int which, void* dst, size_t first, size_t count);
+
+/* ---- GlobalRenderer (Sources/Renderer/GlobalRenderer/GlobalRenderer.swift:72-372, GlobalShaders.metal): the reference's second
+ * renderer behind the same protocol, on the same handle (limits, precision, colour space as RendererConfig; 32 x 16-pixel tiles
+ * of the LIMITS, GlobalRenderer.swift:26-49). gsm_render_global replaces GlobalRenderer.render (:206-247): project + cull,
+ * visibility compaction, two-pass tile assignment, ONE sort of 32-bit [tile:16][half depth:16] keys, headers by binary search,
+ * clear + render of 4 x 2 pixels per thread. Same buffers and errors as gsm_render; gaussianCount > maxGaussians encodes nothing
+ * (validateLimits, :293-297). renderStereo has no entry: the reference's is a fatalError (:249-265).
+ * gsm_global_debug_read mirrors debugReadTotalAssignments (:200-203) and the buffers the stages leave behind. */
+typedef struct {
+    uint32_t totalAssignments, paddedCount, overflow;   /* TileAssignmentHeader */
+    uint32_t visibleCount, activeTileCount, totalRaw, _pad[2];
+} gsm_global_header;
+typedef enum {
+    GSM_GDBG_HEADER = 0,           /* gsm_global_header x1 */
+    GSM_GDBG_SORTED_KEYS = 1,      /* u32 per assignment, sorted */
+    GSM_GDBG_SORTED_INDICES = 2,   /* int32 Gaussian index per assignment */
+    GSM_GDBG_TILE_HEADERS = 3,     /* GSMGaussianHeader per tile of the limits */
+    GSM_GDBG_BOUNDS = 4,           /* int32 x4 per Gaussian ((0,-1,0,-1) = culled) */
+    GSM_GDBG_RENDER_DATA = 5,      /* GSMGaussianRenderData per Gaussian (culled entries unspecified) */
+    GSM_GDBG_VISIBLE_INDICES = 6,  /* u32 per visible Gaussian, ascending */
+    GSM_GDBG_ACTIVE_TILES = 7      /* tile ids, atomic append order */
+} gsm_global_debug_buffer;
+gsm_status gsm_render_global(gsm_renderer* r, void* stream, void* color, void* depth, const void* gaussians, const void* harmonics,
+                             uint32_t gaussianCount, uint32_t shComponents, const gsm_camera* camera, uint32_t width, uint32_t height);
+gsm_status gsm_global_debug_read(gsm_renderer* r, void* stream, int which, void* dst, size_t first, size_t count);
 size_t gsm_debug_element_size(gsm_renderer* r, int which);
 
 /* Device memory and streams for hosts without a CUDA runtime binding (the Swift facade): the MTLBuffer /

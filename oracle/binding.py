@@ -372,3 +372,38 @@ def morton_order(pos: np.ndarray):
     l.gsmo_morton_order.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     l.gsmo_morton_order(_p(np.ascontiguousarray(pos, np.float32)), n, _p(codes), _p(order))
     return codes, order
+
+
+# ---------------------------------------------------------------- GlobalRenderer frame (gsmo_render_global)
+class GlobalInfo(C.Structure):
+    _fields_ = [("totalAssignments", C.c_uint32), ("paddedCount", C.c_uint32), ("overflow", C.c_uint32),
+                ("visibleCount", C.c_uint32), ("activeTileCount", C.c_uint32)]
+
+
+class OracleGlobalFrame:
+    """One GlobalRenderer frame through the oracle, every white-box buffer kept as numpy arrays."""
+
+    def __init__(self, max_gaussians: int, max_width: int, max_height: int):
+        self.G, self.maxW, self.maxH = int(max_gaussians), int(max_width), int(max_height)
+        self.tilesX, self.tilesY = (self.maxW + 31) // 32, (self.maxH + 15) // 16
+        T = max(1, self.tilesX * self.tilesY)
+        G, A = self.G, 4 * self.G
+        self.renderData = np.zeros(G, RENDER_DATA_DTYPE)
+        self.bounds = np.zeros((G, 4), np.int32)
+        self.mask = np.zeros(G, np.uint8)
+        self.visibleIndices = np.zeros(G, np.uint32)
+        self.sortedKeys = np.zeros(A, np.uint32)
+        self.sortedIndices = np.zeros(A, np.int32)
+        self.tileHeaders = np.zeros((T, 2), np.uint32)
+        self.info = GlobalInfo()
+
+    def render(self, gaussians, harmonics, precision, cam: Camera, width, height, want_depth=True):
+        color = np.full((height, width, 4), 0x7E00, np.uint16)
+        depth = np.full((height, width), 0x7E00, np.uint16) if want_depth else None
+        f = lib().gsmo_render_global
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Camera)] + [C.c_uint32] * 5 + [C.c_void_p] * 9 + [C.POINTER(GlobalInfo)]
+        f(_p(gaussians), _p(harmonics), int(precision), C.byref(cam), self.maxW, self.maxH, self.G, int(width), int(height),
+          _p(color), _p(depth), _p(self.renderData), _p(self.bounds), _p(self.mask), _p(self.visibleIndices), _p(self.sortedKeys),
+          _p(self.sortedIndices), _p(self.tileHeaders), C.byref(self.info))
+        return color, depth
