@@ -26,6 +26,10 @@
                                // loads per (thread, splat) cost more LSU time than the 28 FMA-pipe operations they replace
 #endif
 
+#ifndef GSM_BLEND_MUFU
+#define GSM_BLEND_MUFU 1       // 1: exp on the XU pipe (MUFU.EX2) behind the rounding guard of gsm_dmath.cuh (bit-exact); 2: unguarded (A/B only)
+#endif
+
 namespace gsm {
 
 constexpr int kBlendThreads = 64;
@@ -33,6 +37,19 @@ constexpr int kBlendChunk = 64;
 
 __device__ __forceinline__ __half2 h2(float v) { return __float2half2_rn(v); }
 __device__ __forceinline__ uint32_t h2bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+// exp(-0.5h * p) for two packed pairs: the XU-pipe form of gsm_dmath.cuh (MUFU.EX2 + rounding guard) with ONE rarely taken
+// branch to the canonical polynomial for both pairs, or the polynomial outright (GSM_BLEND_MUFU = 0). Bit-identical either way.
+__device__ __forceinline__ void expNegHalfPairs(__half2 p0, __half2 p1, __half2& e0, __half2& e1) {
+#if GSM_BLEND_MUFU == 1
+    const bool ok0 = dhexp2_neghalf_mufu_try(p0, e0), ok1 = dhexp2_neghalf_mufu_try(p1, e1);
+    if (!(ok0 && ok1)) { e0 = dhexp2_neghalf_packed(p0); e1 = dhexp2_neghalf_packed(p1); }
+#elif GSM_BLEND_MUFU == 2
+    e0 = dhexp2_neghalf_mufu_raw(p0); e1 = dhexp2_neghalf_mufu_raw(p1);
+#else
+    e0 = dhexp2_neghalf_packed(p0); e1 = dhexp2_neghalf_packed(p1);
+#endif
+}
 
 struct QuadState {
     __half2 T0, T1;             // transmittance rows (x, x+1)
@@ -158,8 +175,14 @@ __device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, const unsigned
     // fma(dx*dy, cxy2, fma(dy*dy, cyy, t0)) for the two rows of the quad
     const __half2 p0 = __hfma2(__hmul2_rn(dx, __low2half2(dyp)), cxy2, __hfma2(__low2half2(dy2p), cyy, t0));
     const __half2 p1 = __hfma2(__hmul2_rn(dx, __high2half2(dyp)), cxy2, __hfma2(__high2half2(dy2p), cyy, t0));
-    a0 = __hmin2(__hmul2_rn(op, expNegHalfTab(tab, p0)), h099);
-    a1 = __hmin2(__hmul2_rn(op, expNegHalfTab(tab, p1)), h099);
+    __half2 e0, e1;
+#if GSM_BLEND_TABLE
+    e0 = expNegHalfTab(tab, p0); e1 = expNegHalfTab(tab, p1);
+#else
+    expNegHalfPairs(p0, p1, e0, e1);
+#endif
+    a0 = __hmin2(__hmul2_rn(op, e0), h099);
+    a1 = __hmin2(__hmul2_rn(op, e1), h099);
     return m1.x != 0u && ((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) != 0u;
 }
 
@@ -340,8 +363,10 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
     const __half2 out0 = __hgt2(p0, r2Max), out1 = __hgt2(p1, r2Max);  // 1.0 where p > r2Max (false for NaN)
     const uint32_t o0 = h2bits(out0), o1 = h2bits(out1);
     if (o0 == 0x3C003C00u && o1 == 0x3C003C00u) return;  // all four beyond the cutoff: alphas stay 0
-    __half2 a0 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p0)), h099);
-    __half2 a1 = __hmin2(__hmul2_rn(op, dhexp2_neghalf_packed(p1)), h099);
+    __half2 e0, e1;
+    expNegHalfPairs(p0, p1, e0, e1);
+    __half2 a0 = __hmin2(__hmul2_rn(op, e0), h099);
+    __half2 a1 = __hmin2(__hmul2_rn(op, e1), h099);
     // per-pixel cutoff: alpha = 0 where p > r2Max
     uint32_t m0 = ((o0 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o0 >> 16) ? 0u : 0xFFFF0000u);
     uint32_t m1 = ((o1 & 0xFFFFu) ? 0u : 0xFFFFu) | ((o1 >> 16) ? 0u : 0xFFFF0000u);
@@ -571,10 +596,11 @@ __global__ void __launch_bounds__(64) global_render_kernel(GlobalFrame f, uint32
                 const __half2 dxA = __hsub2_rn(pxA, mx), dxB = __hsub2_rn(pxB, mx);
                 const __half2 dy0 = __hsub2_rn(py0, my), dy1 = __hsub2_rn(py1, my);
                 __half2 a[4];
-                a[0] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxA, dy0, sp.cxx, sp.cyy, sp.cxy2))), h099);
-                a[1] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxB, dy0, sp.cxx, sp.cyy, sp.cxy2))), h099);
-                a[2] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxA, dy1, sp.cxx, sp.cyy, sp.cxy2))), h099);
-                a[3] = __hmin2(__hmul2_rn(sp.op, dhexp2_neghalf_packed(power(dxB, dy1, sp.cxx, sp.cyy, sp.cxy2))), h099);
+                __half2 e[4];
+                expNegHalfPairs(power(dxA, dy0, sp.cxx, sp.cyy, sp.cxy2), power(dxB, dy0, sp.cxx, sp.cyy, sp.cxy2), e[0], e[1]);
+                expNegHalfPairs(power(dxA, dy1, sp.cxx, sp.cyy, sp.cxy2), power(dxB, dy1, sp.cxx, sp.cyy, sp.cxy2), e[2], e[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = __hmin2(__hmul2_rn(sp.op, e[k]), h099);
                 if (((h2bits(a[0]) | h2bits(a[1]) | h2bits(a[2]) | h2bits(a[3])) & 0x7FFF7FFFu) == 0u) continue;   // all eight alphas are (+-)0
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {

@@ -1394,8 +1394,8 @@ gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void
     if (!a || !out || n == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
     if (device < 0) cudaGetDevice(&device);
     DeviceGuard guard(device);
-    const size_t inEl = (op == 11) ? 6 : ((op == 5 || op == 7 || op == 8 || op == 12 || op == 13) ? 2 : 4);
-    const size_t outEl = (op == 5 || op == 6 || op == 7 || op == 8 || op == 11 || op == 12 || op == 13) ? 2 : 4;
+    const size_t inEl = (op == 11) ? 6 : ((op == 5 || op == 7 || op == 8 || op == 12 || op == 13 || (op >= 14 && op <= 16)) ? 2 : 4);
+    const size_t outEl = (op == 5 || op == 6 || op == 7 || op == 8 || op == 11 || op == 12 || op == 13 || (op >= 14 && op <= 16)) ? 2 : 4;
     void *da = nullptr, *db = nullptr, *dout = nullptr;
     gsm_status st = GSM_OK;
     cudaError_t e;

@@ -204,4 +204,39 @@ __device__ __forceinline__ __half2 dhexp2_neghalf_packed(__half2 p) {
     return __floats2half2_rn(rx, ry);
 }
 
+// exp(-0.5h * p) with the exponential on the XU pipe (MUFU.EX2) instead of the FMA-pipe polynomial, bit-identical to
+// dhexp2_neghalf_packed by construction: t is the same binary32 product the polynomial starts from; e = ex2.approx(t) is within a
+// few binary32 ulp of the polynomial's pre-rounding value, so the two can only round to different halfs when e sits that close to a
+// half rounding boundary. The guard rounds e(1 - 2^-21) and e(1 + 2^-21) to half (normal, subnormal and zero results alike): equal
+// -> that half is the answer; different (about 1 value in 1000) -> the lane pair evaluates the polynomial. gsm_probe_math ops
+// 14-16 run this on all 65 536 inputs against the oracle (tests/test_gpu_parity.py::test_math_probes_bit_exact), which is the proof;
+// op 15 (no guard) shows the inputs the guard exists for. NaN lanes give NaN here and +inf in the polynomial: the caller's
+// min(opacity * e, 0.99h) maps both to 0.99h.
+__device__ __forceinline__ float dex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ bool dhexp2_neghalf_mufu_try(__half2 p, __half2& out) {
+    const float2 pf = __half22float2(p);
+    const float2 t = __fmul2_rn(pf, make_float2(-0.5f * 1.44269504088896341f, -0.5f * 1.44269504088896341f));
+    const float2 e = make_float2(dex2_approx(t.x), dex2_approx(t.y));
+    const float2 lo = __fmul2_rn(e, make_float2(1.0f - 0x1p-21f, 1.0f - 0x1p-21f));
+    const float2 hi = __fmul2_rn(e, make_float2(1.0f + 0x1p-21f, 1.0f + 0x1p-21f));
+    const __half2 hl = __floats2half2_rn(lo.x, lo.y), hh = __floats2half2_rn(hi.x, hi.y);
+    out = hl;
+    return *reinterpret_cast<const uint32_t*>(&hl) == *reinterpret_cast<const uint32_t*>(&hh);
+}
+__device__ __forceinline__ __half2 dhexp2_neghalf_mufu(__half2 p) {
+    __half2 r;
+    if (!dhexp2_neghalf_mufu_try(p, r)) r = dhexp2_neghalf_packed(p);
+    return r;
+}
+// the unguarded form (probe / A-B builds only: NOT bit-exact)
+__device__ __forceinline__ __half2 dhexp2_neghalf_mufu_raw(__half2 p) {
+    const float2 pf = __half22float2(p);
+    const float2 t = __fmul2_rn(pf, make_float2(-0.5f * 1.44269504088896341f, -0.5f * 1.44269504088896341f));
+    return __floats2half2_rn(dex2_approx(t.x), dex2_approx(t.y));
+}
+
 }  // namespace gsm

@@ -38,6 +38,20 @@ __global__ void probe_kernel(int op, const void* a, const void* b, void* out, ui
             ((unsigned short*)out)[i] = __half_as_ushort(__low2half(dhexp2_neghalf_packed(v)));
             break;
         }
+        case 14: case 15: case 16: {  // exp(-0.5h * p) on the XU pipe: guarded (14), unguarded (15), 1 where the guard sends the pair to the polynomial (16)
+            const unsigned short* ha = (const unsigned short*)a;
+            __half2 v = __halves2half2(__ushort_as_half(ha[i]), __ushort_as_half(ha[i ^ 1u]));
+            __half2 r;
+            if (op == 14) r = dhexp2_neghalf_mufu(v);
+            else if (op == 15) r = dhexp2_neghalf_mufu_raw(v);
+            else {  // the guard is per PAIR: pair the value with itself so the flag is this input's own
+                __half2 tmp;
+                ((unsigned short*)out)[i] = dhexp2_neghalf_mufu_try(__half2half2(__ushort_as_half(ha[i])), tmp) ? 0 : 1;
+                break;
+            }
+            ((unsigned short*)out)[i] = __half_as_ushort(__low2half(r));
+            break;
+        }
         case 11: {  // fused half FMA: a holds (x, y, z) triples
             const unsigned short* ha = (const unsigned short*)a;
             ((unsigned short*)out)[i] = __half_as_ushort(__hfma(__ushort_as_half(ha[3 * i]), __ushort_as_half(ha[3 * i + 1]), __ushort_as_half(ha[3 * i + 2])));

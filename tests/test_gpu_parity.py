@@ -71,6 +71,15 @@ def test_math_probes_bit_exact(oracle):
     assert np.array_equal(tab[notnan], oracle.probe_hexp(x.view(np.uint16))[notnan])
     shuffled = rng.permutation(bits)                          # pairs of unrelated values share a half2 in the probe
     assert np.array_equal(probe_math(13, shuffled), probe_math(12, shuffled))
+    # the blend kernels' XU-pipe form (MUFU.EX2 + rounding guard, gsm_dmath.cuh): identical to the polynomial, hence to the oracle,
+    # on every non-NaN input, whatever value shares the half2; the guard catches every input the bare MUFU.EX2 gets wrong
+    mufu, raw, flag = probe_math(14, bits), probe_math(15, bits), probe_math(16, bits)
+    assert np.array_equal(mufu[notnan], probe_math(12, bits)[notnan])
+    assert np.array_equal(probe_math(14, shuffled)[~np.isnan(shuffled.view(np.float16))],
+                          probe_math(12, shuffled)[~np.isnan(shuffled.view(np.float16))])
+    wrong = notnan & (raw != probe_math(12, bits))
+    assert not np.any(wrong & (flag == 0)), "an input the unguarded form gets wrong passes the guard"
+    assert int(flag[notnan].sum()) < 400                     # the guard is the rare path (about 1 input in 1000 of [0, 35])
     xf = np.concatenate([rng.normal(0, 300, 200_000), [65504, 65520, 1e10, -1e10, 6e-8, 2.9e-8, 0.0]]).astype(np.float32)
     assert np.array_equal(probe_math(6, xf), oracle.probe_f2h(xf))
 
