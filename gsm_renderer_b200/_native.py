@@ -135,6 +135,7 @@ EXPORTS = {
     "gsm_render_strips": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                     C.c_uint32, C.POINTER(gsm_camera), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "gsm_probe_math": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "gsm_blend_exp_mode": (C.c_int, [C.c_int]),
     "gsm_status_string": (C.c_char_p, [C.c_int]),
     "gsm_last_error_string": (C.c_char_p, []),
     "gsm_abi_version": (C.c_int, []),

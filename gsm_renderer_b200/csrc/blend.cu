@@ -9,6 +9,11 @@
 // polynomial of gsm_dmath.cuh; a CTA-wide vote stops fetching once every thread has closed its quad.
 // Per-thread semantics are untouched: a thread's early exit depends only on its own four transmittances
 // (quirk Q8), and unfused mul/add keep one rounding per reference operation.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
 #include "gsm_common.cuh"
 #include "gsm_dmath.cuh"
 #include "gsm_kernels.h"
@@ -26,10 +31,6 @@
                                // loads per (thread, splat) cost more LSU time than the 28 FMA-pipe operations they replace
 #endif
 
-#ifndef GSM_BLEND_MUFU
-#define GSM_BLEND_MUFU 1       // 1: exp on the XU pipe (MUFU.EX2) behind the rounding guard of gsm_dmath.cuh (bit-exact); 2: unguarded (A/B only)
-#endif
-
 namespace gsm {
 
 constexpr int kBlendThreads = 64;
@@ -38,17 +39,17 @@ constexpr int kBlendChunk = 64;
 __device__ __forceinline__ __half2 h2(float v) { return __float2half2_rn(v); }
 __device__ __forceinline__ uint32_t h2bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
-// exp(-0.5h * p) for two packed pairs: the XU-pipe form of gsm_dmath.cuh (MUFU.EX2 + rounding guard) with ONE rarely taken
-// branch to the canonical polynomial for both pairs, or the polynomial outright (GSM_BLEND_MUFU = 0). Bit-identical either way.
+// exp(-0.5h * p) for two packed pairs. EXPM 1: the guard-free XU-pipe form of gsm_dmath.cuh (MUFU.EX2 on a tuned argument, one
+// exceptional input sent to the polynomial) -- C2 mono blend 147 -> 123 us, the FMA pipe loses 28 of its 47 operations per (warp,
+// splat); EXPM 0: the canonical polynomial itself. Bit-identical on all inputs (blendExpSelfTest below decides per device).
+template <int EXPM>
 __device__ __forceinline__ void expNegHalfPairs(__half2 p0, __half2 p1, __half2& e0, __half2& e1) {
-#if GSM_BLEND_MUFU == 1
-    const bool ok0 = dhexp2_neghalf_mufu_try(p0, e0), ok1 = dhexp2_neghalf_mufu_try(p1, e1);
-    if (!(ok0 && ok1)) { e0 = dhexp2_neghalf_packed(p0); e1 = dhexp2_neghalf_packed(p1); }
-#elif GSM_BLEND_MUFU == 2
-    e0 = dhexp2_neghalf_mufu_raw(p0); e1 = dhexp2_neghalf_mufu_raw(p1);
-#else
-    e0 = dhexp2_neghalf_packed(p0); e1 = dhexp2_neghalf_packed(p1);
-#endif
+    if (EXPM == 1) {
+        dhexp2_neghalf_tuned(p0, p1, e0, e1);
+    } else {
+        e0 = dhexp2_neghalf_packed(p0);
+        e1 = dhexp2_neghalf_packed(p1);
+    }
 }
 
 struct QuadState {
@@ -162,6 +163,7 @@ __device__ __forceinline__ __half2 expNegHalfTab(const unsigned short* __restric
 // Alphas of one staged splat on this thread's quad (DFS.metal:1770-1781), branch-free. Returns false when the splat does
 // nothing here: an invalid instance (DFS.metal:1750) or all four alphas zero (:1781) -- which covers p > 35, where
 // -0.5h * p < -17.5 makes the canonical exp exactly +0.
+template <int EXPM>
 __device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, const unsigned short* __restrict__ tab, unsigned lx, unsigned ly,
                                            __half2& a0, __half2& a1) {
     const uint2 c = sp.col[lx], r = sp.row[ly];
@@ -179,7 +181,7 @@ __device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, const unsigned
 #if GSM_BLEND_TABLE
     e0 = expNegHalfTab(tab, p0); e1 = expNegHalfTab(tab, p1);
 #else
-    expNegHalfPairs(p0, p1, e0, e1);
+    expNegHalfPairs<EXPM>(p0, p1, e0, e1);
 #endif
     a0 = __hmin2(__hmul2_rn(op, e0), h099);
     a1 = __hmin2(__hmul2_rn(op, e1), h099);
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(256) blend_exp_probe_kernel(const unsigned sho
     }
 }
 
+template <int EXPM>
 __global__ void __launch_bounds__(kBlendThreads * kBlendGroups, GSM_BLEND_CTAS) blend_mono_kernel(const uint32_t* __restrict__ lowerBounds,
                                                                    const BlendSplat* __restrict__ splats,
                                                                    const int32_t* __restrict__ instanceIdx, uint32_t width,
@@ -315,8 +318,8 @@ __global__ void __launch_bounds__(kBlendThreads * kBlendGroups, GSM_BLEND_CTAS) 
                 for (uint32_t j = 0; j < n; j += 2) {
                     if (quadClosed(q.T0, q.T1, thr)) { done = true; break; }
                     __half2 aA0, aA1, aB0, aB1;
-                    const bool useA = evalAlphas(s_sp[j], s_tab, lx, ly, aA0, aA1);
-                    const bool useB = evalAlphas(s_sp[j + 1u], s_tab, lx, ly, aB0, aB1);  // slot n is the invalid sentinel
+                    const bool useA = evalAlphas<EXPM>(s_sp[j], s_tab, lx, ly, aA0, aA1);
+                    const bool useB = evalAlphas<EXPM>(s_sp[j + 1u], s_tab, lx, ly, aB0, aB1);  // slot n is the invalid sentinel
                     GSM_BLEND_STAT(useA);
                     if (useA) {
                         const StagedSplat& sp = s_sp[j];
@@ -351,6 +354,7 @@ __global__ void __launch_bounds__(kBlendThreads * kBlendGroups, GSM_BLEND_CTAS) 
 }
 
 // one eye of depthFirstStereoRender for one splat (DFS.metal:1881-1920)
+template <int EXPM>
 __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 mean, __half2 cxx_cyy, __half cxy2h, __half2 op,
                                           __half2 cr, __half2 cg, __half2 cb, __half2 px, __half2 py0, __half2 py1) {
     if (!eyeOpen) return;
@@ -364,7 +368,7 @@ __device__ __forceinline__ void stereoEye(QuadState& q, bool eyeOpen, __half2 me
     const uint32_t o0 = h2bits(out0), o1 = h2bits(out1);
     if (o0 == 0x3C003C00u && o1 == 0x3C003C00u) return;  // all four beyond the cutoff: alphas stay 0
     __half2 e0, e1;
-    expNegHalfPairs(p0, p1, e0, e1);
+    expNegHalfPairs<EXPM>(p0, p1, e0, e1);
     __half2 a0 = __hmin2(__hmul2_rn(op, e0), h099);
     __half2 a1 = __hmin2(__hmul2_rn(op, e1), h099);
     // per-pixel cutoff: alpha = 0 where p > r2Max
@@ -400,6 +404,7 @@ __device__ __forceinline__ bool eyeRectBeyondCutoff(__half2 mean, __half2 cxx_cy
     return __hgt(__hfma(mMin, cxy2, inner), r2Max) && __hgt(__hfma(mMax, cxy2, inner), r2Max);
 }
 
+template <int EXPM>
 __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint32_t* __restrict__ lowerBounds,
                                                                      const GSMStereoTiledRenderData* __restrict__ splats,
                                                                      const int32_t* __restrict__ instanceIdx, uint32_t width,
@@ -474,9 +479,9 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
                 const uint4 sc = s_col[j];
                 const __half2 op = *reinterpret_cast<const __half2*>(&sc.x), cr = *reinterpret_cast<const __half2*>(&sc.y);
                 const __half2 cg = *reinterpret_cast<const __half2*>(&sc.z), cb = *reinterpret_cast<const __half2*>(&sc.w);
-                stereoEye(qL, !skipL, *reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&ra.y),
+                stereoEye<EXPM>(qL, !skipL, *reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&ra.y),
                           __low2half(*reinterpret_cast<const __half2*>(&ra.z)), op, cr, cg, cb, px, py0, py1);
-                stereoEye(qR, !skipR, *reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
+                stereoEye<EXPM>(qR, !skipR, *reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
                           __low2half(*reinterpret_cast<const __half2*>(&rb.y)), op, cr, cg, cb, px, py0, py1);
             }
         }
@@ -535,6 +540,7 @@ struct GlobalStaged {
     uint32_t valid;
 };
 
+template <int EXPM>
 __global__ void __launch_bounds__(64) global_render_kernel(GlobalFrame f, uint32_t width, uint32_t height, uint32_t maxWidth,
                                                            uint32_t maxHeight, __half* __restrict__ color, __half* __restrict__ depth) {
     __shared__ GlobalStaged s_sp[64];
@@ -597,8 +603,8 @@ __global__ void __launch_bounds__(64) global_render_kernel(GlobalFrame f, uint32
                 const __half2 dy0 = __hsub2_rn(py0, my), dy1 = __hsub2_rn(py1, my);
                 __half2 a[4];
                 __half2 e[4];
-                expNegHalfPairs(power(dxA, dy0, sp.cxx, sp.cyy, sp.cxy2), power(dxB, dy0, sp.cxx, sp.cyy, sp.cxy2), e[0], e[1]);
-                expNegHalfPairs(power(dxA, dy1, sp.cxx, sp.cyy, sp.cxy2), power(dxB, dy1, sp.cxx, sp.cyy, sp.cxy2), e[2], e[3]);
+                expNegHalfPairs<EXPM>(power(dxA, dy0, sp.cxx, sp.cyy, sp.cxy2), power(dxB, dy0, sp.cxx, sp.cyy, sp.cxy2), e[0], e[1]);
+                expNegHalfPairs<EXPM>(power(dxA, dy1, sp.cxx, sp.cyy, sp.cxy2), power(dxB, dy1, sp.cxx, sp.cyy, sp.cxy2), e[2], e[3]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) a[k] = __hmin2(__hmul2_rn(sp.op, e[k]), h099);
                 if (((h2bits(a[0]) | h2bits(a[1]) | h2bits(a[2]) | h2bits(a[3])) & 0x7FFF7FFFu) == 0u) continue;   // all eight alphas are (+-)0
@@ -639,9 +645,59 @@ __global__ void __launch_bounds__(64) global_render_kernel(GlobalFrame f, uint32
     }
 }
 
+// ---- which form of exp(-0.5h * p) the blend kernels of a device run (see expNegHalfPairs): decided once per device by comparing
+// the tuned XU-pipe form with the canonical polynomial on all 65 536 half inputs, in both lanes and in both pair slots. A device
+// on which any input differs (another MUFU implementation) runs the polynomial; GSM_BLEND_EXP=poly forces it (A/B, tests).
+__global__ void __launch_bounds__(256) blend_exp_selftest_kernel(uint32_t* __restrict__ mismatches) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;  // 65 536 threads: input i in the low lane, a different input in the high lane
+    const uint32_t a = i | (((i * 40503u + 977u) & 0xFFFFu) << 16), b = (a >> 16) | (a << 16);
+    const __half2 pa = *reinterpret_cast<const __half2*>(&a), pb = *reinterpret_cast<const __half2*>(&b);
+    __half2 t0, t1;
+    dhexp2_neghalf_tuned(pa, pb, t0, t1);
+    const __half2 c0 = dhexp2_neghalf_packed(pa), c1 = dhexp2_neghalf_packed(pb);
+    // NaN inputs: the tuned form gives NaN, the polynomial +inf; both become 0.99h in min(opacity * e, 0.99h) -- not compared
+    const bool nanLo = (i & 0x7FFFu) > 0x7C00u, nanHi = ((a >> 16) & 0x7FFFu) > 0x7C00u;
+    uint32_t bad = 0;
+    if (!nanLo) bad += (h2bits(t0) & 0xFFFFu) != (h2bits(c0) & 0xFFFFu);
+    if (!nanHi) bad += (h2bits(t0) >> 16) != (h2bits(c0) >> 16);
+    if (!nanHi) bad += (h2bits(t1) & 0xFFFFu) != (h2bits(c1) & 0xFFFFu);
+    if (!nanLo) bad += (h2bits(t1) >> 16) != (h2bits(c1) >> 16);
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+constexpr int kMaxDevices = 64;
+static int g_blendExpMode[kMaxDevices];  // 0 not tested yet (the polynomial runs), 1 polynomial, 2 tuned XU-pipe form
+static std::mutex g_blendExpMutex;
+
+cudaError_t blendExpSelfTest(int device) {  // called by gsm_renderer_create with the device current; synchronises (never in a frame)
+    if (device < 0 || device >= kMaxDevices) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(g_blendExpMutex);
+    if (g_blendExpMode[device] != 0) return cudaSuccess;
+    const char* env = getenv("GSM_BLEND_EXP");
+    if (env && strcmp(env, "poly") == 0) { g_blendExpMode[device] = 1; return cudaSuccess; }
+    uint32_t* d = nullptr;
+    uint32_t h = 1;
+    cudaError_t e = cudaMalloc((void**)&d, sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(d, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) { blend_exp_selftest_kernel<<<256, 256>>>(d); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return e;
+    g_blendExpMode[device] = (h == 0u) ? 2 : 1;
+    if (h != 0u) fprintf(stderr, "[gsm] device %d: MUFU.EX2 form of the blend's exp differs from the canonical polynomial on %u checks; using the polynomial\n", device, h);
+    return cudaSuccess;
+}
+int blendExpMode(int device) { return (device >= 0 && device < kMaxDevices) ? g_blendExpMode[device] : 0; }
+static bool tunedExpOnCurrentDevice() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess && blendExpMode(dev) == 2;
+}
+
 cudaError_t launchGlobalRender(cudaStream_t s, const GlobalFrame& f, uint32_t width, uint32_t height, uint32_t maxWidth, uint32_t maxHeight,
                                __half* color, __half* depth) {
-    global_render_kernel<<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
+    if (tunedExpOnCurrentDevice()) global_render_kernel<1><<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
+    else global_render_kernel<0><<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
     return cudaGetLastError();
 }
 
@@ -653,15 +709,17 @@ cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const B
     if (tileRowCount == 0) return cudaSuccess;
     static bool attrSet = false;
     if (!attrSet) {
-        cudaError_t e = cudaFuncSetAttribute(blend_mono_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlendSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(blend_mono_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlendSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_mono_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlendSmemBytes);
         if (e != cudaSuccess) return e;
         attrSet = true;
     }
     const uint32_t numTiles = tilesX * tileRowCount;
     uint32_t grid = (numTiles + kBlendGroups - 1) / kBlendGroups;
     if (grid > (uint32_t)numSMs * GSM_BLEND_CTAS) grid = (uint32_t)numSMs * GSM_BLEND_CTAS;  // persistent: GSM_BLEND_CTAS CTAs of kBlendGroups tile groups per SM
-    return launchChainedSmem(blend_mono_kernel, grid, kBlendThreads * kBlendGroups, s, kBlendSmemBytes, lowerBounds, splats, instanceIdx,
-                         width, height, tilesX, tileRowFirst, numTiles, expTable, ticket, color, depth, tout);
+    return launchChainedSmem(tunedExpOnCurrentDevice() ? blend_mono_kernel<1> : blend_mono_kernel<0>, grid, kBlendThreads * kBlendGroups, s,
+                             kBlendSmemBytes, lowerBounds, splats, instanceIdx, width, height, tilesX, tileRowFirst, numTiles, expTable,
+                             ticket, color, depth, tout);
 }
 
 cudaError_t buildBlendExpTable(cudaStream_t s, unsigned short* table) {
@@ -681,7 +739,7 @@ cudaError_t launchBlendExpProbe(cudaStream_t s, const unsigned short* table, con
 cudaError_t launchBlendStereo(cudaStream_t s, const uint32_t* lowerBounds, const GSMStereoTiledRenderData* splats,
                               const int32_t* instanceIdx, uint32_t width, uint32_t height, uint32_t tilesX, uint32_t tilesY,
                               __half* dstSideBySide, int eyeMask, int flipY, TileOut tout) {
-    return launchChained(blend_stereo_kernel, tilesX * tilesY, kBlendThreads, s, lowerBounds, splats, instanceIdx, width, height,
+    return launchChained(tunedExpOnCurrentDevice() ? blend_stereo_kernel<1> : blend_stereo_kernel<0>, tilesX * tilesY, kBlendThreads, s, lowerBounds, splats, instanceIdx, width, height,
                          tilesX, dstSideBySide, flipY, eyeMask, tout);
 }
 

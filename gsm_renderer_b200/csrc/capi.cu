@@ -521,10 +521,11 @@ gsm_status gsm_renderer_create(const gsm_config* cfg, gsm_renderer** out) {
         if (e == cudaSuccess) e = buildBlendExpTable(nullptr, r->expTable);
         if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
     }
+    if (e == cudaSuccess) e = blendExpSelfTest(dev);  // once per device: which form of exp(-0.5h * p) its blend kernels run
     if (e != cudaSuccess) {
         if (r->expTable) cudaFree(r->expTable);
         delete r;
-        return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "blend exp table", e);
+        return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "blend exp table / self-test", e);
     }
     *out = r;
     return GSM_OK;
@@ -1394,8 +1395,8 @@ gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void
     if (!a || !out || n == 0) return fail(GSM_ERR_INVALID_ARGUMENT, "null argument");
     if (device < 0) cudaGetDevice(&device);
     DeviceGuard guard(device);
-    const size_t inEl = (op == 11) ? 6 : ((op == 5 || op == 7 || op == 8 || op == 12 || op == 13 || (op >= 14 && op <= 16)) ? 2 : 4);
-    const size_t outEl = (op == 5 || op == 6 || op == 7 || op == 8 || op == 11 || op == 12 || op == 13 || (op >= 14 && op <= 16)) ? 2 : 4;
+    const size_t inEl = (op == 11) ? 6 : ((op == 5 || op == 7 || op == 8 || op == 12 || op == 13 || (op >= 14 && op <= 17)) ? 2 : 4);
+    const size_t outEl = (op == 5 || op == 6 || op == 7 || op == 8 || op == 11 || op == 12 || op == 13 || (op >= 14 && op <= 17)) ? 2 : 4;
     void *da = nullptr, *db = nullptr, *dout = nullptr;
     gsm_status st = GSM_OK;
     cudaError_t e;
@@ -1421,6 +1422,11 @@ gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void
     if (e != cudaSuccess) st = fail(GSM_ERR_RENDER_FAILED, "gsm_probe_math", e);
     cudaFree(da); cudaFree(db); cudaFree(dout);
     return st;
+}
+
+int gsm_blend_exp_mode(int device) {
+    if (device < 0) cudaGetDevice(&device);
+    return blendExpMode(device);
 }
 
 const char* gsm_status_string(gsm_status s) {

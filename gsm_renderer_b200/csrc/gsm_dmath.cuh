@@ -239,4 +239,40 @@ __device__ __forceinline__ __half2 dhexp2_neghalf_mufu_raw(__half2 p) {
     return __floats2half2_rn(dex2_approx(t.x), dex2_approx(t.y));
 }
 
+// The form the blend kernels run: exp(-0.5h * p) for two packed pairs with NO guard. t = fma.rm(float(p), c, 3 * 2^-24) -- the
+// canonical constant, a round-down fused add of a fixed offset -- then MUFU.EX2 and one rounding to half. A search over the offset and
+// the fma's rounding mode on the device (tools/micro/mufu_tune.cu, profiles/r2_mufu_tune.txt) found this form equal to the canonical
+// polynomial on every one of the 65 536 half inputs except p = 0x297F (0.04294), which is tested for (one packed compare per pair)
+// and sent to the polynomial. The domain is finite and MUFU.EX2 is a fixed function of its input bits, so the exhaustive comparison
+// (gsm_probe_math op 17 against the oracle in tests/test_gpu_parity.py, and blendExpSelfTest on every device at renderer creation --
+// a device whose MUFU differs runs the polynomial) is the proof, not an error bound.
+constexpr float kExpTunedOffset = 3.0f * 0x1p-24f;
+constexpr unsigned short kExpTunedException = 0x297Fu;
+__device__ __forceinline__ __half2 dhexp2_neghalf_tuned_raw(__half2 p) {
+    const float2 t = __ffma2_rd(__half22float2(p), make_float2(-0.5f * 1.44269504088896341f, -0.5f * 1.44269504088896341f),
+                                make_float2(kExpTunedOffset, kExpTunedOffset));
+    return __floats2half2_rn(dex2_approx(t.x), dex2_approx(t.y));
+}
+// true if any of the four halves is the exceptional input (or a NaN): two packed compares with two predicate results each (HSETP2), chained through the predicate input
+__device__ __forceinline__ bool dhexp2_tuned_exception2(__half2 p0, __half2 p1) {
+    const uint32_t xb = (uint32_t)kExpTunedException | ((uint32_t)kExpTunedException << 16);
+    uint32_t r;
+    asm("{ .reg .pred a, b, c, d;\n\t"
+        "setp.ne.f16x2 a|b, %1, %3;\n\t"
+        "and.pred a, a, b;\n\t"
+        "setp.ne.and.f16x2 c|d, %2, %3, a;\n\t"
+        "and.pred c, c, d;\n\t"
+        "selp.u32 %0, 0, 1, c; }"
+        : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&p0)), "r"(*reinterpret_cast<const uint32_t*>(&p1)), "r"(xb));
+    return r != 0u;
+}
+__device__ __forceinline__ void dhexp2_neghalf_tuned(__half2 p0, __half2 p1, __half2& e0, __half2& e1) {
+    e0 = dhexp2_neghalf_tuned_raw(p0);
+    e1 = dhexp2_neghalf_tuned_raw(p1);
+    if (dhexp2_tuned_exception2(p0, p1)) {
+        e0 = dhexp2_neghalf_packed(p0);
+        e1 = dhexp2_neghalf_packed(p1);
+    }
+}
+
 }  // namespace gsm

@@ -117,6 +117,8 @@ cudaError_t launchBlendMono(cudaStream_t s, const uint32_t* lowerBounds, const B
                             uint32_t tileRowCount, __half* color, __half* depth, TileOut tout, const unsigned short* expTable,
                             uint32_t* ticket, int numSMs);
 // exact table of the blend's exp(-0.5h * p) over the non-negative halfs (built once per renderer from the canonical function)
+cudaError_t blendExpSelfTest(int device);   // decides, once per device, which form of exp(-0.5h * p) the blend kernels run
+int blendExpMode(int device);                // 0 not decided (polynomial), 1 polynomial, 2 tuned XU-pipe (MUFU.EX2) form
 size_t blendExpTableBytes();
 bool blendUsesExpTable();   // false in the default build: the polynomial is faster (blend.cu, GSM_BLEND_TABLE)
 cudaError_t buildBlendExpTable(cudaStream_t s, unsigned short* table);

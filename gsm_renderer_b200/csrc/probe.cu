@@ -52,6 +52,14 @@ __global__ void probe_kernel(int op, const void* a, const void* b, void* out, ui
             ((unsigned short*)out)[i] = __half_as_ushort(__low2half(r));
             break;
         }
+        case 17: {  // the blend kernels' tuned XU-pipe form, the value paired with its neighbour as in a quad row
+            const unsigned short* ha = (const unsigned short*)a;
+            __half2 v = __halves2half2(__ushort_as_half(ha[i]), __ushort_as_half(ha[i ^ 1u]));
+            __half2 e0, e1;
+            dhexp2_neghalf_tuned(v, __lowhigh2highlow(v), e0, e1);
+            ((unsigned short*)out)[i] = __half_as_ushort(__low2half(e0));
+            break;
+        }
         case 11: {  // fused half FMA: a holds (x, y, z) triples
             const unsigned short* ha = (const unsigned short*)a;
             ((unsigned short*)out)[i] = __half_as_ushort(__hfma(__ushort_as_half(ha[3 * i]), __ushort_as_half(ha[3 * i + 1]), __ushort_as_half(ha[3 * i + 2])));

@@ -457,10 +457,10 @@ def probe_math(op: int, a, b=None, device: int = -1) -> np.ndarray:
     """gsm_probe_math: device restatement of the canonical math (0 sin, 1 cos, 2 log, 3 atan2, 4 powr 2.4,
     5 half exp, 6 float->half, 7/8 packed half exp forms, 9/10 min/max, 11 fused half fma on (n,3) triples,
     12 exp(-0.5h * p) with the -0.5 folded in, 13 the same through the blend's shared-memory table, 14 the same on the XU pipe
-    (MUFU.EX2 behind the rounding guard), 15 unguarded, 16 the guard's flag)."""
+    (MUFU.EX2 behind the rounding guard), 15 unguarded, 16 the guard's flag, 17 the tuned guard-free form the blend kernels run)."""
     a = np.ascontiguousarray(a)
     n = a.shape[0] if op == 11 else a.size  # op 11 (half fma) takes (n, 3) uint16 triples
-    out = np.empty(n if op == 11 else a.shape, np.uint16 if op in (5, 6, 7, 8, 11, 12, 13, 14, 15, 16) else np.float32)
+    out = np.empty(n if op == 11 else a.shape, np.uint16 if op in (5, 6, 7, 8, 11, 12, 13, 14, 15, 16, 17) else np.float32)
     bp = None if b is None else N.ptr(np.ascontiguousarray(b))
     _check(N.lib().gsm_probe_math(device, op, N.ptr(a), bp, N.ptr(out), n))
     return out

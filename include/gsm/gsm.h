@@ -334,6 +334,11 @@ gsm_status gsm_render_strips(gsm_group* g, void* stream, void* color, void* dept
  * tests can compare them bit-for-bit with the CPU oracle. op: 0 sin, 1 cos, 2 log, 3 atan2(a,b),
  * 4 powr(a, 2.4), 5 half exp (a,out are u16), 6 float->half (out u16). Host pointers. */
 gsm_status gsm_probe_math(int device, int op, const void* a, const void* b, void* out, uint32_t n);
+/* Which evaluation of exp(-0.5h * p) (DepthFirstShaders.metal:1775-1778, GlobalShaders.metal:1117-1124) the blend kernels of
+ * `device` (-1: current) run: 2 = MUFU.EX2 on a tuned argument, 1 = the canonical polynomial, 0 = no renderer created on the
+ * device yet. Both give identical bits; gsm_renderer_create proves it on the device over all 65 536 half inputs and falls back to
+ * the polynomial if any input differs (environment GSM_BLEND_EXP=poly forces the polynomial). */
+int gsm_blend_exp_mode(int device);
 
 const char* gsm_status_string(gsm_status s);
 const char* gsm_last_error_string(void);

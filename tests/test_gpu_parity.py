@@ -80,8 +80,63 @@ def test_math_probes_bit_exact(oracle):
     wrong = notnan & (raw != probe_math(12, bits))
     assert not np.any(wrong & (flag == 0)), "an input the unguarded form gets wrong passes the guard"
     assert int(flag[notnan].sum()) < 400                     # the guard is the rare path (about 1 input in 1000 of [0, 35])
+    # the form the blend kernels RUN: MUFU.EX2 on a tuned argument, no guard, one exceptional input (gsm_dmath.cuh) -- equal to the
+    # oracle on every non-NaN input, whichever value shares the half2
+    tuned = probe_math(17, bits)
+    assert np.array_equal(tuned[notnan], oracle.probe_hexp(x.view(np.uint16))[notnan])
+    assert np.array_equal(probe_math(17, shuffled)[~np.isnan(shuffled.view(np.float16))],
+                          probe_math(12, shuffled)[~np.isnan(shuffled.view(np.float16))])
     xf = np.concatenate([rng.normal(0, 300, 200_000), [65504, 65520, 1e10, -1e10, 6e-8, 2.9e-8, 0.0]]).astype(np.float32)
     assert np.array_equal(probe_math(6, xf), oracle.probe_f2h(xf))
+
+
+def test_blend_runs_the_xu_pipe_exp_and_equals_the_polynomial_build_gpu(pu):
+    """gsm_renderer_create's self-test must select the MUFU.EX2 form on a B200 (mode 2; a silent fall-back to the polynomial would
+    hide a regression), and a process forced to the polynomial (GSM_BLEND_EXP=poly) must produce the same mono, stereo and Global
+    frames byte for byte."""
+    import hashlib, json, os, subprocess, sys
+    code = r'''
+import hashlib, json, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from gsm_renderer_b200 import synthetic as syn
+from gsm_renderer_b200 import _native as N
+from gsm_renderer_b200.renderer import (DepthFirstRenderer, GlobalRenderer, GaussianInput, RendererConfig, RenderPrecision, StereoCameraParams, StereoRenderTarget)
+import tests.parity_util as pu
+cl = syn.synthetic_cloud(60_000, 2, seed=11, scale_median=0.02)
+g, h = pu.make_scene_inputs(cl, "float16")
+W, H = 1280, 720
+cam = pu.default_camera(W, H)
+dev = torch.device("cuda:0")
+tg = torch.from_numpy(g.view(np.uint8).reshape(-1)).to(dev); th = torch.from_numpy(h.view(np.uint8).reshape(-1)).to(dev)
+inp = GaussianInput(tg, th, g.shape[0], cl.sh_components)
+out = {}
+for name, cls in (("mono", DepthFirstRenderer), ("global", GlobalRenderer)):
+    r = cls(device=0, config=RendererConfig(maxGaussians=cl.count, maxWidth=W, maxHeight=H, precision=RenderPrecision.float16))
+    color = torch.zeros((H, W, 4), dtype=torch.int16, device=dev); depth = torch.zeros((H, W), dtype=torch.int16, device=dev)
+    r.render(torch.cuda.current_stream(), color, depth, inp, cam, W, H)
+    torch.cuda.synchronize()
+    out[name] = hashlib.sha256(color.cpu().numpy().tobytes() + depth.cpu().numpy().tobytes()).hexdigest()
+    if name == "mono":
+        camR = pu.default_camera(W, H, position=(0.065, 0.0, 0.0))
+        sbs = torch.zeros((H, 2 * W, 4), dtype=torch.int16, device=dev)
+        r.renderStereo(torch.cuda.current_stream(), StereoRenderTarget.sideBySide(sbs), inp, StereoCameraParams(cam, camR), W, H)
+        torch.cuda.synchronize()
+        out["stereo"] = hashlib.sha256(sbs.cpu().numpy().tobytes()).hexdigest()
+    r.close()
+out["mode"] = int(N.lib().gsm_blend_exp_mode(0))
+print(json.dumps(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for label, env in (("tuned", {}), ("poly", {"GSM_BLEND_EXP": "poly"})):
+        e = dict(os.environ); e.pop("GSM_BLEND_EXP", None); e.update(env)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[label] = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["tuned"]["mode"] == 2, "the self-test rejected the MUFU.EX2 form on this device"
+    assert res["poly"]["mode"] == 1
+    for k in ("mono", "global", "stereo"):
+        assert res["tuned"][k] == res["poly"][k], k
 
 
 # ---------------------------------------------------------------- sorts: the reference's own KATs on the device
