@@ -20,10 +20,13 @@
 
 // A/B knobs of the mono blend (tools/build_variant.sh builds variants; the defaults are the measured best)
 #ifndef GSM_BLEND_GROUPS
-#define GSM_BLEND_GROUPS 4
+#define GSM_BLEND_GROUPS 5
 #endif
 #ifndef GSM_BLEND_CTAS
 #define GSM_BLEND_CTAS 2       // resident CTAs per SM the launch bounds ask for
+#endif
+#ifndef GSM_BLEND_PREFETCH
+#define GSM_BLEND_PREFETCH 1       // 1: records one chunk and indices two chunks ahead (C2 blend 124 -> 119 us at 4 groups, 114 us at 5); 2: indices only
 #endif
 #ifndef GSM_BLEND_TABLE
 #define GSM_BLEND_TABLE 0      // 1: exact exp table in shared memory instead of the polynomial. Measured SLOWER (C2 blend 162.8 us
@@ -142,8 +145,14 @@ struct StagedSplat {
     uint2 col[8];  // per x pair k: {T0(x=2k), T0(2k+1)} , {dx(2k), dx(2k+1)}
     uint2 row[8];  // per y pair k: {dy*dy(y=2k), dy*dy(2k+1)} , {dy(2k), dy(2k+1)}
     uint4 m0;      // cxy2|cxy2, op|op, r|r, g|g
-    uint4 m1;      // b|b, depth|depth, valid, cyy|cyy
+    uint4 m1;      // b|b, depth|depth, unused, cyy|cyy
 };
+
+__device__ __forceinline__ void zeroStaged(StagedSplat& sp) {
+    uint4* w = reinterpret_cast<uint4*>(&sp);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(StagedSplat) / 16); ++k) w[k] = make_uint4(0u, 0u, 0u, 0u);
+}
 
 // exp(-0.5h * p) of both halves of p from the exact table (tab[bits(p)] == dhexp2_neghalf_packed(p), built by
 // blend_exp_table_kernel from that very function, so bit-identical by construction and checked on all inputs by
@@ -168,10 +177,10 @@ __device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, const unsigned
                                            __half2& a0, __half2& a1) {
     const uint2 c = sp.col[lx], r = sp.row[ly];
     const uint4 m0 = sp.m0;
-    const uint2 m1 = *reinterpret_cast<const uint2*>(&sp.m1.z);  // valid, cyy|cyy
+    const uint32_t m1y = sp.m1.w;  // cyy|cyy
     const __half2 t0 = *reinterpret_cast<const __half2*>(&c.x), dx = *reinterpret_cast<const __half2*>(&c.y);
     const __half2 dy2p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
-    const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x), cyy = *reinterpret_cast<const __half2*>(&m1.y);
+    const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x), cyy = *reinterpret_cast<const __half2*>(&m1y);
     const __half2 op = *reinterpret_cast<const __half2*>(&m0.y);
     const __half2 h099 = h2(0.99f);
     // fma(dx*dy, cxy2, fma(dy*dy, cyy, t0)) for the two rows of the quad
@@ -185,7 +194,9 @@ __device__ __forceinline__ bool evalAlphas(const StagedSplat& sp, const unsigned
 #endif
     a0 = __hmin2(__hmul2_rn(op, e0), h099);
     a1 = __hmin2(__hmul2_rn(op, e1), h099);
-    return m1.x != 0u && ((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) != 0u;
+    // an invalid instance (DFS.metal:1750) is staged as all zeros: p = 0, opacity 0, alphas +0 -- it leaves here like any other
+    // splat without effect, no flag to test
+    return ((h2bits(a0) | h2bits(a1)) & 0x7FFF7FFFu) != 0u;
 }
 
 // ---- persistent form: kBlendGroups tiles in flight per CTA (one 64-thread group each) sharing the CTA's exp table
@@ -277,14 +288,34 @@ __global__ void __launch_bounds__(kBlendThreads * kBlendGroups, GSM_BLEND_CTAS) 
         q.r0 = q.g0 = q.b0 = q.d0 = q.r1 = q.g1 = q.b1 = q.d1 = zero;
         bool done = false;
 
+#if GSM_BLEND_PREFETCH == 2
+        int32_t giCur = tid < count ? __ldg(instanceIdx + start + tid) : -1;   // index one chunk ahead only (one register)
+#elif GSM_BLEND_PREFETCH
+        // The staging of a chunk is two dependent global loads (instance index -> 32-byte record). They are issued one chunk
+        // (records) and two chunks (indices) ahead, so their latency runs under the previous chunk's blending instead of in
+        // front of this chunk's barrier.
+        int32_t giCur = tid < count ? __ldg(instanceIdx + start + tid) : -1;
+        int32_t giNext = kBlendChunk + tid < count ? __ldg(instanceIdx + start + kBlendChunk + tid) : -1;
+        uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+        if (giCur >= 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(splats + giCur);
+            ra = __ldg(src); rb = __ldg(src + 1);
+        }
+#endif
         for (uint32_t base = 0; base < count; base += kBlendChunk) {
             const uint32_t n = min((uint32_t)kBlendChunk, count - base);
             if (tid < n) {
+#if GSM_BLEND_PREFETCH
+                const int32_t gi = giCur;
+#else
                 const int32_t gi = __ldg(instanceIdx + start + base + tid);
+#endif
                 StagedSplat& sp = s_sp[tid];
                 if (gi >= 0) {
+#if GSM_BLEND_PREFETCH != 1
                     const uint4* src = reinterpret_cast<const uint4*>(splats + gi);
                     const uint4 ra = __ldg(src), rb = __ldg(src + 1);
+#endif
                     const __half2 mean = *reinterpret_cast<const __half2*>(&ra.x);
                     const __half2 cxx_cyy = *reinterpret_cast<const __half2*>(&ra.y);
                     const __half2 cxy2_op = *reinterpret_cast<const __half2*>(&ra.z);
@@ -302,13 +333,23 @@ __global__ void __launch_bounds__(kBlendThreads * kBlendGroups, GSM_BLEND_CTAS) 
                     }
                     sp.m0 = make_uint4(h2bits(__low2half2(cxy2_op)), h2bits(__high2half2(cxy2_op)), h2bits(__low2half2(rg)),
                                        h2bits(__high2half2(rg)));
-                    sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 1u, h2bits(cyy));
+                    sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 0u, h2bits(cyy));
                 } else {
-                    sp.m1 = make_uint4(0, 0, 0, 0);  // valid = 0: "continue" (DFS.metal:1750)
+                    zeroStaged(sp);  // "continue" (DFS.metal:1750): opacity 0 makes every alpha +0
                 }
             }
-            if (tid == 0) s_sp[n].m1 = make_uint4(0, 0, 0, 0);  // the loop below reads slot j + 1 unconditionally
+            if (tid == 0) zeroStaged(s_sp[n]);  // the loop below reads slot j + 1 unconditionally
             groupBarrier(group);
+#if GSM_BLEND_PREFETCH == 2
+            giCur = base + kBlendChunk + tid < count ? __ldg(instanceIdx + start + base + kBlendChunk + tid) : -1;
+#elif GSM_BLEND_PREFETCH
+            giCur = giNext;
+            if (giCur >= 0) {
+                const uint4* src = reinterpret_cast<const uint4*>(splats + giCur);
+                ra = __ldg(src); rb = __ldg(src + 1);
+            }
+            giNext = base + 2u * kBlendChunk + tid < count ? __ldg(instanceIdx + start + base + 2u * kBlendChunk + tid) : -1;
+#endif
             if (!done) {
                 // Two splats per trip: the alphas of splat j+1 do not depend on splat j (only the accumulation does), and
                 // evaluating both before either is accumulated gives each warp four independent chains instead of two

@@ -259,9 +259,9 @@ __device__ __forceinline__ bool dhexp2_tuned_exception2(__half2 p0, __half2 p1) 
     uint32_t r;
     asm("{ .reg .pred a, b, c, d;\n\t"
         "setp.ne.f16x2 a|b, %1, %3;\n\t"
-        "and.pred a, a, b;\n\t"
         "setp.ne.and.f16x2 c|d, %2, %3, a;\n\t"
         "and.pred c, c, d;\n\t"
+        "and.pred c, c, b;\n\t"
         "selp.u32 %0, 0, 1, c; }"
         : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&p0)), "r"(*reinterpret_cast<const uint32_t*>(&p1)), "r"(xb));
     return r != 0u;
