@@ -299,6 +299,7 @@ bool depthBucketsEnabled() {
 void attachDepthPlan(const gsm_renderer* r, Resources& res, ProjectOut& po, uint32_t gaussianCount) {
     if (depthBucketsEnabled() && r->cfg.depthSortKeyPrecision != GSM_KEY_BITS16 && bucketSortCovers(gaussianCount, r->numSMs)) {
         po.keyRange = res.keyRange;
+        po.depthPasses = 0u;   // the bucket sort builds its own counts: no LSD digit histograms from the compaction (0.7 M x 4 shared-memory atomics + the per-CTA flush)
     }
 }
 

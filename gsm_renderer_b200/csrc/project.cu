@@ -767,6 +767,12 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
             cnt += nt[i] > 0u ? 1u : 0u;
             tsum += nt[i];
         }
+        // the keys of the visible elements do not depend on the prefix: their loads are in flight under the scan and the wait for
+        // the predecessors' aggregates instead of behind them
+        uint32_t keys[kCompactItems];
+#pragma unroll
+        for (int i = 0; i < kCompactItems; ++i)
+            keys[i] = nt[i] > 0u ? (o.recTouched ? o.recKey[first + i] : o.preDepthKeys[o.gidFirst + first + i]) : 0u;
         uint32_t blockVisible;
         const uint32_t excl = block_exclusive_scan_256(cnt, s_scan, blockVisible);
         for (int off = 16; off > 0; off >>= 1) tsum += __shfl_xor_sync(0xFFFFFFFFu, tsum, off);
@@ -799,7 +805,7 @@ __global__ void __launch_bounds__(256) compact_visible_kernel(uint32_t N, Projec
                 if (dst < o.maxOut) {  // DFS.metal:605
                     // projection: element l is Gaussian gidFirst + l; strip ingest: element l is gathered record l
                     const uint32_t gid = o.recTouched ? o.recGid[first + i] : o.gidFirst + first + i;
-                    uint32_t key = o.recTouched ? o.recKey[first + i] : o.preDepthKeys[gid];
+                    uint32_t key = keys[i];
                     if (o.depthKey16) {  // DFS.metal:607-612; key is float_to_sortable_uint of a depth > 0
                         uint32_t bits = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
                         key = (uint32_t)(__half_as_ushort(__float2half_rn(__uint_as_float(bits))) ^ 0x8000u);
