@@ -527,25 +527,33 @@ def main():
         ms = stage_ms.get(k, 0.0) + stage_ms.get(fold.get(k, ""), 0.0)
         gbs = sb[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stage_roofline.append({"stage": k, "ms": ms, "bytes": int(sb[k]), "GBps": gbs, "frac": gbs / peak})
-    dom = max(stage_roofline, key=lambda s: s["ms"])
-
-    def _profile_json(name):
-        pth = os.path.join(ROOT, "profiles", name)
+    def _profile_doc(name):
         try:
-            d = json.load(open(pth))
-            return d.get(dom["stage"]), d.get("_source") or d.get("note")
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
         except Exception:
-            return None, None
-    traffic, traffic_src = _profile_json("traffic.json")
-    pipes, pipes_src = _profile_json("pipes.json")
+            return {}
+    traffic_doc, pipes_doc = _profile_doc("traffic.json"), _profile_doc("pipes.json")
+    # The dominant KERNEL, not the longest stage interval: a stage interval can hold several kernels (project = projection +
+    # compaction, tileSort = three kernels). Each interval is split by its kernels' shares in the committed ncu capture.
+    kern_us = pipes_doc.get("kernels_us") or []
+    def _largest_kernel_share(stage):
+        us = [k["us"] for k in kern_us if k.get("stage") == stage]
+        return max(us) / sum(us) if us else 1.0
+    dom = max(stage_roofline, key=lambda s: s["ms"] * _largest_kernel_share(s["stage"]))
+    traffic, traffic_src = traffic_doc.get(dom["stage"]), traffic_doc.get("_source") or traffic_doc.get("note")
+    pipes, pipes_src = pipes_doc.get(dom["stage"]), pipes_doc.get("_source") or pipes_doc.get("note")
     hbm = {"achieved": dom["GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src,
            "algorithmic_bytes": dom["bytes"], "ms": dom["ms"]}
-    if dom["stage"] == "blend" and pipes and pipes.get("fma_pipe_cycles_active_pct"):
-        # the blend is bound by the FMA pipe and issue slots, not by bytes: its roofline is the pipe's utilisation
-        # from the ncu capture named in pipes_source; the live HBM figure stays beside it
-        roofline = {"bound": "fp_pipe", "kernel": "blend", "achieved": pipes["fma_pipe_cycles_active_pct"], "peak": 100.0,
-                    "unit": "% of FMA-pipe cycles active (ncu sm__pipe_fma_cycles_active)", "frac": pipes["fma_pipe_cycles_active_pct"] / 100.0,
-                    "traffic": traffic, "traffic_source": traffic_src, "pipes": pipes, "pipes_source": pipes_src, "hbm": hbm}
+    if dom["stage"] == "blend" and pipes and pipes.get("issue_active_pct"):
+        # the blend is bound by instruction issue and the FMA / XU pipes, not by bytes: its roofline is the busiest of
+        # those three from the ncu capture named in pipes_source; the live HBM figure stays beside it
+        cands = {"issue": ("% of issue slots active (ncu smsp__issue_active)", pipes.get("issue_active_pct") or 0.0),
+                 "fp_pipe": ("% of FMA-pipe cycles active (ncu sm__pipe_fma_cycles_active)", pipes.get("fma_pipe_cycles_active_pct") or 0.0),
+                 "xu_pipe": ("% of XU-pipe issue (ncu sm__inst_executed_pipe_xu)", pipes.get("xu_pipe_inst_pct") or 0.0)}
+        bound = max(cands, key=lambda k: cands[k][1])
+        roofline = {"bound": bound, "kernel": "blend", "achieved": cands[bound][1], "peak": 100.0, "unit": cands[bound][0],
+                    "frac": cands[bound][1] / 100.0, "traffic": traffic, "traffic_source": traffic_src, "pipes": pipes,
+                    "pipes_source": pipes_src, "hbm": hbm}
     else:
         roofline = {"bound": "hbm", "kernel": dom["stage"], **hbm, "traffic": traffic, "traffic_source": traffic_src,
                     "pipes": pipes, "pipes_source": pipes_src}

@@ -81,7 +81,10 @@ for key, pat in (("project", "project_cull"), ("expand", "create_instances"), ("
         if pat in r[ki]:
             pipes[key] = {"kernel": r[ki], "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                           "fma_pipe_cycles_active_pct": val(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                          "xu_pipe_inst_pct": val(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
                           "duration_us_under_ncu": round(to_us(r), 3)}
             break
+# every kernel of the frame with its stage and duration: bench.py splits a stage interval among its kernels by these shares
+pipes["kernels_us"] = [{"stage": stage_of(r[ki]), "kernel": r[ki].split("(")[0], "us": round(to_us(r), 3)} for r in data if stage_of(r[ki])]
 json.dump(pipes, open("profiles/pipes.json", "w"), indent=1)
 print(json.dumps({"traffic": traffic, "pipes": pipes}, indent=1))
