@@ -288,6 +288,11 @@ bool tileSortMsdEnabled() {
     static const bool on = [] { const char* e = getenv("GSM_TILE_MSD"); return !(e && e[0] == '0'); }();
     return on;
 }
+// GSM_TILE_PAIRS=0 in the environment keeps the MSD pass on one tile per CTA (A/B measurement)
+bool tilePairsEnabled() {
+    static const bool on = [] { const char* e = getenv("GSM_TILE_PAIRS"); return !(e && e[0] == '0'); }();
+    return on;
+}
 // GSM_DEPTH_BUCKETS=0 in the environment keeps the depth sort on the four LSD passes (A/B measurement)
 bool depthBucketsEnabled() {
     static const bool on = [] { const char* e = getenv("GSM_DEPTH_BUCKETS"); return !(e && e[0] == '0'); }();
@@ -367,7 +372,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     tp.largeTiles = largeSort(res.frameGaussians);
     tp.tilesCap = res.tileTilesCap; tp.keyBits = tile16 ? 16 : 32; tp.numPasses = tilePasses;
     tp.numSMs = r->numSMs; tp.histogramReady = true;  // create_instances_kernel filled hist[4..7]; the status words were cleared with the frame state
-    if (msdTiles) { tp.numPasses = 1; tp.shift0 = (int)lowBits; tp.leaveInScratch = true; }
+    if (msdTiles) { tp.numPasses = 1; tp.shift0 = (int)lowBits; tp.leaveInScratch = true; tp.pairTiles = tilePairsEnabled(); }
     GSM_CUDA(launchSort(s, tp), "tile sort");
     if (msdTiles)
         GSM_CUDA(launchTileLocalSort(s, res.tileIds[1], (const uint32_t*)res.instIdx[1], res.tileIds[0], (uint32_t*)res.instIdx[0],

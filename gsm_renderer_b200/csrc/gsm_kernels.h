@@ -67,6 +67,7 @@ struct SortPlan {
     bool histogramReady; // hist filled and status/gstatus zeroed by earlier kernels of the frame (fused); else a histogram kernel runs
     int shift0 = 0;      // digit of pass p = (key >> (shift0 + 8p)) & 0xFF
     bool leaveInScratch = false;  // odd pass counts: do not copy the result back from (k1, v1) (the MSD tile sort's local pass reads it there)
+    bool pairTiles = false;       // one 16-bit pass left in scratch: two consecutive tiles per CTA and one count exchange (onesweep_pair_kernel)
 };
 uint32_t sortTileSize(int keyBits, bool large);
 cudaError_t launchSort(cudaStream_t s, const SortPlan& p);

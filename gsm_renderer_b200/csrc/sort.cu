@@ -372,6 +372,205 @@ __global__ void __launch_bounds__(kSortThreads, ((sizeof(KeyT) == 4 && ITEMS == 
     }
 }
 
+// ---- the MSD tile sort's pass (tilesort.cu) on frames of a few million instances: TWO consecutive tiles per CTA, ONE exchange.
+// A 16-bit pass over 2.9 M pairs is 710 tiles on 444 resident CTAs: two waves of a latency chain that costs ~17 us however few keys
+// it moves (ticket, loads, 128 ballots, publish, wait for every predecessor, scatter). Here a CTA takes a UNIT of two consecutive
+// tiles, ranks them one after the other into two shared-memory staging buffers (48 KB), publishes the unit's per-digit counts once,
+// waits once, and writes both tiles out: one wave, one wait. Everything else -- ranking in index order, direct summation of the
+// predecessors' counts behind arrival masks for few units, two-level look-back for many, tickets after the dependent-launch wait --
+// is onesweep_pass_kernel's, with "tile" read as "unit" in the status words.
+template <int ITEMS>
+__global__ void __launch_bounds__(kSortThreads, 3) onesweep_pair_kernel(const unsigned short* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                                        unsigned short* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
+                                                                        const uint32_t* __restrict__ countPtr, uint32_t countCap,
+                                                                        const uint32_t* __restrict__ digitHist, uint32_t* status,
+                                                                        uint32_t* gstatus, uint32_t* ticket, int shift) {
+    typedef unsigned short KeyT;
+    constexpr int TILE = kSortThreads * ITEMS;
+    constexpr uint32_t SENTINEL = 0xFFFFu;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_dyn);                      // [2][TILE]
+    KeyT* s_keys = reinterpret_cast<KeyT*>(s_dyn + 2 * TILE * sizeof(uint32_t));  // [2][TILE]
+    __shared__ uint32_t s_warpHist[kSortWarps][256];
+    __shared__ uint32_t s_binExcl[2][256];     // tile-local exclusive offset of each digit, per tile of the unit
+    __shared__ uint32_t s_globalBase[2][256];  // global position of the tile's first element of each digit, minus s_binExcl
+    __shared__ uint32_t s_histPrefix[256];
+    __shared__ uint32_t s_scan[9];
+    __shared__ uint32_t s_unit;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    pdlLaunchDependents();
+    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
+    pdlWait();
+    uint32_t firstTicket = 0;
+    if (tid == 0) firstTicket = atomicAdd(ticket, 1u);
+    const uint32_t digitTotal = ldAfterWait(digitHist + tid);
+    const uint32_t count = min(ldAfterWait(countPtr), countCap);
+    const uint32_t numTiles = (count + TILE - 1) / TILE;
+    const uint32_t numUnits = (numTiles + 1u) / 2u;
+    if (tid == 0) s_unit = firstTicket;
+    __syncthreads();
+    bool firstTile = true;
+    const uint32_t sentinelDigit = (SENTINEL >> shift) & 0xFFu;
+
+    while (true) {
+        const uint32_t unit = s_unit;
+        if (unit >= numUnits) break;
+        uint32_t vc0 = 0u, vc1 = 0u;   // thread d: valid keys of digit d in the unit's first / second tile
+#pragma unroll 1
+        for (uint32_t k = 0; k < 2u; ++k) {
+            const uint32_t tile = unit * 2u + k;
+            if (tile >= numTiles) { s_binExcl[1][tid] = 0u; break; }   // uniform: the last unit of an odd tile count
+            const uint32_t base = tile * TILE;
+            const uint32_t tileValid = min((uint32_t)TILE, count - base);
+            uint32_t key[ITEMS], rank[ITEMS], val[ITEMS];
+            const uint32_t warpBase = warp * ITEMS * 32u + lane;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t j = warpBase + i * 32u;
+                key[i] = (j < tileValid) ? (uint32_t)keysIn[base + j] : SENTINEL;
+            }
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t j = warpBase + i * 32u;
+                val[i] = (j < tileValid) ? valsIn[base + j] : 0u;
+            }
+            if (firstTile) {  // uniform; under the loads just issued
+                uint32_t total;
+                s_histPrefix[tid] = block_exclusive_scan_256(digitTotal, s_scan, total);
+                firstTile = false;
+            }
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t d = (key[i] >> shift) & 0xFFu;
+                unsigned peers = 0xFFFFFFFFu;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const bool bit = (d >> b) & 1u;
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
+                    peers &= bit ? bal : ~bal;
+                }
+                const uint32_t lower = __popc(peers & ((1u << lane) - 1u));
+                uint32_t pre = 0;
+                if (lower == 0) pre = atomicAdd(&s_warpHist[warp][d], (uint32_t)__popc(peers));
+                pre = __shfl_sync(0xFFFFFFFFu, pre, __ffs(peers) - 1);
+                rank[i] = pre + lower;
+            }
+            __syncthreads();
+            uint32_t binCount = 0;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const uint32_t c = s_warpHist[w][tid];
+                s_warpHist[w][tid] = binCount;
+                binCount += c;
+            }
+            const uint32_t validCount = binCount - ((tid == sentinelDigit) ? (TILE - tileValid) : 0u);
+            if (k == 0u) vc0 = validCount; else vc1 = validCount;
+            uint32_t total;
+            const uint32_t binExcl = block_exclusive_scan_256(binCount, s_scan, total);
+            s_binExcl[k][tid] = binExcl;
+            __syncthreads();
+            KeyT* sk = s_keys + k * TILE;
+            uint32_t* sv = s_vals + k * TILE;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t d = (key[i] >> shift) & 0xFFu;
+                const uint32_t pos = rank[i] + s_binExcl[k][d] + s_warpHist[warp][d];  // position inside the tile
+                sk[pos] = (KeyT)key[i];
+                sv[pos] = val[i];
+            }
+            __syncthreads();
+            for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_warpHist[0][0])[i] = 0;
+            __syncthreads();
+        }
+
+        const uint32_t validCount = vc0 + vc1;
+        uint32_t* myStatus = status + (size_t)unit * 256u + tid;
+        uint32_t exclusive = 0;
+        const uint32_t group = unit / kLookGroup;
+        uint32_t* myGroup = gstatus + (size_t)group * 256u + tid;
+        if (numUnits <= kFlatMaxTiles) {
+            const uint32_t numGroups = (numUnits + kLookGroup - 1u) / kLookGroup;
+            uint32_t* arriveMask = gstatus + (size_t)numGroups * 256u;
+            st_status32(myStatus, validCount);
+            if ((group + 1u) * kLookGroup < numUnits) atomicAdd(myGroup, validCount);  // RED: result unused
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicOr(arriveMask + group, 1u << (unit % kLookGroup));
+            if (tid < 32u) {
+                const uint32_t mine = (1u << (unit % kLookGroup)) - 1u;
+                bool ok;
+                do {
+                    ok = true;
+                    for (uint32_t g = lane; g <= group; g += 32u) {
+                        const uint32_t m = ld_status32(arriveMask + g);
+                        const uint32_t need = g < group ? 0xFFFFu : mine;
+                        ok = ok && (m & need) == need;
+                    }
+                } while (!__all_sync(0xFFFFFFFFu, ok));
+                __threadfence();
+            }
+            __syncthreads();
+            const uint32_t groupStart = group * kLookGroup, nPred = unit - groupStart;
+            for (uint32_t b = 0; b < group; b += kLookBatch) {
+                uint32_t sv[kLookBatch];
+#pragma unroll
+                for (int q = 0; q < kLookBatch; ++q)
+                    sv[q] = (b + q < group) ? ld_status32(gstatus + (size_t)(b + q) * 256u + tid) : 0u;
+#pragma unroll
+                for (int q = 0; q < kLookBatch; ++q) exclusive += sv[q];
+            }
+            for (uint32_t b = 0; b < nPred; b += kLookBatch) {
+                uint32_t sv[kLookBatch];
+#pragma unroll
+                for (int q = 0; q < kLookBatch; ++q)
+                    sv[q] = (b + q < nPred) ? ld_status32(status + (size_t)(groupStart + b + q) * 256u + tid) : 0u;
+#pragma unroll
+                for (int q = 0; q < kLookBatch; ++q) exclusive += sv[q];
+            }
+        } else {
+            // many units: chained look-back over the units, one thread per digit (flat: these frames are rare on this path)
+            if (unit == 0) {
+                st_status32(myStatus, kStatusInclusive | validCount);
+            } else {
+                st_status32(myStatus, kStatusAggregate | validCount);
+                int look = (int)unit - 1;
+                bool done = false;
+                while (!done) {
+                    const uint32_t sw = ld_status32(status + (size_t)look * 256u + tid);
+                    if (sw & kStatusInclusive) { exclusive += sw & kStatusValueMask; done = true; }
+                    else if (sw & kStatusAggregate) { exclusive += sw & kStatusValueMask; look--; }
+                }
+                st_status32(myStatus, kStatusInclusive | (exclusive + validCount));
+            }
+        }
+        s_globalBase[0][tid] = s_histPrefix[tid] + exclusive - s_binExcl[0][tid];
+        s_globalBase[1][tid] = s_histPrefix[tid] + exclusive + vc0 - s_binExcl[1][tid];
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t k = 0; k < 2u; ++k) {
+            const uint32_t tile = unit * 2u + k;
+            if (tile >= numTiles) break;
+            const uint32_t tileValid = min((uint32_t)TILE, count - tile * TILE);
+            const KeyT* sk = s_keys + k * TILE;
+            const uint32_t* sv = s_vals + k * TILE;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t j = tid + i * kSortThreads;
+                if (j < tileValid) {
+                    const uint32_t kk = sk[j];
+                    const uint32_t dst = s_globalBase[k][(kk >> shift) & 0xFFu] + j;
+                    keysOut[dst] = (KeyT)kk;
+                    valsOut[dst] = sv[j];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(ticket, 1u);
+        __syncthreads();
+    }
+}
+
 template <typename KeyT, int ITEMS>
 static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
     if (p.numPasses <= 0) return cudaSuccess;
@@ -383,6 +582,19 @@ static cudaError_t runSort(cudaStream_t s, const SortPlan& p) {
         case 2: launchChained(radix_histogram_kernel<KeyT, 2, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
         case 3: launchChained(radix_histogram_kernel<KeyT, 3, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
         default: launchChained(radix_histogram_kernel<KeyT, 4, ITEMS>, gridHist, 256, s, k0, p.countPtr, p.countCap, p.hist, p.status, p.gstatus, p.tilesCap); break;
+    }
+    if (sizeof(KeyT) == 2 && p.pairTiles && p.numPasses == 1 && p.gatherSrc == nullptr) {   // the MSD tile sort's pass: two tiles per CTA, one exchange
+        constexpr size_t smem = 2u * (size_t)kSortThreads * ITEMS * (sizeof(uint32_t) + sizeof(unsigned short));
+        static int pairBlocksPerSM = 0;
+        if (pairBlocksPerSM == 0) {
+            cudaError_t e = cudaFuncSetAttribute(onesweep_pair_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pairBlocksPerSM, onesweep_pair_kernel<ITEMS>, kSortThreads, smem);
+            if (pairBlocksPerSM < 1) pairBlocksPerSM = 1;
+        }
+        launchChainedSmem(onesweep_pair_kernel<ITEMS>, p.numSMs * pairBlocksPerSM, kSortThreads, s, smem, (const unsigned short*)k0, (const uint32_t*)p.v0,
+                          (unsigned short*)k1, p.v1, p.countPtr, p.countCap, (const uint32_t*)p.hist, p.status, p.gstatus, p.tickets, p.shift0);
+        return cudaGetLastError();
     }
     static int blocksPerSM = 0;  // per template instance
     if (blocksPerSM == 0) {
