@@ -508,11 +508,14 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
         __syncthreads();
         if (!done) {
             for (uint32_t j = 0; j < n; ++j) {
-                const bool closedL = !doL || quadClosed(qL.T0, qL.T1, thr), closedR = !doR || quadClosed(qR.T0, qR.T1, thr);
-                if (closedL && closedR) { done = true; break; }  // DFS.metal:1868-1871
+                // Most entries of a stereo list do nothing on this half of the tile (the lists hold every tile of the union box):
+                // their flags are looked at FIRST. The exit test of DFS.metal:1868-1871 runs before every entry in the reference;
+                // running it only before the entries that can change a pixel ends the thread before the same accumulations.
                 const uint32_t flags = s_valid[j];
-                if (!(flags & 1u)) continue;
                 const uint32_t wf = flags >> (2u * (tid >> 5));  // this warp's pair of bits
+                if (!(flags & 1u) || (wf & 6u) == 6u) continue;
+                const bool closedL = !doL || quadClosed(qL.T0, qL.T1, thr), closedR = !doR || quadClosed(qR.T0, qR.T1, thr);
+                if (closedL && closedR) { done = true; break; }
                 const bool skipL = closedL || (wf & 2u), skipR = closedR || (wf & 4u);
                 if (skipL && skipR) continue;  // nothing this splat can change on this tile
                 const uint4 ra = s_rec[j][0], rb = s_rec[j][1];
@@ -525,6 +528,8 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
                 stereoEye<EXPM>(qR, !skipR, *reinterpret_cast<const __half2*>(&ra.w), *reinterpret_cast<const __half2*>(&rb.x),
                           __low2half(*reinterpret_cast<const __half2*>(&rb.y)), op, cr, cg, cb, px, py0, py1);
             }
+            // the exit test once more at the end of the chunk, so that the vote below sees quads closed by its last entries
+            if (!done && (!doL || quadClosed(qL.T0, qL.T1, thr)) && (!doR || quadClosed(qR.T0, qR.T1, thr))) done = true;
         }
         if (__syncthreads_and(done ? 1 : 0)) break;
     }

@@ -407,7 +407,10 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pair_kernel(const un
     const uint32_t digitTotal = ldAfterWait(digitHist + tid);
     const uint32_t count = min(ldAfterWait(countPtr), countCap);
     const uint32_t numTiles = (count + TILE - 1) / TILE;
-    const uint32_t numUnits = (numTiles + 1u) / 2u;
+    // two tiles per unit only where that makes ONE wave out of two: more tiles than resident CTAs, at most twice as many. Fewer
+    // tiles are one wave already; with more, a CTA's second unit would queue behind a whole pair (stereo C4, 977 tiles: 91 -> 105 us)
+    const uint32_t tpu = (numTiles > gridDim.x && (numTiles + 1u) / 2u <= gridDim.x) ? 2u : 1u;
+    const uint32_t numUnits = (numTiles + tpu - 1u) / tpu;
     if (tid == 0) s_unit = firstTicket;
     __syncthreads();
     bool firstTile = true;
@@ -419,8 +422,8 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pair_kernel(const un
         uint32_t vc0 = 0u, vc1 = 0u;   // thread d: valid keys of digit d in the unit's first / second tile
 #pragma unroll 1
         for (uint32_t k = 0; k < 2u; ++k) {
-            const uint32_t tile = unit * 2u + k;
-            if (tile >= numTiles) { s_binExcl[1][tid] = 0u; break; }   // uniform: the last unit of an odd tile count
+            const uint32_t tile = unit * tpu + k;
+            if (k >= tpu || tile >= numTiles) { s_binExcl[1][tid] = 0u; break; }   // uniform: one tile per unit, or the last unit of an odd tile count
             const uint32_t base = tile * TILE;
             const uint32_t tileValid = min((uint32_t)TILE, count - base);
             uint32_t key[ITEMS], rank[ITEMS], val[ITEMS];
@@ -548,8 +551,8 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pair_kernel(const un
         s_globalBase[1][tid] = s_histPrefix[tid] + exclusive + vc0 - s_binExcl[1][tid];
         __syncthreads();
 #pragma unroll 1
-        for (uint32_t k = 0; k < 2u; ++k) {
-            const uint32_t tile = unit * 2u + k;
+        for (uint32_t k = 0; k < tpu; ++k) {
+            const uint32_t tile = unit * tpu + k;
             if (tile >= numTiles) break;
             const uint32_t tileValid = min((uint32_t)TILE, count - tile * TILE);
             const KeyT* sk = s_keys + k * TILE;
