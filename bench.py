@@ -50,6 +50,7 @@ WORKLOADS = {
     "C1": (50_000, 1, "float32", 1920, 1080, 0.015, "C1: 50k Gaussians SH1 float32, 1920x1080 mono"),
     "C2": (1_000_000, 3, "float16", 1920, 1080, 0.015, "C2: 1M Gaussians SH3 float16, 1920x1080 mono"),
     "C5v": (3_000_000, 3, "float16", 1280, 720, 0.012, "C5 (one view): 3M Gaussians SH3 float16, 1280x720"),
+    "C3": (6_000_000, 3, "float16", 3840, 2160, 0.008, "C3 (one GPU): 6M Gaussians SH3 float16, 3840x2160 mono"),
 }
 NEAR, FAR = 0.1, 100.0  # PLYBenchmarkTests.swift:60-62
 KERNELS_PER_FRAME = 10  # project, compaction (+header), depth bucket rank + scatter + local sort, scan+expand, one tile onesweep pass + chunk count + chunk place (writes the ranges), blend

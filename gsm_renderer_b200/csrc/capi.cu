@@ -288,6 +288,13 @@ bool tileSortMsdEnabled() {
     static const bool on = [] { const char* e = getenv("GSM_TILE_MSD"); return !(e && e[0] == '0'); }();
     return on;
 }
+// Frames of at least this many Gaussians keep the two LSD passes (GSM_TILE_MSD_MAX in the environment: A/B measurement). No limit
+// by default: most-significant-digit first also wins on the large frames (C5 view, 3 M Gaussians: tile sort + ranges 123 -> 99 us;
+// C3, 6 M at 4K, 18.6 M instances: 364 -> 329 us; profiles/r2_tile_msd_large_ab.txt) -- the range kernel disappears there too.
+uint32_t tileSortMsdMaxGaussians() {
+    static const uint32_t v = [] { const char* e = getenv("GSM_TILE_MSD_MAX"); return e ? (uint32_t)strtoul(e, nullptr, 10) : 0xFFFFFFFFu; }();
+    return v;
+}
 // GSM_TILE_PAIRS=0 in the environment keeps the MSD pass on one tile per CTA (A/B measurement)
 bool tilePairsEnabled() {
     static const bool on = [] { const char* e = getenv("GSM_TILE_PAIRS"); return !(e && e[0] == '0'); }();
@@ -357,7 +364,7 @@ gsm_status encodeSortExpandRange(gsm_renderer* r, Resources& res, cudaStream_t s
     // 16-bit ids of 9..16 bits on frames small enough for the direct-summation prefix: one pass on the high byte + a local
     // pass per bucket that also writes the tile ranges (tilesort.cu); else the LSD passes + the range kernel
     const uint32_t lowBits = tileSortLowBits(tilesX * tilesY);
-    const bool msdTiles = tileSortMsdEnabled() && tile16 && tilePasses == 2 && lowBits > 0u && !largeSort(res.frameGaussians);
+    const bool msdTiles = tileSortMsdEnabled() && tile16 && tilePasses == 2 && lowBits > 0u && res.frameGaussians < tileSortMsdMaxGaussians();
     // stage 5
     GSM_CUDA(launchCreateInstances(s, stereo, tile16, res.primIdx[0], res.offsets, res.hitMask, res.offsets, res.scanStatus, res.scanGroups, &res.fs->ticketScan, res.bounds, res.renderData, res.tileIds[0],
                                    res.instIdx[0], res.header, tilesX, res.maxInstances, res.maxGaussians, &res.fs->hist[4][0],

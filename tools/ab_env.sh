@@ -1,9 +1,11 @@
 #!/bin/bash
-# A/B by environment: tools/ab_env.sh VAR=VAL ...   (each run: bench 20 steps; then the default)
+# A/B by environment on a bench workload: tools/ab_env.sh [-w WORKLOAD] VAR=VAL ...   (one run per setting, then the default)
+W=C2
+if [ "${1:-}" == "-w" ]; then W=$2; shift 2; fi
 for kv in "$@" ""; do
   name=${kv:-default}
   if [ -n "$kv" ]; then export "$kv"; fi
-  python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_ab.json 2>/dev/null
+  python bench.py --workload $W --steps 20 --warmup 5 --no-cpu-baseline --no-modes > gpurun_out/bench_ab.json 2>/dev/null
   python - "$name" <<'PY'
 import json, sys
 d = json.loads(open("gpurun_out/bench_ab.json").read().strip().splitlines()[-1])
