@@ -532,17 +532,37 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pair_kernel(const un
                 for (int q = 0; q < kLookBatch; ++q) exclusive += sv[q];
             }
         } else {
-            // many units: chained look-back over the units, one thread per digit (flat: these frames are rare on this path)
+            // Many units (streaming sizes): decoupled look-back over the units, one thread per digit, eight status words per round
+            // trip. In the steady state the predecessor is already inclusive and the walk is one load. (The two-level form of
+            // onesweep_pass_kernel measured slower here: C3 tile sort 339 us against 326 us.)
             if (unit == 0) {
                 st_status32(myStatus, kStatusInclusive | validCount);
             } else {
                 st_status32(myStatus, kStatusAggregate | validCount);
-                int look = (int)unit - 1;
                 bool done = false;
-                while (!done) {
+                int look = (int)unit - 1;
+                {
                     const uint32_t sw = ld_status32(status + (size_t)look * 256u + tid);
                     if (sw & kStatusInclusive) { exclusive += sw & kStatusValueMask; done = true; }
                     else if (sw & kStatusAggregate) { exclusive += sw & kStatusValueMask; look--; }
+                }
+                while (!done) {
+                    uint32_t sv[kLookBatch];
+#pragma unroll
+                    for (int q = 0; q < kLookBatch; ++q) {
+                        const int t = look - q;
+                        sv[q] = (t >= 0) ? ld_status32(status + (size_t)t * 256u + tid) : 0u;
+                    }
+                    int consumed = 0;
+#pragma unroll
+                    for (int q = 0; q < kLookBatch; ++q) {
+                        if (!done && consumed == q && look - q >= 0) {  // only a contiguous run of published words
+                            const uint32_t sw = sv[q];
+                            if (sw & kStatusInclusive) { exclusive += sw & kStatusValueMask; done = true; }
+                            else if (sw & kStatusAggregate) { exclusive += sw & kStatusValueMask; consumed++; }
+                        }
+                    }
+                    look -= consumed;
                 }
                 st_status32(myStatus, kStatusInclusive | (exclusive + validCount));
             }
