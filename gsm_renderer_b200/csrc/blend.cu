@@ -92,9 +92,9 @@ __device__ __forceinline__ bool quadClosed(const __half2& T0, const __half2& T1,
 }
 
 __device__ __forceinline__ void storePixelRow(__half* color, __half* depth, uint32_t width, uint32_t height, uint32_t x, uint32_t y,
-                                              __half2 r, __half2 g, __half2 b, __half2 a, __half2 d) {
-    if (y >= height || x >= width) return;
-    const size_t o = (size_t)y * width + x;
+                                              __half2 r, __half2 g, __half2 b, __half2 a, __half2 d, uint32_t pitch = 0u) {
+    if (y >= height || x >= width) return;   // `width` x `height` bound the stores; rows are `pitch` pixels apart (0 = width)
+    const size_t o = (size_t)y * (pitch ? pitch : width) + x;
     uint2 v;  // 8-byte pixel stores: always aligned, and 8 lanes x 2 pixels still cover one 128-byte line per row
     v.x = h2bits(__halves2half2(__low2half(r), __low2half(g)));
     v.y = h2bits(__halves2half2(__low2half(b), __low2half(a)));
@@ -691,6 +691,142 @@ __global__ void __launch_bounds__(64) global_render_kernel(GlobalFrame f, uint32
     }
 }
 
+// ---- globalRender in the mono blend's form: persistent CTAs (tile groups of 64 threads on a ticket), the 32-byte record written
+// once per Gaussian by the tile count, per-column / per-row terms of p staged once per (tile, splat), staging loads issued one and
+// two chunks ahead. A thread owns 4 x 2 pixels = two 2 x 2 quads side by side; its exit test looks at all eight transmittances and
+// a splat is skipped when all eight alphas are zero, as in the reference (accumulating a quad whose four alphas are +0 changes
+// nothing: w = +0, fma(c, +0, acc) = acc for the non-negative accumulators, T * (1 - 0) = T). C2 cloud: 295 -> see profiles.
+struct StagedSplatG {
+    uint2 col[16];  // per x pair k of the 32 columns: {T0(2k), T0(2k+1)}, {dx(2k), dx(2k+1)}
+    uint2 row[8];   // per y pair k of the 16 rows: {dy*dy(2k), dy*dy(2k+1)}, {dy(2k), dy(2k+1)}
+    uint4 m0;       // cxy2|cxy2, op|op, r|r, g|g
+    uint4 m1;       // b|b, depth|depth, unused, cyy|cyy
+};
+constexpr int kGlobalGroups = 4;
+constexpr size_t kGlobalSmemBytes = (size_t)kGlobalGroups * (kBlendChunk + 1) * sizeof(StagedSplatG);
+
+template <int EXPM>
+__global__ void __launch_bounds__(kBlendThreads * kGlobalGroups, 2) global_render_staged_kernel(GlobalFrame f, uint32_t width, uint32_t height,
+                                                                                                 uint32_t maxWidth, uint32_t maxHeight,
+                                                                                                 __half* __restrict__ color,
+                                                                                                 __half* __restrict__ depth) {
+    extern __shared__ uint4 s_raw[];
+    __shared__ uint32_t s_tileOf[kGlobalGroups];
+    const unsigned group = threadIdx.x >> 6, tid = threadIdx.x & 63u;
+    StagedSplatG* s_sp = reinterpret_cast<StagedSplatG*>(s_raw) + group * (kBlendChunk + 1);
+    const unsigned lx = tid & 7u, ly = tid >> 3;
+    const uint32_t numTiles = f.tilesX * f.tilesY;
+    const __half thr = __float2half_rn(1.0f / 255.0f);
+    const __half2 zero = h2(0.0f), one = h2(1.0f), h099 = h2(0.99f);
+    const uint32_t W = min(width, maxWidth), H = min(height, maxHeight);   // texture writes outside the target are dropped
+
+    while (true) {
+        if (tid == 0) s_tileOf[group] = atomicAdd(f.renderTicket, 1u);
+        groupBarrier(group);
+        const uint32_t tile = s_tileOf[group];
+        if (tile >= numTiles) break;
+        const uint32_t tileX = tile % f.tilesX, tileY = tile / f.tilesX;
+        const GSMGaussianHeader hdr = f.tileHeaders[tile];
+        const uint32_t start = hdr.offset, count = hdr.count;
+        const uint32_t baseX = tileX * 32u + lx * 4u, baseY = tileY * 16u + ly * 2u;
+
+        QuadState qa, qb;   // columns baseX, baseX + 1 and baseX + 2, baseX + 3
+        qa.T0 = qa.T1 = one;
+        qa.r0 = qa.g0 = qa.b0 = qa.d0 = qa.r1 = qa.g1 = qa.b1 = qa.d1 = zero;
+        qb = qa;
+        bool done = false;
+
+        int32_t giCur = tid < count ? __ldg(f.sortedIndices + start + tid) : -1;
+        int32_t giNext = kBlendChunk + tid < count ? __ldg(f.sortedIndices + start + kBlendChunk + tid) : -1;
+        uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+        if (giCur >= 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(f.blendSplats + giCur);
+            ra = __ldg(src); rb = __ldg(src + 1);
+        }
+        for (uint32_t base = 0; base < count; base += kBlendChunk) {
+            const uint32_t n = min((uint32_t)kBlendChunk, count - base);
+            if (tid < n) {
+                StagedSplatG& sp = s_sp[tid];
+                if (giCur >= 0) {
+                    const __half2 mean = *reinterpret_cast<const __half2*>(&ra.x);
+                    const __half2 cxx_cyy = *reinterpret_cast<const __half2*>(&ra.y);
+                    const __half2 cxy2_op = *reinterpret_cast<const __half2*>(&ra.z);
+                    const __half2 rg = *reinterpret_cast<const __half2*>(&ra.w);
+                    const __half2 b_d = *reinterpret_cast<const __half2*>(&rb.x);
+                    const __half2 mx = __low2half2(mean), my = __high2half2(mean);
+                    const __half2 cxx = __low2half2(cxx_cyy), cyy = __high2half2(cxx_cyy);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const __half2 px = __halves2half2(__uint2half_rn(tileX * 32u + 2u * k), __uint2half_rn(tileX * 32u + 2u * k + 1u));
+                        const __half2 dx = __hsub2_rn(px, mx);
+                        sp.col[k] = make_uint2(h2bits(__hmul2_rn(__hmul2_rn(dx, dx), cxx)), h2bits(dx));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const __half2 py = __halves2half2(__uint2half_rn(tileY * 16u + 2u * k), __uint2half_rn(tileY * 16u + 2u * k + 1u));
+                        const __half2 dy = __hsub2_rn(py, my);
+                        sp.row[k] = make_uint2(h2bits(__hmul2_rn(dy, dy)), h2bits(dy));
+                    }
+                    sp.m0 = make_uint4(h2bits(__low2half2(cxy2_op)), h2bits(__high2half2(cxy2_op)), h2bits(__low2half2(rg)),
+                                       h2bits(__high2half2(rg)));
+                    sp.m1 = make_uint4(h2bits(__low2half2(b_d)), h2bits(__high2half2(b_d)), 0u, h2bits(cyy));
+                } else {
+                    uint4* w = reinterpret_cast<uint4*>(&sp);   // invalid instance: opacity 0 makes every alpha +0
+#pragma unroll
+                    for (int k = 0; k < (int)(sizeof(StagedSplatG) / 16); ++k) w[k] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            groupBarrier(group);
+            giCur = giNext;
+            if (giCur >= 0) {
+                const uint4* src = reinterpret_cast<const uint4*>(f.blendSplats + giCur);
+                ra = __ldg(src); rb = __ldg(src + 1);
+            }
+            giNext = base + 2u * kBlendChunk + tid < count ? __ldg(f.sortedIndices + start + base + 2u * kBlendChunk + tid) : -1;
+            if (!done) {
+                for (uint32_t j = 0; j < n; ++j) {
+                    // GlobalShaders.metal:1081-1084, before every list entry: all eight pixels of the thread
+                    if (quadClosed(qa.T0, qa.T1, thr) && quadClosed(qb.T0, qb.T1, thr)) { done = true; break; }
+                    const StagedSplatG& sp = s_sp[j];
+                    const uint4 c = *reinterpret_cast<const uint4*>(&sp.col[2u * lx]);   // columns of quad a (x, y), of quad b (z, w)
+                    const uint2 r = sp.row[ly];
+                    const uint4 m0 = sp.m0, m1 = sp.m1;
+                    const __half2 t0a = *reinterpret_cast<const __half2*>(&c.x), dxa = *reinterpret_cast<const __half2*>(&c.y);
+                    const __half2 t0b = *reinterpret_cast<const __half2*>(&c.z), dxb = *reinterpret_cast<const __half2*>(&c.w);
+                    const __half2 dy2p = *reinterpret_cast<const __half2*>(&r.x), dyp = *reinterpret_cast<const __half2*>(&r.y);
+                    const __half2 cxy2 = *reinterpret_cast<const __half2*>(&m0.x), op = *reinterpret_cast<const __half2*>(&m0.y);
+                    const __half2 cyy = *reinterpret_cast<const __half2*>(&m1.w);
+                    const __half2 dy0 = __low2half2(dyp), dy1 = __high2half2(dyp);
+                    const __half2 in0a = __hfma2(__low2half2(dy2p), cyy, t0a), in1a = __hfma2(__high2half2(dy2p), cyy, t0a);
+                    const __half2 in0b = __hfma2(__low2half2(dy2p), cyy, t0b), in1b = __hfma2(__high2half2(dy2p), cyy, t0b);
+                    const __half2 p0a = __hfma2(__hmul2_rn(dxa, dy0), cxy2, in0a), p1a = __hfma2(__hmul2_rn(dxa, dy1), cxy2, in1a);
+                    const __half2 p0b = __hfma2(__hmul2_rn(dxb, dy0), cxy2, in0b), p1b = __hfma2(__hmul2_rn(dxb, dy1), cxy2, in1b);
+                    __half2 e0a, e1a, e0b, e1b;
+                    expNegHalfPairs<EXPM>(p0a, p1a, e0a, e1a);
+                    expNegHalfPairs<EXPM>(p0b, p1b, e0b, e1b);
+                    const __half2 a0a = __hmin2(__hmul2_rn(op, e0a), h099), a1a = __hmin2(__hmul2_rn(op, e1a), h099);
+                    const __half2 a0b = __hmin2(__hmul2_rn(op, e0b), h099), a1b = __hmin2(__hmul2_rn(op, e1b), h099);
+                    const bool useA = ((h2bits(a0a) | h2bits(a1a)) & 0x7FFF7FFFu) != 0u, useB = ((h2bits(a0b) | h2bits(a1b)) & 0x7FFF7FFFu) != 0u;
+                    const __half2 cr = *reinterpret_cast<const __half2*>(&m0.z), cg = *reinterpret_cast<const __half2*>(&m0.w);
+                    const __half2 cb = *reinterpret_cast<const __half2*>(&m1.x), cd = *reinterpret_cast<const __half2*>(&m1.y);
+                    if (useA) accumulate(qa, a0a, a1a, cr, cg, cb, cd, true);
+                    if (useB) accumulate(qb, a0b, a1b, cr, cg, cb, cd, true);
+                }
+            }
+            if (groupAll(group, done)) break;
+        }
+
+        __half2 al0a, al1a, al0b, al1b;
+        if (count > 0) { al0a = __hsub2_rn(one, qa.T0); al1a = __hsub2_rn(one, qa.T1); al0b = __hsub2_rn(one, qb.T0); al1b = __hsub2_rn(one, qb.T1); }
+        else { al0a = al1a = al0b = al1b = one; }
+        storePixelRow(color, depth, W, H, baseX, baseY, qa.r0, qa.g0, qa.b0, al0a, qa.d0, width);
+        storePixelRow(color, depth, W, H, baseX, baseY + 1u, qa.r1, qa.g1, qa.b1, al1a, qa.d1, width);
+        storePixelRow(color, depth, W, H, baseX + 2u, baseY, qb.r0, qb.g0, qb.b0, al0b, qb.d0, width);
+        storePixelRow(color, depth, W, H, baseX + 2u, baseY + 1u, qb.r1, qb.g1, qb.b1, al1b, qb.d1, width);
+        groupBarrier(group);  // the staging buffer and s_tileOf are reused by the next tile
+    }
+}
+
 // ---- which form of exp(-0.5h * p) the blend kernels of a device run (see expNegHalfPairs): decided once per device by comparing
 // the tuned XU-pipe form with the canonical polynomial on all 65 536 half inputs, in both lanes and in both pair slots. A device
 // on which any input differs (another MUFU implementation) runs the polynomial; GSM_BLEND_EXP=poly forces it (A/B, tests).
@@ -741,9 +877,27 @@ static bool tunedExpOnCurrentDevice() {
 }
 
 cudaError_t launchGlobalRender(cudaStream_t s, const GlobalFrame& f, uint32_t width, uint32_t height, uint32_t maxWidth, uint32_t maxHeight,
-                               __half* color, __half* depth) {
-    if (tunedExpOnCurrentDevice()) global_render_kernel<1><<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
-    else global_render_kernel<0><<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
+                               __half* color, __half* depth, int numSMs) {
+    // GSM_GLOBAL_RENDER=simple keeps the first form (one CTA per tile, conic per (tile, splat)): A/B measurement
+    static const bool simple = [] { const char* e = getenv("GSM_GLOBAL_RENDER"); return e && strcmp(e, "simple") == 0; }();
+    const bool tuned = tunedExpOnCurrentDevice();
+    if (simple) {
+        if (tuned) global_render_kernel<1><<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
+        else global_render_kernel<0><<<f.tilesX * f.tilesY, 64, 0, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
+        return cudaGetLastError();
+    }
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(global_render_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGlobalSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(global_render_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGlobalSmemBytes);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    const uint32_t numTiles = f.tilesX * f.tilesY;
+    uint32_t grid = (numTiles + kGlobalGroups - 1) / kGlobalGroups;
+    if (grid > (uint32_t)numSMs * 2u) grid = (uint32_t)numSMs * 2u;
+    if (tuned) global_render_staged_kernel<1><<<grid, kBlendThreads * kGlobalGroups, kGlobalSmemBytes, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
+    else global_render_staged_kernel<0><<<grid, kBlendThreads * kGlobalGroups, kGlobalSmemBytes, s>>>(f, width, height, maxWidth, maxHeight, color, depth);
     return cudaGetLastError();
 }
 

@@ -1261,6 +1261,7 @@ static gsm_status ensureGlobalResources(gsm_renderer* r) {
     const size_t oKeys = take((size_t)A * 4), oIdx = take((size_t)A * 4);
     const size_t oHeaders = take((size_t)T * 8), oActive = take((size_t)T * 4), oHeader = take(sizeof(GlobalHeader));
     const size_t oSort = take(L.total);
+    const size_t oBlend = take((size_t)G * sizeof(BlendSplat)), oTicket = take(256);
     cudaError_t e = cudaMalloc((void**)&r->globalArena, off);
     if (e != cudaSuccess) { r->globalArena = nullptr; return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "GlobalRenderer arena", e); }
     e = cudaMemset(r->globalArena, 0, off);
@@ -1272,6 +1273,7 @@ static gsm_status ensureGlobalResources(gsm_renderer* r) {
     f.offsets = (uint32_t*)(a + oOffsets); f.blockSums = (uint32_t*)(a + oBlockSums); f.sortKeys = (uint32_t*)(a + oKeys);
     f.sortedIndices = (int32_t*)(a + oIdx); f.tileHeaders = (GSMGaussianHeader*)(a + oHeaders); f.activeTiles = (uint32_t*)(a + oActive);
     f.header = (GlobalHeader*)(a + oHeader);
+    f.blendSplats = (BlendSplat*)(a + oBlend); f.renderTicket = (uint32_t*)(a + oTicket);
     f.capGaussians = G; f.maxAssignments = A; f.tileW = tileW; f.tileH = tileH; f.tilesX = tilesX; f.tilesY = tilesY;
     r->globalSortScratch = a + oSort;
     return GSM_OK;
@@ -1298,21 +1300,22 @@ gsm_status gsm_render_global(gsm_renderer* r, void* stream, void* color, void* d
     GSM_CUDA(launchGlobalCompact(s, f, gaussianCount), "global visibility compaction");
     GSM_CUDA(launchGlobalTileCount(s, f, gaussianCount), "global tile count");
     GSM_CUDA(launchGlobalAssignOffsets(s, f, gaussianCount), "global assignment offsets");
-    GSM_CUDA(launchGlobalTileScatter(s, f, gaussianCount), "global tile scatter");
     {
         const SortScratchLayout L = sortScratchLayout(f.maxAssignments, 32, 4);
         char* scratch = r->globalSortScratch;
-        GSM_CUDA(cudaMemsetAsync(scratch, 0, L.oK1, s), "global sort state memset");
+        GSM_CUDA(cudaMemsetAsync(scratch, 0, L.oK1, s), "global sort state memset");   // histograms, status words, tickets
+        // the scatter writes the keys and counts their digits: no histogram kernel in front of the sort
+        GSM_CUDA(launchGlobalTileScatter(s, f, gaussianCount, (uint32_t*)(scratch + L.oHist)), "global tile scatter");
         SortPlan p;
         p.k0 = f.sortKeys; p.k1 = scratch + L.oK1; p.v0 = (uint32_t*)f.sortedIndices; p.v1 = (uint32_t*)(scratch + L.oV1);
         p.countPtr = &f.header->totalAssignments; p.countCap = f.maxAssignments;
         p.hist = (uint32_t*)(scratch + L.oHist); p.status = (uint32_t*)(scratch + L.oStatus); p.gstatus = (uint32_t*)(scratch + L.oGStatus);
         p.tickets = (uint32_t*)(scratch + L.oTickets);
-        p.tilesCap = L.tiles; p.keyBits = 32; p.numPasses = 4; p.numSMs = r->numSMs; p.histogramReady = false; p.largeTiles = L.large;
+        p.tilesCap = L.tiles; p.keyBits = 32; p.numPasses = 4; p.numSMs = r->numSMs; p.histogramReady = true; p.largeTiles = L.large;
         GSM_CUDA(launchSort(s, p), "global sort");   // RadixSortEncoder.swift:52-63 sorts 3 or 4 bytes: the same order
     }
     GSM_CUDA(launchGlobalHeaders(s, f), "global tile headers");
-    GSM_CUDA(launchGlobalRender(s, f, width, height, r->cfg.maxWidth, r->cfg.maxHeight, (__half*)color, (__half*)depth), "global render");
+    GSM_CUDA(launchGlobalRender(s, f, width, height, r->cfg.maxWidth, r->cfg.maxHeight, (__half*)color, (__half*)depth, r->numSMs), "global render");
     return GSM_OK;
 }
 

@@ -109,6 +109,7 @@ __global__ void global_assign_totals_kernel(GlobalFrame f, uint32_t numBlocks) {
     f.header->overflow = overflow;
     f.header->paddedCount = ((total + kRadixAlignment - 1u) / kRadixAlignment) * kRadixAlignment;
     f.header->activeTileCount = 0u;
+    *f.renderTicket = 0u;
 }
 
 // buildHeadersFromSortedKernel (GS.metal:304-363)

@@ -212,16 +212,18 @@ struct GlobalFrame {
     GSMGaussianHeader* tileHeaders;
     uint32_t* activeTiles;
     GlobalHeader* header;
+    BlendSplat* blendSplats;        // the render's 32-byte record per Gaussian (conic and colours as halfs), written by the tile count
+    uint32_t* renderTicket;         // tile ticket of the persistent render kernel, zeroed by the totals kernel
     uint32_t capGaussians, maxAssignments, tileW, tileH, tilesX, tilesY;
 };
 cudaError_t launchGlobalProject(cudaStream_t s, bool halfInput, const void* g, const void* h, const MonoCam& cam, const GlobalFrame& f);
 cudaError_t launchGlobalCompact(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);        // flags -> visibleIndices, visibleCount
 cudaError_t launchGlobalTileCount(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);
 cudaError_t launchGlobalAssignOffsets(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);  // counts -> offsets, header totals
-cudaError_t launchGlobalTileScatter(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount);
+cudaError_t launchGlobalTileScatter(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount, uint32_t* sortHist);  // also accumulates the sort's 4 x 256 digit histograms (zeroed by the caller)
 cudaError_t launchGlobalHeaders(cudaStream_t s, const GlobalFrame& f);
 cudaError_t launchGlobalRender(cudaStream_t s, const GlobalFrame& f, uint32_t width, uint32_t height, uint32_t maxWidth, uint32_t maxHeight,
-                               __half* color, __half* depth);
+                               __half* color, __half* depth, int numSMs);
 
 // math probes (probe.cu)
 cudaError_t launchProbe(cudaStream_t s, int op, const void* a, const void* b, void* out, uint32_t n);

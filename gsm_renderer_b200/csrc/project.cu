@@ -949,7 +949,7 @@ __device__ __forceinline__ bool globalIntersectsTile(int minX, int minY, int max
 // counts the tiles of visible Gaussian i, EMIT true stores key [tile:16][half depth ^ 0x8000:16] and the Gaussian's index from
 // `writePos` on, bounded by maxAssignments per store. Returns the count.
 template <bool EMIT>
-__device__ __forceinline__ uint32_t globalWalkTiles(const GlobalFrame& f, uint32_t g, uint32_t writePos) {
+__device__ __forceinline__ uint32_t globalWalkTiles(const GlobalFrame& f, uint32_t g, uint32_t writePos, uint32_t* sHist = nullptr) {
     const int4 rect = f.bounds[g];
     if (rect.x > rect.y || rect.z > rect.w) return 0u;
     const uint4 rd = f.renderData[g];
@@ -961,6 +961,21 @@ __device__ __forceinline__ uint32_t globalWalkTiles(const GlobalFrame& f, uint32
     float A, B, C;
     conicFromThetaSigmasF(theta, __half2float(__ushort_as_half((unsigned short)(rd.y >> 16))),
                           __half2float(__ushort_as_half((unsigned short)(rd.z & 0xFFFFu))), A, B, C);
+    if (!EMIT) {
+        // the render's record (globalRender, GlobalShaders.metal:1036-1187: conic from the quantised theta / sigmas, opacity and
+        // colour bytes over 255, all rounded to half): a function of the Gaussian alone, so it is computed here once instead of
+        // once per (tile, Gaussian) in the render
+        BlendSplat bs;
+        bs.mean = *reinterpret_cast<const __half2*>(&rd.x);
+        bs.cxx_cyy = __floats2half2_rn(A, C);
+        bs.cxy2_op = __halves2half2(__float2half_rn(2.0f * B), u8_over_255h((uint8_t)(rd.w >> 24)));
+        bs.rg = __halves2half2(u8_over_255h((uint8_t)(rd.w & 0xFFu)), u8_over_255h((uint8_t)((rd.w >> 8) & 0xFFu)));
+        bs.b_depth = __halves2half2(u8_over_255h((uint8_t)((rd.w >> 16) & 0xFFu)), __ushort_as_half((unsigned short)(rd.z >> 16)));
+        bs.valid = 1u; bs._pad[0] = 0u; bs._pad[1] = 0u;
+        uint4* d = reinterpret_cast<uint4*>(f.blendSplats + g);
+        d[0] = *reinterpret_cast<uint4*>(&bs);
+        d[1] = *(reinterpret_cast<uint4*>(&bs) + 1);
+    }
     const float LN2 = 0.693147180559945f;
     const float power = LN2 * 8.0f + LN2 * (dlog(dmax(alpha, 1e-6f)) * 1.44269504088896341f);
     const uint32_t depthBits = ((rd.z >> 16) ^ 0x8000u) & 0xFFFFu;
@@ -971,8 +986,13 @@ __device__ __forceinline__ uint32_t globalWalkTiles(const GlobalFrame& f, uint32
             if (globalIntersectsTile(px0, py0, px0 + (int)f.tileW - 1, py0 + (int)f.tileH - 1, cx, cy, A, B, C, power)) {
                 if (!EMIT) n++;
                 else if (writePos < f.maxAssignments) {
-                    f.sortKeys[writePos] = ((uint32_t)(ty * (int)f.tilesX + tx) << 16) | depthBits;
+                    const uint32_t key = ((uint32_t)(ty * (int)f.tilesX + tx) << 16) | depthBits;
+                    f.sortKeys[writePos] = key;
                     f.sortedIndices[writePos] = (int32_t)g;
+                    if (sHist) {   // the sort's four digit histograms, of exactly the keys that are stored
+#pragma unroll
+                        for (uint32_t p = 0; p < 4u; ++p) atomicAdd(&sHist[p * 256u + ((key >> (8u * p)) & 0xFFu)], 1u);
+                    }
                     writePos++;
                     n++;
                 }
@@ -985,9 +1005,17 @@ __global__ void __launch_bounds__(256) global_tile_count_kernel(GlobalFrame f) {
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     if (i < f.capGaussians) f.counts[i] = i < f.header->visibleCount ? globalWalkTiles<false>(f, f.visibleIndices[i], 0u) : 0u;
 }
-__global__ void __launch_bounds__(256) global_tile_scatter_kernel(GlobalFrame f) {
+__global__ void __launch_bounds__(256) global_tile_scatter_kernel(GlobalFrame f, uint32_t* __restrict__ sortHist) {
+    __shared__ uint32_t s_hist[4 * 256];
+    for (int k = threadIdx.x; k < 4 * 256; k += 256) s_hist[k] = 0u;
+    __syncthreads();
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i < f.header->visibleCount) globalWalkTiles<true>(f, f.visibleIndices[i], f.offsets[i]);
+    if (i < f.header->visibleCount) globalWalkTiles<true>(f, f.visibleIndices[i], f.offsets[i], s_hist);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * 256; k += 256) {
+        const uint32_t v = s_hist[k];
+        if (v) atomicAdd(&sortHist[k], v);
+    }
 }
 
 // ---------------------------------------------------------------- launchers
@@ -1043,8 +1071,8 @@ cudaError_t launchGlobalTileCount(cudaStream_t s, const GlobalFrame& f, uint32_t
     global_tile_count_kernel<<<(gaussianCount + 255u) / 256u, 256, 0, s>>>(f);
     return cudaGetLastError();
 }
-cudaError_t launchGlobalTileScatter(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount) {
-    global_tile_scatter_kernel<<<(gaussianCount + 255u) / 256u, 256, 0, s>>>(f);
+cudaError_t launchGlobalTileScatter(cudaStream_t s, const GlobalFrame& f, uint32_t gaussianCount, uint32_t* sortHist) {
+    global_tile_scatter_kernel<<<(gaussianCount + 255u) / 256u, 256, 0, s>>>(f, sortHist);
     return cudaGetLastError();
 }
 }  // namespace gsm
