@@ -1261,7 +1261,7 @@ static gsm_status ensureGlobalResources(gsm_renderer* r) {
     const size_t oKeys = take((size_t)A * 4), oIdx = take((size_t)A * 4);
     const size_t oHeaders = take((size_t)T * 8), oActive = take((size_t)T * 4), oHeader = take(sizeof(GlobalHeader));
     const size_t oSort = take(L.total);
-    const size_t oBlend = take((size_t)G * sizeof(BlendSplat)), oTicket = take(256);
+    const size_t oBlend = take((size_t)G * sizeof(BlendSplat)), oTicket = take(256), oMask = take((size_t)G * 8);
     cudaError_t e = cudaMalloc((void**)&r->globalArena, off);
     if (e != cudaSuccess) { r->globalArena = nullptr; return fail(GSM_ERR_FAILED_TO_ALLOCATE_BUFFER, "GlobalRenderer arena", e); }
     e = cudaMemset(r->globalArena, 0, off);
@@ -1273,7 +1273,7 @@ static gsm_status ensureGlobalResources(gsm_renderer* r) {
     f.offsets = (uint32_t*)(a + oOffsets); f.blockSums = (uint32_t*)(a + oBlockSums); f.sortKeys = (uint32_t*)(a + oKeys);
     f.sortedIndices = (int32_t*)(a + oIdx); f.tileHeaders = (GSMGaussianHeader*)(a + oHeaders); f.activeTiles = (uint32_t*)(a + oActive);
     f.header = (GlobalHeader*)(a + oHeader);
-    f.blendSplats = (BlendSplat*)(a + oBlend); f.renderTicket = (uint32_t*)(a + oTicket);
+    f.blendSplats = (BlendSplat*)(a + oBlend); f.renderTicket = (uint32_t*)(a + oTicket); f.hitMask = (uint2*)(a + oMask);
     f.capGaussians = G; f.maxAssignments = A; f.tileW = tileW; f.tileH = tileH; f.tilesX = tilesX; f.tilesY = tilesY;
     r->globalSortScratch = a + oSort;
     return GSM_OK;

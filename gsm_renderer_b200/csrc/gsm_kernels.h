@@ -213,6 +213,7 @@ struct GlobalFrame {
     uint32_t* activeTiles;
     GlobalHeader* header;
     BlendSplat* blendSplats;        // the render's 32-byte record per Gaussian (conic and colours as halfs), written by the tile count
+    uint2* hitMask;                 // per Gaussian: the tiles of an AABB of <= 64 tiles that pass the ellipse test (count pass -> scatter pass)
     uint32_t* renderTicket;         // tile ticket of the persistent render kernel, zeroed by the totals kernel
     uint32_t capGaussians, maxAssignments, tileW, tileH, tilesX, tilesY;
 };

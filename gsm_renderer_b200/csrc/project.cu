@@ -979,13 +979,40 @@ __device__ __forceinline__ uint32_t globalWalkTiles(const GlobalFrame& f, uint32
     const float LN2 = 0.693147180559945f;
     const float power = LN2 * 8.0f + LN2 * (dlog(dmax(alpha, 1e-6f)) * 1.44269504088896341f);
     const uint32_t depthBits = ((rd.z >> 16) ^ 0x8000u) & 0xFFFFu;
+    // AABBs of at most 64 tiles (almost all): the count pass leaves a 64-bit hit mask, bit k = tile k of the box in row-major order,
+    // and the scatter pass replays it instead of running the ellipse test a second time (as the DepthFirst expansion does)
+    const int bw = rect.y - rect.x + 1, bh = rect.w - rect.z + 1;
+    const bool masked = bw * bh <= 64;
     uint32_t n = 0u;
+    if (EMIT && masked) {
+        const uint2 m = f.hitMask[g];
+        unsigned long long bits = ((unsigned long long)m.y << 32) | m.x;
+        while (bits) {
+            const int k = __ffsll((long long)bits) - 1;
+            bits &= bits - 1ull;
+            if (writePos >= f.maxAssignments) break;   // every later store would be dropped too
+            const int ty = rect.z + k / bw, tx = rect.x + k % bw;
+            const uint32_t key = ((uint32_t)(ty * (int)f.tilesX + tx) << 16) | depthBits;
+            f.sortKeys[writePos] = key;
+            f.sortedIndices[writePos] = (int32_t)g;
+            if (sHist) {
+#pragma unroll
+                for (uint32_t p = 0; p < 4u; ++p) atomicAdd(&sHist[p * 256u + ((key >> (8u * p)) & 0xFFu)], 1u);
+            }
+            writePos++;
+            n++;
+        }
+        return n;
+    }
+    unsigned long long mask = 0ull;
     for (int ty = rect.z; ty <= rect.w; ++ty)
         for (int tx = rect.x; tx <= rect.y; ++tx) {
             const int px0 = tx * (int)f.tileW, py0 = ty * (int)f.tileH;
             if (globalIntersectsTile(px0, py0, px0 + (int)f.tileW - 1, py0 + (int)f.tileH - 1, cx, cy, A, B, C, power)) {
-                if (!EMIT) n++;
-                else if (writePos < f.maxAssignments) {
+                if (!EMIT) {
+                    n++;
+                    if (masked) mask |= 1ull << ((ty - rect.z) * bw + (tx - rect.x));
+                } else if (writePos < f.maxAssignments) {
                     const uint32_t key = ((uint32_t)(ty * (int)f.tilesX + tx) << 16) | depthBits;
                     f.sortKeys[writePos] = key;
                     f.sortedIndices[writePos] = (int32_t)g;
@@ -998,6 +1025,7 @@ __device__ __forceinline__ uint32_t globalWalkTiles(const GlobalFrame& f, uint32
                 }
             }
         }
+    if (!EMIT && masked) f.hitMask[g] = make_uint2((uint32_t)mask, (uint32_t)(mask >> 32));
     return n;
 }
 
