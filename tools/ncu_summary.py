@@ -56,7 +56,7 @@ def stage_of(name):
         return "depthSort"
     if "tile_chunk_count" in name or "tile_chunk_place" in name:
         return "tileSort"
-    if "onesweep_pass_kernel<unsigned short" in name:
+    if "onesweep_pass_kernel<unsigned short" in name or "onesweep_pair_kernel" in name:
         return "tileSort"
     if "create_instances" in name:
         return "expand"

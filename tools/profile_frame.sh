@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-fi
 KPF=${KPF:-10}
 SKIP=$((3 * KPF))
 N=$(grep -c "project_cull_mono_kernel" $OUT/${TAG}_launches.csv)
-ncu --set full --import-source on --clock-control none -k regex:"project_cull|compact_visible|onesweep_pass|bucket_rank|bucket_scatter|bucket_local_sort|create_instances|tile_chunk|tile_lower_bounds|blend_mono" \
+ncu --set full --import-source on --clock-control none -k regex:"project_cull|compact_visible|onesweep_pass|onesweep_pair|bucket_rank|bucket_scatter|bucket_local_sort|create_instances|tile_chunk|tile_lower_bounds|blend_mono" \
     --launch-skip $SKIP -c $KPF -o $OUT/${TAG}_frame $BENCH > $OUT/${TAG}_ncu_full.log 2>&1
 echo "launch list rows: $N, skipped $SKIP"
 ls -la $OUT/${TAG}_frame.ncu-rep
