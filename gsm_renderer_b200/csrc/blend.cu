@@ -95,7 +95,24 @@ __device__ __forceinline__ void storePixelRow(__half* color, __half* depth, uint
                                               __half2 r, __half2 g, __half2 b, __half2 a, __half2 d, uint32_t pitch = 0u) {
     if (y >= height || x >= width) return;   // `width` x `height` bound the stores; rows are `pitch` pixels apart (0 = width)
     const size_t o = (size_t)y * (pitch ? pitch : width) + x;
-    uint2 v;  // 8-byte pixel stores: always aligned, and 8 lanes x 2 pixels still cover one 128-byte line per row
+    // the thread's two pixels of a row are 16 contiguous bytes of colour and 4 of depth: one store each when the pair is whole and
+    // aligned (x is even, so an even row pitch is enough) -- half the store instructions, and whole 128-byte lines per 8 lanes when the
+    // target is a peer's memory (strip-sharded frames write the image owner's buffer over NVLink); else 8- and 2-byte stores
+    const uint32_t rowPitch = pitch ? pitch : width;
+    if (x + 1 < width && (rowPitch & 1u) == 0u && ((reinterpret_cast<uintptr_t>(color) & 15u) == 0u)) {
+        uint4 v;
+        v.x = h2bits(__halves2half2(__low2half(r), __low2half(g)));
+        v.y = h2bits(__halves2half2(__low2half(b), __low2half(a)));
+        v.z = h2bits(__halves2half2(__high2half(r), __high2half(g)));
+        v.w = h2bits(__halves2half2(__high2half(b), __high2half(a)));
+        *reinterpret_cast<uint4*>(color + 4 * o) = v;
+        if (depth) {
+            if ((reinterpret_cast<uintptr_t>(depth) & 3u) == 0u) *reinterpret_cast<__half2*>(depth + o) = d;
+            else { depth[o] = __low2half(d); depth[o + 1] = __high2half(d); }
+        }
+        return;
+    }
+    uint2 v;  // 8-byte pixel stores: always aligned
     v.x = h2bits(__halves2half2(__low2half(r), __low2half(g)));
     v.y = h2bits(__halves2half2(__low2half(b), __low2half(a)));
     *reinterpret_cast<uint2*>(color + 4 * o) = v;
