@@ -295,6 +295,28 @@ def e2e_sharded_upload(torch, dist, dev, rank, world, rs, pg, ph, N, K, cam, W, 
     return time.perf_counter() - t0, int((hi - lo) * (rec_bytes + sh_bytes))
 
 
+def bind_near_gpu(torch, local):
+    """Pin this rank's process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated, so that the
+    e2e path's staging memory is first touched on the GPU's NUMA node. Returns (note, previous affinity); any
+    failure leaves the affinity alone."""
+    prev = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        h = nv.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        want = near & prev if prev is not None else set()
+        if want and want != prev:
+            os.sched_setaffinity(0, want)
+            return f"bound to {len(want)} of {len(prev)} CPUs local to GPU {bus}", prev
+        return f"all {len(prev) if prev else 0} CPUs are local to GPU {bus} (or no overlap): not bound", prev
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})", prev
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -324,6 +346,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity_note, prev_affinity = bind_near_gpu(torch, local)
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
@@ -565,6 +588,8 @@ def main():
     # ---- CPU baseline (bounded sample: whole frames of the same workload on this box's cores)
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)   # the CPU arm runs on every core the box gives this job
         run, fr, ob = oracle_frame_runner(g, h, spec)
         run()
         n_s, t_acc = 0, 0.0
@@ -582,6 +607,7 @@ def main():
         "config": base_config(spec, V, I),
         "run": {"activeTiles": active, "tiles": T, "maxInstancesPerTile": max_per_tile, "overflow": hd.overflow,
                 "parallelism": f"views sharded over {world} GPU(s), one C2 view per GPU per step, no collective",
+                "cpu_affinity": affinity_note,
                 "l2": "inputs+arena > L2 and " + ("no flush" if args.no_flush else "L2 flushed between steps (256 MiB write, untimed)"),
                 "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                 "warmup_extra_steps": extra},

@@ -570,6 +570,23 @@ __global__ void __launch_bounds__(kBlendThreads) blend_stereo_kernel(const uint3
             __half* r = dstSideBySide + 4 * ((size_t)dy * sbsWidth + width + baseX);
             const __half2 Lr = row ? qL.r1 : qL.r0, Lg = row ? qL.g1 : qL.g0, Lb = row ? qL.b1 : qL.b0;
             const __half2 Rr = row ? qR.r1 : qR.r0, Rg = row ? qR.g1 : qR.g0, Rb = row ? qR.b1 : qR.b0;
+            // both pixels of the pair as one 16-byte store when the pair is whole and aligned (baseX is even: an even eye width and a
+            // 16-byte aligned target are enough) -- what a peer's memory wants (one eye per GPU writes rank 0's target over NVLink)
+            const bool wide = two && (width & 1u) == 0u && (reinterpret_cast<uintptr_t>(dstSideBySide) & 15u) == 0u;
+            if (wide) {
+                uint4 w;
+                if (doL) {
+                    w.x = h2bits(__halves2half2(__low2half(Lr), __low2half(Lg))); w.y = h2bits(__halves2half2(__low2half(Lb), __low2half(aL)));
+                    w.z = h2bits(__halves2half2(__high2half(Lr), __high2half(Lg))); w.w = h2bits(__halves2half2(__high2half(Lb), __high2half(aL)));
+                    *reinterpret_cast<uint4*>(l) = w;
+                }
+                if (doR) {
+                    w.x = h2bits(__halves2half2(__low2half(Rr), __low2half(Rg))); w.y = h2bits(__halves2half2(__low2half(Rb), __low2half(aR)));
+                    w.z = h2bits(__halves2half2(__high2half(Rr), __high2half(Rg))); w.w = h2bits(__halves2half2(__high2half(Rb), __high2half(aR)));
+                    *reinterpret_cast<uint4*>(r) = w;
+                }
+                continue;
+            }
             uint2 v;
             if (doL) {
                 v.x = h2bits(__halves2half2(__low2half(Lr), __low2half(Lg))); v.y = h2bits(__halves2half2(__low2half(Lb), __low2half(aL)));
