@@ -224,6 +224,52 @@ private:
     gsm_renderer* h_ = nullptr;
 };
 
+// ---- GlobalRenderer (Sources/Renderer/GlobalRenderer/GlobalRenderer.swift:72-372): the reference's second GaussianRenderer,
+// same RendererConfig and limits, 32 x 16 tiles, one [tile:16][half depth:16] sort. render() binds to gsm_render_global;
+// renderStereo is a fatalError in the reference (:249-255) and throws here.
+class GlobalRenderer {
+public:
+    explicit GlobalRenderer(int device = -1, RendererConfig config = RendererConfig()) {
+        gsm_config c;
+        gsm_config_default(&c);
+        c.maxGaussians = (uint32_t)config.maxGaussians;
+        c.maxWidth = (uint32_t)config.maxWidth;
+        c.maxHeight = (uint32_t)config.maxHeight;
+        c.precision = (uint32_t)config.precision;
+        c.gaussianColorSpace = (uint32_t)config.gaussianColorSpace;
+        c.device = device;
+        check(gsm_renderer_create(&c, &h_));
+    }
+    ~GlobalRenderer() { gsm_renderer_destroy(h_); }
+    GlobalRenderer(const GlobalRenderer&) = delete;
+    GlobalRenderer& operator=(const GlobalRenderer&) = delete;
+
+    void render(void* commandBuffer, void* colorTexture, void* depthTexture, const GaussianInput& input,
+                const CameraParams& camera, int width, int height) {
+        gsm_camera c = camera.native();
+        check(gsm_render_global(h_, commandBuffer, colorTexture, depthTexture, input.gaussians, input.harmonics,
+                                (uint32_t)input.gaussianCount, (uint32_t)input.shComponents, &c, (uint32_t)width, (uint32_t)height));
+    }
+    void renderStereo(void*, const StereoRenderTarget&, const GaussianInput&, const StereoCameraParams&, int, int) {
+        throw RendererError(GSM_ERR_INVALID_ARGUMENT, "GlobalRenderer does not support stereo rendering. Use DepthFirstRenderer instead.");
+    }
+    gsm_global_header debugReadHeader() {
+        gsm_global_header h{};
+        check(gsm_global_debug_read(h_, nullptr, GSM_GDBG_HEADER, &h, 0, 1));
+        return h;
+    }
+    uint32_t debugReadTotalAssignments() { return debugReadHeader().totalAssignments; }   // GlobalRenderer.swift:200-203
+    std::vector<uint32_t> debugReadSortedKeys(size_t n) {
+        std::vector<uint32_t> v(n);
+        if (n) check(gsm_global_debug_read(h_, nullptr, GSM_GDBG_SORTED_KEYS, v.data(), 0, n));
+        return v;
+    }
+    gsm_renderer* handle() const { return h_; }
+
+private:
+    gsm_renderer* h_ = nullptr;
+};
+
 // ---- scene ingest (gsm_scene.h): PLYLoader.load(url:) + GaussianSceneBuilder (PLYLoader.swift:246-281, Scene.swift:73-190).
 // The caller supplies the file in host memory (mmap or read); the records are decoded on the device, straight into the
 // renderer's input layout. PLYLoaderError cases arrive as RendererError with the GSM_ERR_PLY_* status.

@@ -72,6 +72,25 @@ int main() {
         size_t nonBlack = 0;
         for (size_t i = 0; i < px.size(); i += 4) nonBlack += (px[i] | px[i + 1] | px[i + 2]) & 0x7FFF ? 1 : 0;
         std::printf("nonBlackPixels=%zu\n", nonBlack);
+        // the same scene through the reference's second renderer (GlobalRenderer.swift): 32 x 16 tiles, one sort of [tile | depth] keys
+        bool okGlobal = false;
+        {
+            gsm::GlobalRenderer global(-1, config);
+            global.render(queue, colorTexture, depthTexture, input, camera, width, height);
+            gsm::check(gsm_stream_synchronize(queue));
+            gsm_global_header gh = global.debugReadHeader();
+            std::vector<uint32_t> keys = global.debugReadSortedKeys(gh.totalAssignments);
+            bool sorted = true;
+            for (size_t i = 1; i < keys.size(); ++i) sorted = sorted && keys[i - 1] <= keys[i];
+            std::vector<uint16_t> gpx(size_t(width) * height * 4);
+            gsm::check(gsm_buffer_download(gpx.data(), colorTexture, gpx.size() * 2, queue));
+            size_t nb = 0;
+            for (size_t i = 0; i < gpx.size(); i += 4) nb += (gpx[i] | gpx[i + 1] | gpx[i + 2]) & 0x7FFF ? 1 : 0;
+            std::printf("global visible=%u assignments=%u overflow=%u activeTiles=%u sorted=%d nonBlackPixels=%zu\n", gh.visibleCount,
+                        gh.totalAssignments, gh.overflow, gh.activeTileCount, (int)sorted, nb);
+            okGlobal = gh.overflow == 0 && gh.visibleCount > 0 && gh.totalAssignments >= gh.visibleCount && sorted && nb > 0;
+        }
+        ok = ok && okGlobal;
         gsm_buffer_free(gaussianBuf); gsm_buffer_free(harmonicsBuf); gsm_buffer_free(colorTexture); gsm_buffer_free(depthTexture);
         gsm_stream_destroy(queue);
         std::printf(ok && nonBlack > 0 ? "PASS\n" : "FAIL\n");

@@ -32,3 +32,5 @@ def test_facade_pipeline_stages_scene_gpu():
     r = subprocess.run([EXE], capture_output=True, text=True)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
     assert "visible=872 instances=2656" in r.stdout  # the oracle's counters for this scene (tests/test_oracle_kats.py)
+    # the same scene through gsm::GlobalRenderer: the oracle's GlobalRenderer frame gives 872 visible, 2 347 assignments, 499 tiles
+    assert "global visible=872 assignments=2347 overflow=0 activeTiles=499 sorted=1" in r.stdout, r.stdout
