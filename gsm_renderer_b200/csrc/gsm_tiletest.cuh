@@ -107,6 +107,7 @@ __device__ __forceinline__ bool tileHit(const QuantSplat& q, int tx, int ty) {
 struct WarpTileWork {
     float meanX[32], meanY[32], ca[32], cb[32], cc[32], cutoff[32];
     int minTX[32], minTY[32], w[32];
+    float rcpW[32];                   // 1 / w, for rowOf()
     uint32_t prefix[32];
     uint32_t counter[32];
     uint32_t maskLo[32], maskHi[32];  // hit bits of the first 64 AABB tiles (row-major), see warpCountTiles
@@ -124,8 +125,17 @@ __device__ __forceinline__ uint32_t warpExclusiveScan(uint32_t v, uint32_t& tota
     return inc - v;
 }
 
+// k / w for k < 2^23 without the ~20-instruction integer division: the binary32 estimate k * (1 / w) is within k * 2^-23 < 1 / w
+// of the quotient, so its floor is exact unless the quotient is an integer the estimate falls just short of -- one fix-up.
+__device__ __forceinline__ uint32_t rowOf(uint32_t k, uint32_t w, float rcpW) {
+    uint32_t q = (uint32_t)__float2uint_rz(__fmul_rn(__uint2float_rn(k), rcpW));
+    if (k - q * w >= w) q++;
+    return q;
+}
+
 __device__ __forceinline__ void warpPublish(WarpTileWork& s, uint32_t excl, const QuantSplat& q, int minTX, int minTY, int w) {
     const unsigned lane = threadIdx.x & 31u;
+    s.rcpW[lane] = 1.0f / (float)(w > 0 ? w : 1);
     s.meanX[lane] = q.meanX; s.meanY[lane] = q.meanY;
     s.ca[lane] = q.ca; s.cb[lane] = q.cb; s.cc[lane] = q.cc; s.cutoff[lane] = q.d2Cutoff;
     s.minTX[lane] = minTX; s.minTY[lane] = minTY; s.w[lane] = w;
@@ -164,7 +174,7 @@ __device__ __forceinline__ uint32_t warpCountTiles(WarpTileWork& s, uint32_t n, 
             const uint32_t o = warpOwnerOf(s, j);
             const uint32_t k = j - s.prefix[o];
             const uint32_t ww = (uint32_t)s.w[o];
-            const uint32_t row = k / ww;
+            const uint32_t row = rowOf(k, ww, s.rcpW[o]);
             const int ty = s.minTY[o] + (int)row, tx = s.minTX[o] + (int)(k - row * ww);
             if (tileHitP(s.meanX[o], s.meanY[o], s.ca[o], s.cb[o], s.cc[o], s.cutoff[o], tx, ty)) {
                 if (k < 32u) atomicOr(&s.maskLo[o], 1u << k);
@@ -337,7 +347,7 @@ __device__ __forceinline__ void warpEmitTiles(WarpTileWork& s, uint32_t n, const
             o = warpOwnerOf(s, j);
             const uint32_t k = j - s.prefix[o];
             const uint32_t ww = (uint32_t)s.w[o];
-            const uint32_t row = k / ww;
+            const uint32_t row = rowOf(k, ww, s.rcpW[o]);
             const int ty = s.minTY[o] + (int)row, tx = s.minTX[o] + (int)(k - row * ww);
             hit = tileHitP(s.meanX[o], s.meanY[o], s.ca[o], s.cb[o], s.cc[o], s.cutoff[o], tx, ty);
             tileId = (uint32_t)(ty * (int)tilesX + tx);
