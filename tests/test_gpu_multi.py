@@ -74,6 +74,42 @@ def test_strip_sharded_frame_equals_single_gpu(world):
     r.close()
 
 
+def test_empty_strip_frame_after_a_full_one_shows_the_clear_colour():
+    """gsm_strip_render with recordCount == 0 launches nothing that writes the frame header; without clearing
+    it the sorts and the blend would run on the previous frame's counts. A strip that sees nothing (the camera turned away) must
+    show the clear colour -- alpha 1, everything else 0 -- and report zero visible Gaussians and instances."""
+    import torch
+    import tests.parity_util as pu
+    cl = syn.synthetic_cloud(30_000, 1, seed=21, scale_median=0.02)
+    precision, W, H = "float16", 1280, 720
+    g, h = pu.make_scene_inputs(cl, precision)
+    cam = pu.default_camera(W, H)
+    dev = torch.device("cuda:0")
+    r = _mk(cl, precision, W, H, cl.count)
+    tg = torch.from_numpy(g.view(np.uint8).reshape(-1)).to(dev)
+    th = torch.from_numpy(h.view(np.uint8).reshape(-1)).to(dev)
+    s = torch.cuda.current_stream()
+    scratch = torch.zeros(cl.count * mg.RECORD_BYTES, dtype=torch.uint8, device=dev)
+    n = r.stripProject(s, tg, th, 0, cl.count, cl.sh_components, cam, W, H, scratch)
+    assert n > 1000
+    out_c = torch.full((H, W, 4), 0x7E00, dtype=torch.int16, device=dev)
+    out_d = torch.full((H, W), 0x7E00, dtype=torch.int16, device=dev)
+    rows = (H + 15) // 16
+    r.stripRender(s, out_c, out_d, scratch, n, W, H, 0, rows)          # a full frame first
+    torch.cuda.synchronize()
+    assert r.debugReadHeader().visibleCount > 1000 and int((out_c[..., 0] != 0).sum()) > 0
+    out_c.fill_(0x7E00)
+    out_d.fill_(0x7E00)
+    r.stripRender(s, out_c, out_d, scratch, 0, W, H, 0, rows)          # then a frame without a single record
+    torch.cuda.synchronize()
+    hd = r.debugReadHeader()
+    assert hd.visibleCount == 0 and hd.totalInstances == 0
+    c = out_c.cpu().numpy().view(np.uint16)
+    assert np.all(c[..., :3] == 0) and np.all(c[..., 3] == 0x3C00)     # colour (0, 0, 0), alpha 1.0h on every pixel
+    assert np.all(out_d.cpu().numpy().view(np.uint16) == 0)
+    r.close()
+
+
 def test_stereo_eye_split_equals_joint():
     import torch
     import tests.parity_util as pu
