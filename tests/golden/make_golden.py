@@ -123,8 +123,40 @@ def reference_kats():
     }
 
 
+# ---- GlobalRenderer frames: digests of the oracle's GlobalRenderer restatement on the same scenes
+GLOBAL_SCENES = ("pipeline_stages_f32_640x480", "synthetic_8k_sh3_f16_1280x720", "synthetic_5k_sh1_f32_333x77")
+
+
+def global_frame_digests(header, bounds, visibleIndices, sortedKeys, sortedIndices, tileHeaders, activeTiles, color, depth):
+    V, A = header["visibleCount"], header["totalAssignments"]
+    return {"header": header, "bounds": sha(bounds), "visibleIndices": sha(visibleIndices[:V]), "sortedKeys": sha(sortedKeys[:A]),
+            "sortedIndices": sha(sortedIndices[:A]), "tileHeaders": sha(tileHeaders),
+            "activeTilesSorted": sha(np.sort(np.asarray(activeTiles).astype(np.uint32))), "color": sha(color), "depth": sha(depth)}
+
+
+def global_digests():
+    from oracle import binding as ob
+    ob.build()
+    out = {}
+    for name in GLOBAL_SCENES:
+        mk, prec, W, H, near, far, srgb, sh = SCENES[name]
+        cl = mk()
+        g, h = cl.pack(prec)
+        proj = syn.make_projection_matrix(W, H, near, far)
+        cam = ob.make_camera(np.eye(4), proj, (0, 0, 0), W, H, near, far, sh, cl.count, srgb)
+        fr = ob.OracleGlobalFrame(cl.count, W, H)
+        color, depth = fr.render(g, h, ob.F16 if prec == "float16" else ob.F32, cam, W, H)
+        info = fr.info
+        header = {k: int(getattr(info, k)) for k in ("visibleCount", "totalAssignments", "paddedCount", "overflow", "activeTileCount")}
+        active = np.nonzero(fr.tileHeaders[:, 1] > 0)[0]
+        out[name] = global_frame_digests(header, fr.bounds[:cl.count], fr.visibleIndices, fr.sortedKeys, fr.sortedIndices,
+                                         fr.tileHeaders, active, color, depth)
+    return out
+
+
 if __name__ == "__main__":
     json.dump(reference_kats(), open(os.path.join(HERE, "reference_kats.json"), "w"), indent=1, sort_keys=True)
     json.dump(oracle_digests(), open(os.path.join(HERE, "oracle_digests.json"), "w"), indent=1, sort_keys=True)
     json.dump(copy_digests(), open(os.path.join(HERE, "foveated_copy_digests.json"), "w"), indent=1, sort_keys=True)
+    json.dump(global_digests(), open(os.path.join(HERE, "global_digests.json"), "w"), indent=1, sort_keys=True)
     print("wrote", HERE)
